@@ -1,0 +1,170 @@
+/*
+ * oracle/me.c — restatement of the motion-search cost and scan semantics of rav1e
+ * src/me.rs (get_mv_range :339-362, get_fullpel_mv_rd :1386-1409, compute_mv_rd
+ * :1445-1461, full_search :1464-1509, get_mv_rate :1512-1523).
+ * TEST INFRASTRUCTURE ONLY (see oracle.h).
+ *
+ * `ILog::ilog` comes from v_frame 0.3.9 (off disk): bits - leading_zeros, 0 for x <= 0.
+ * No reference test pins it ("parity unpinned" for the rate term); SAD itself is pinned.
+ */
+#include "oracle.h"
+
+#include <limits.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define MI_SIZE 4          /* context/superblock_unit.rs:12 */
+#define MV_LOW (-(1 << 14)) /* context/mod.rs:130-132 */
+#define MV_UPP (1 << 14)
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+static inline uint32_t ilog_i16(int16_t v) { /* v_frame ILog::ilog for i16 */
+  if (v <= 0) return 0;
+  return 32 - (uint32_t)__builtin_clz((uint32_t)v);
+}
+
+/* me.rs:1516-1519 diff_to_rate */
+static inline uint32_t diff_to_rate(int16_t diff, int allow_hp) {
+  int16_t d = allow_hp ? diff : (int16_t)(diff >> 1); /* arithmetic shift on i16 */
+  int16_t a = (int16_t)(d < 0 ? -d : d);
+  return 2 * ilog_i16(a);
+}
+
+/* me.rs:1512-1523 */
+uint32_t orc_get_mv_rate(orc_mv a, orc_mv b, int allow_hp) {
+  return diff_to_rate((int16_t)(a.row - b.row), allow_hp) +
+         diff_to_rate((int16_t)(a.col - b.col), allow_hp);
+}
+
+/* me.rs:1455-1460 */
+uint64_t orc_mv_cost(uint32_t sad, orc_mv cand, orc_mv pmv0, orc_mv pmv1, uint32_t lambda,
+                     int allow_hp) {
+  uint32_t rate1 = orc_get_mv_rate(cand, pmv0, allow_hp);
+  uint32_t rate2 = orc_get_mv_rate(cand, pmv1, allow_hp);
+  uint32_t rate = rate1 < rate2 + 1 ? rate1 : rate2 + 1;
+  return 256 * (uint64_t)sad + (uint64_t)rate * (uint64_t)lambda;
+}
+
+/* me.rs:339-362 — bo in 4x4 block units, blk_w/h in pixels; result in 1/8 pel. */
+void orc_get_mv_range(int w_in_b, int h_in_b, int bo_x, int bo_y, int blk_w, int blk_h,
+                      int *mvx_min, int *mvx_max, int *mvy_min, int *mvy_max) {
+  int border_w = 128 + blk_w * 8;
+  int border_h = 128 + blk_h * 8;
+  int x_min = -bo_x * (8 * MI_SIZE) - border_w;
+  int x_max = ((w_in_b - bo_x) - (blk_w / MI_SIZE)) * (8 * MI_SIZE) + border_w;
+  int y_min = -bo_y * (8 * MI_SIZE) - border_h;
+  int y_max = ((h_in_b - bo_y) - (blk_h / MI_SIZE)) * (8 * MI_SIZE) + border_h;
+  *mvx_min = x_min > MV_LOW + 1 ? x_min : MV_LOW + 1;
+  *mvx_max = x_max < MV_UPP - 1 ? x_max : MV_UPP - 1;
+  *mvy_min = y_min > MV_LOW + 1 ? y_min : MV_LOW + 1;
+  *mvy_max = y_max < MV_UPP - 1 ? y_max : MV_UPP - 1;
+}
+
+static inline uint32_t dist_any(const void *org, ptrdiff_t os, const void *ref, ptrdiff_t rs,
+                                int bpp, int w, int h, int use_satd) {
+  if (bpp == 1)
+    return use_satd ? orc_get_satd_u8((const uint8_t *)org, os, (const uint8_t *)ref, rs, w, h)
+                    : orc_get_sad_u8((const uint8_t *)org, os, (const uint8_t *)ref, rs, w, h);
+  return use_satd ? orc_get_satd_u16((const uint16_t *)org, os, (const uint16_t *)ref, rs, w, h)
+                  : orc_get_sad_u16((const uint16_t *)org, os, (const uint16_t *)ref, rs, w, h);
+}
+
+static inline const void *px_at(const void *p0, ptrdiff_t stride, int bpp, int x, int y) {
+  return (const uint8_t *)p0 + ((ptrdiff_t)y * stride + x) * bpp;
+}
+
+/* me.rs:1464-1509.  vert_windows(h).step_by(step) x horz_windows(w).step_by(step): rows
+ * y_lo, y_lo+step, ... <= y_hi outer; columns x_lo ... <= x_hi inner; strict `<` keeps
+ * the first minimum in scan order. */
+orc_me_result orc_full_search(const void *org, ptrdiff_t org_stride, const void *ref0,
+                              ptrdiff_t ref_stride, int bpp, int x_lo, int x_hi, int y_lo,
+                              int y_hi, int w, int h, int po_x, int po_y, int step,
+                              uint32_t lambda, orc_mv pmv0, orc_mv pmv1, int allow_hp) {
+  orc_me_result best;
+  best.cost = UINT64_MAX;
+  best.sad = UINT32_MAX;
+  best.mv.row = 0;
+  best.mv.col = 0;
+  for (int y = y_lo; y <= y_hi; y += step) {
+    for (int x = x_lo; x <= x_hi; x += step) {
+      orc_mv mv;
+      mv.row = (int16_t)(8 * (int16_t)((int16_t)y - (int16_t)po_y));
+      mv.col = (int16_t)(8 * (int16_t)((int16_t)x - (int16_t)po_x));
+      uint32_t sad = dist_any(org, org_stride, px_at(ref0, ref_stride, bpp, x, y), ref_stride,
+                              bpp, w, h, 0);
+      uint64_t cost = orc_mv_cost(sad, mv, pmv0, pmv1, lambda, allow_hp);
+      if (cost < best.cost) {
+        best.cost = cost;
+        best.sad = sad;
+        best.mv = mv;
+      }
+    }
+  }
+  return best;
+}
+
+/* me.rs:1386-1409 applied to a list.  The block offset bo = (x/4, y/4). */
+void orc_fullpel_candidates(const void *cur0, ptrdiff_t cur_stride, const void *ref0,
+                            ptrdiff_t ref_stride, int bpp, int frame_w_in_b, int frame_h_in_b,
+                            const orc_block *blocks, const orc_cand *cands, size_t n, int w,
+                            int h, int use_satd, uint32_t lambda, const orc_mv *pmv,
+                            int allow_hp, uint32_t *out_sad, uint64_t *out_cost, int threads) {
+  (void)threads;
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : orc_num_threads())
+  for (ptrdiff_t i = 0; i < (ptrdiff_t)n; i++) {
+    const orc_cand c = cands[i];
+    const orc_block b = blocks[c.block];
+    int mvx_min, mvx_max, mvy_min, mvy_max;
+    orc_get_mv_range(frame_w_in_b, frame_h_in_b, b.x / MI_SIZE, b.y / MI_SIZE, w, h, &mvx_min,
+                     &mvx_max, &mvy_min, &mvy_max);
+    uint32_t sad = UINT32_MAX;
+    uint64_t cost = UINT64_MAX;
+    if (!(c.mv_col < mvx_min || c.mv_col > mvx_max || c.mv_row < mvy_min || c.mv_row > mvy_max)) {
+      /* Rust `/` on i16 truncates toward zero, as C does. */
+      int rx = b.x + c.mv_col / 8, ry = b.y + c.mv_row / 8;
+      sad = dist_any(px_at(cur0, cur_stride, bpp, b.x, b.y), cur_stride,
+                     px_at(ref0, ref_stride, bpp, rx, ry), ref_stride, bpp, w, h, use_satd);
+      orc_mv z = {0, 0};
+      orc_mv cm = {c.mv_row, c.mv_col};
+      cost = orc_mv_cost(sad, cm, pmv ? pmv[2 * c.block] : z, pmv ? pmv[2 * c.block + 1] : z,
+                         lambda, allow_hp);
+    }
+    if (out_sad) out_sad[i] = sad;
+    if (out_cost) out_cost[i] = cost;
+  }
+}
+
+/* me.rs:822-846 (ssdec = 0 form): window = po +- range clamped to the mv range, step. */
+void orc_full_search_blocks(const void *cur0, ptrdiff_t cur_stride, const void *ref0,
+                            ptrdiff_t ref_stride, int bpp, int frame_w_in_b, int frame_h_in_b,
+                            const orc_block *blocks, size_t nblocks, int w, int h, int range_x,
+                            int range_y, int step, uint32_t lambda, int allow_hp,
+                            orc_me_result *out, int threads) {
+  (void)threads;
+#pragma omp parallel for schedule(dynamic, 4) num_threads(threads > 0 ? threads : orc_num_threads())
+  for (ptrdiff_t i = 0; i < (ptrdiff_t)nblocks; i++) {
+    const orc_block b = blocks[i];
+    int mvx_min, mvx_max, mvy_min, mvy_max;
+    orc_get_mv_range(frame_w_in_b, frame_h_in_b, b.x / MI_SIZE, b.y / MI_SIZE, w, h, &mvx_min,
+                     &mvx_max, &mvy_min, &mvy_max);
+    int lo, hi;
+    lo = -range_x > mvx_min / 8 ? -range_x : mvx_min / 8;
+    hi = range_x < mvx_max / 8 ? range_x : mvx_max / 8;
+    int x_lo = b.x + lo, x_hi = b.x + hi;
+    lo = -range_y > mvy_min / 8 ? -range_y : mvy_min / 8;
+    hi = range_y < mvy_max / 8 ? range_y : mvy_max / 8;
+    int y_lo = b.y + lo, y_hi = b.y + hi;
+    orc_mv z = {0, 0};
+    out[i] = orc_full_search(px_at(cur0, cur_stride, bpp, b.x, b.y), cur_stride, ref0, ref_stride,
+                             bpp, x_lo, x_hi, y_lo, y_hi, w, h, b.x, b.y, step, lambda, z, z,
+                             allow_hp);
+  }
+}

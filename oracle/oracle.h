@@ -1,0 +1,137 @@
+/*
+ * oracle.h — CPU restatement of rav1e's RDO inner-loop kernels (TEST INFRASTRUCTURE ONLY).
+ *
+ * This library is the checker for the CUDA product path in rav1e_b200/csrc.  Only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+ * load it.  Nothing under rav1e_b200/ links, imports or calls it.
+ *
+ * Every function cites the reference file:line (relative to xiph/rav1e @ 564ae3b) that it
+ * restates.  Arithmetic that lives in the off-disk crate v_frame 0.3.9 (Cargo.lock:2075)
+ * is restated from its published semantics: msb(x)=31-clz(x), round_shift(v,b)=
+ * (v+(1<<b>>1))>>b, ILog::ilog(x)=bits-clz(x) (0 for x<=0), clamp, `as` casts wrap.
+ *
+ * Parity pinning status (see DESIGN.md "Oracle"):
+ *   SAD / SATD                : pinned by src/dist.rs:418-441, :477-500 (22 sizes, u8+u16)
+ *   intra 4x4 predictors      : pinned by src/predict.rs:1514-1693
+ *   cdef first_max_element    : pinned by src/cdef.rs:304-309
+ *   fwd txfm / mc / cdef filt : no stored vectors in the reference (only asm==rust random
+ *                               tests that need rustc) -> "parity unpinned" for those, with
+ *                               independent cross-checks documented per module.
+ *
+ * All strides are in ELEMENTS (pixels), pointers address pixel (0,0) of a region; planes
+ * may be addressed at negative coordinates when the caller padded them.
+ */
+#ifndef RAV1E_B200_ORACLE_H
+#define RAV1E_B200_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ dist.rs */
+uint32_t orc_get_sad_u8(const uint8_t *org, ptrdiff_t org_stride, const uint8_t *ref,
+                        ptrdiff_t ref_stride, int w, int h);
+uint32_t orc_get_sad_u16(const uint16_t *org, ptrdiff_t org_stride, const uint16_t *ref,
+                         ptrdiff_t ref_stride, int w, int h);
+uint32_t orc_get_satd_u8(const uint8_t *org, ptrdiff_t org_stride, const uint8_t *ref,
+                         ptrdiff_t ref_stride, int w, int h);
+uint32_t orc_get_satd_u16(const uint16_t *org, ptrdiff_t org_stride, const uint16_t *ref,
+                          ptrdiff_t ref_stride, int w, int h);
+
+/* -------------------------------------------------------------------- me.rs */
+typedef struct {
+  int16_t row, col; /* 1/8 pel, src/mc.rs:29-32 */
+} orc_mv;
+
+typedef struct {
+  uint64_t cost; /* 256*sad + rate*lambda; UINT64_MAX == empty (src/me.rs:128-146) */
+  uint32_t sad;
+  orc_mv mv;
+} orc_me_result;
+
+uint32_t orc_get_mv_rate(orc_mv a, orc_mv b, int allow_high_precision_mv);
+void orc_get_mv_range(int w_in_b, int h_in_b, int bo_x, int bo_y, int blk_w, int blk_h,
+                      int *mvx_min, int *mvx_max, int *mvy_min, int *mvy_max);
+uint64_t orc_mv_cost(uint32_t sad, orc_mv cand, orc_mv pmv0, orc_mv pmv1, uint32_t lambda,
+                     int allow_high_precision_mv);
+
+/* me.rs:1464-1509 — exhaustive window scan, first-min argmin.  bpp = 1|2 bytes/pixel.
+ * org points at the block's pixel (0,0); ref0 at plane pixel (0,0); po = block position. */
+orc_me_result orc_full_search(const void *org, ptrdiff_t org_stride, const void *ref0,
+                              ptrdiff_t ref_stride, int bpp, int x_lo, int x_hi, int y_lo,
+                              int y_hi, int w, int h, int po_x, int po_y, int step,
+                              uint32_t lambda, orc_mv pmv0, orc_mv pmv1, int allow_hp);
+
+/* Batched forms used by the parity tests and the CPU baseline (OpenMP over units).
+ * Descriptors mirror include/b200rdo.h (b200_block / b200_cand) field for field. */
+typedef struct {
+  int16_t x, y; /* luma px of block top-left */
+} orc_block;
+typedef struct {
+  uint32_t block;      /* index into blocks[] */
+  int16_t mv_row, mv_col; /* 1/8 pel; fullpel offsets are mv/8 (trunc toward 0, me.rs:1402) */
+} orc_cand;
+
+/* me.rs:1386-1409 get_fullpel_mv_rd over a candidate list: out_sad[i] (UINT32_MAX when the
+ * mv is out of range), out_cost[i] (UINT64_MAX likewise); either may be NULL. */
+void orc_fullpel_candidates(const void *cur0, ptrdiff_t cur_stride, const void *ref0,
+                            ptrdiff_t ref_stride, int bpp, int frame_w_in_b, int frame_h_in_b,
+                            const orc_block *blocks, const orc_cand *cands, size_t n, int w,
+                            int h, int use_satd, uint32_t lambda, const orc_mv *pmv /*2 per block or NULL*/,
+                            int allow_hp, uint32_t *out_sad, uint64_t *out_cost, int threads);
+
+/* full_pixel_me's final stage (me.rs:822-846) for every block: window +-range, step. */
+void orc_full_search_blocks(const void *cur0, ptrdiff_t cur_stride, const void *ref0,
+                            ptrdiff_t ref_stride, int bpp, int frame_w_in_b, int frame_h_in_b,
+                            const orc_block *blocks, size_t nblocks, int w, int h, int range_x,
+                            int range_y, int step, uint32_t lambda, int allow_hp,
+                            orc_me_result *out, int threads);
+
+/* -------------------------------------------------------------- transform/ */
+/* forward.rs:71-161.  coeff_is_i32: 0 -> int16_t out (8-bit pixels), 1 -> int32_t out. */
+int orc_valid_av1_transform(int tx_size, int tx_type);
+void orc_forward_transform(const int16_t *input, void *output, size_t stride, int tx_size,
+                           int tx_type, int bd, int coeff_is_i32);
+void orc_forward_transform_batch(const int16_t *input, void *output, size_t nblocks, int tx_size,
+                                 int tx_type, int bd, int coeff_is_i32, int threads);
+int orc_tx_width(int tx_size);
+int orc_tx_height(int tx_size);
+
+/* ------------------------------------------------------------------- mc.rs */
+/* put_8tap mc.rs:250-353; prep_8tap :360-451; mc_avg :454-479.  mode_x/mode_y = FilterMode
+ * (0 REGULAR, 1 SMOOTH, 2 SHARP, 3 BILINEAR); col_frac/row_frac 0..15. */
+void orc_put_8tap(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride, int bpp,
+                  int w, int h, int col_frac, int row_frac, int mode_x, int mode_y, int bit_depth);
+void orc_prep_8tap(int16_t *tmp, const void *src, ptrdiff_t src_stride, int bpp, int w, int h,
+                   int col_frac, int row_frac, int mode_x, int mode_y, int bit_depth);
+void orc_mc_avg(void *dst, ptrdiff_t dst_stride, int bpp, const int16_t *tmp1, const int16_t *tmp2,
+                int w, int h, int bit_depth);
+
+/* -------------------------------------------------------------- predict.rs */
+/* dispatch_predict_intra predict.rs:705-784.  edge points at the top-left element of an
+ * IntraEdge-style buffer: left[k] = edge[-1-k] (k=0 nearest the top), above[k] = edge[1+k].
+ * mode: PredictionMode discriminant (predict.rs:58-100); variant: 0 NONE,1 LEFT,2 TOP,3 BOTH;
+ * angle: full prediction angle in degrees for directional modes / alpha for CfL;
+ * ief_params: <0 none, else (enable<<1)|smooth... see orc_predict_intra in predict.c. */
+void orc_predict_intra(int mode, int variant, void *dst, ptrdiff_t dst_stride, int bpp, int w,
+                       int h, int bit_depth, const int16_t *ac, int angle, int ief_params,
+                       const void *edge_tl, int left_len, int above_len);
+void orc_pred_cfl_ac(int16_t *ac, const void *luma, ptrdiff_t luma_stride, int bpp, int bw, int bh,
+                     int w_pad, int h_pad, int xdec, int ydec);
+
+/* ----------------------------------------------------------------- cdef.rs */
+int orc_cdef_find_dir(const void *img, ptrdiff_t stride, int bpp, uint32_t *var, int coeff_shift);
+void orc_cdef_filter_block(void *dst, ptrdiff_t dst_stride, int dst_bpp, const uint16_t *in,
+                           ptrdiff_t in_stride, int pri_strength, int sec_strength, int dir,
+                           int damping, int bit_depth, int xdec, int ydec, int edges);
+int orc_first_max_element(const int32_t *elems, int n, int32_t *max_out);
+
+int orc_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

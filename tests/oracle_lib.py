@@ -1,0 +1,140 @@
+"""ctypes loader for oracle/liboracle.so — the CPU checker (test infrastructure only).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+_LIB = None
+
+
+class Mv(C.Structure):
+    _fields_ = [("row", C.c_int16), ("col", C.c_int16)]
+
+
+class MeResult(C.Structure):
+    _fields_ = [("cost", C.c_uint64), ("sad", C.c_uint32), ("mv", Mv)]
+
+
+ME_RESULT_DTYPE = np.dtype(
+    {"names": ["cost", "sad", "mv_row", "mv_col"],
+     "formats": ["<u8", "<u4", "<i2", "<i2"], "offsets": [0, 8, 12, 14], "itemsize": 16})
+BLOCK_DTYPE = np.dtype([("x", "<i2"), ("y", "<i2")])
+CAND_DTYPE = np.dtype([("block", "<u4"), ("mv_row", "<i2"), ("mv_col", "<i2")])
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(ORACLE_DIR, "liboracle.so")
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR)
+            if f.endswith((".c", ".h"))]
+    if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
+        build()
+    L = C.CDLL(path)
+    vp, pd, i32, u32, u64, sz = C.c_void_p, C.c_ssize_t, C.c_int, C.c_uint32, C.c_uint64, C.c_size_t
+    for name in ("orc_get_sad_u8", "orc_get_sad_u16", "orc_get_satd_u8", "orc_get_satd_u16"):
+        f = getattr(L, name)
+        f.restype = u32
+        f.argtypes = [vp, pd, vp, pd, i32, i32]
+    L.orc_get_mv_rate.restype = u32
+    L.orc_get_mv_rate.argtypes = [Mv, Mv, i32]
+    L.orc_mv_cost.restype = u64
+    L.orc_mv_cost.argtypes = [u32, Mv, Mv, Mv, u32, i32]
+    L.orc_get_mv_range.restype = None
+    L.orc_get_mv_range.argtypes = [i32] * 6 + [C.POINTER(i32)] * 4
+    L.orc_full_search.restype = MeResult
+    L.orc_full_search.argtypes = [vp, pd, vp, pd, i32, i32, i32, i32, i32, i32, i32, i32, i32,
+                                  i32, u32, Mv, Mv, i32]
+    L.orc_fullpel_candidates.restype = None
+    L.orc_fullpel_candidates.argtypes = [vp, pd, vp, pd, i32, i32, i32, vp, vp, sz, i32, i32, i32,
+                                         u32, vp, i32, vp, vp, i32]
+    L.orc_full_search_blocks.restype = None
+    L.orc_full_search_blocks.argtypes = [vp, pd, vp, pd, i32, i32, i32, vp, sz, i32, i32, i32, i32,
+                                         i32, u32, i32, vp, i32]
+    L.orc_num_threads.restype = i32
+    _LIB = L
+    return L
+
+
+def ptr(a, offset_elems=0):
+    """Address of element `offset_elems` of a C-contiguous numpy array."""
+    return a.ctypes.data + offset_elems * a.itemsize
+
+
+class Plane:
+    """A padded plane: `data` is the whole allocation, pixel (0,0) sits at (pad, pad)."""
+
+    def __init__(self, width, height, pad, dtype=np.uint8, stride=None):
+        self.width, self.height, self.pad = width, height, pad
+        self.stride = stride or (width + 2 * pad)
+        self.data = np.zeros((height + 2 * pad, self.stride), dtype=dtype)
+
+    @property
+    def bpp(self):
+        return self.data.itemsize
+
+    def origin_ptr(self):
+        return ptr(self.data, self.pad * self.stride + self.pad)
+
+    def at(self, x, y):
+        return ptr(self.data, (self.pad + y) * self.stride + self.pad + x)
+
+    def view(self):
+        return self.data[self.pad:self.pad + self.height, self.pad:self.pad + self.width]
+
+    def fill_from(self, img):
+        """Copy `img` (height x width) in and replicate edges into the padding (Plane::pad)."""
+        p = self.pad
+        self.data[p:p + self.height, p:p + self.width] = img
+        full = np.pad(img, ((p, p), (p, self.stride - self.width - p)), mode="edge")
+        self.data[:, :] = full
+
+
+def get_sad(org: Plane, ox, oy, ref: Plane, rx, ry, w, h):
+    L = lib()
+    f = L.orc_get_sad_u8 if org.bpp == 1 else L.orc_get_sad_u16
+    return f(org.at(ox, oy), org.stride, ref.at(rx, ry), ref.stride, w, h)
+
+
+def get_satd(org: Plane, ox, oy, ref: Plane, rx, ry, w, h):
+    L = lib()
+    f = L.orc_get_satd_u8 if org.bpp == 1 else L.orc_get_satd_u16
+    return f(org.at(ox, oy), org.stride, ref.at(rx, ry), ref.stride, w, h)
+
+
+def fullpel_candidates(cur: Plane, ref: Plane, blocks, cands, w, h, use_satd=False, lambda_=0,
+                       pmv=None, allow_hp=False, want_cost=True, threads=0):
+    L = lib()
+    n = len(cands)
+    sad = np.empty(n, np.uint32)
+    cost = np.empty(n, np.uint64) if want_cost else None
+    w_in_b = 2 * ((cur.width + 7) >> 3)
+    h_in_b = 2 * ((cur.height + 7) >> 3)
+    L.orc_fullpel_candidates(cur.origin_ptr(), cur.stride, ref.origin_ptr(), ref.stride, cur.bpp,
+                             w_in_b, h_in_b, ptr(blocks), ptr(cands), n, w, h, int(use_satd),
+                             int(lambda_), ptr(pmv) if pmv is not None else None, int(allow_hp),
+                             ptr(sad), ptr(cost) if want_cost else None, threads)
+    return sad, cost
+
+
+def full_search_blocks(cur: Plane, ref: Plane, blocks, w, h, range_x, range_y, step, lambda_,
+                       allow_hp=False, threads=0):
+    L = lib()
+    out = np.zeros(len(blocks), ME_RESULT_DTYPE)
+    w_in_b = 2 * ((cur.width + 7) >> 3)
+    h_in_b = 2 * ((cur.height + 7) >> 3)
+    L.orc_full_search_blocks(cur.origin_ptr(), cur.stride, ref.origin_ptr(), ref.stride, cur.bpp,
+                             w_in_b, h_in_b, ptr(blocks), len(blocks), w, h, range_x, range_y,
+                             step, int(lambda_), int(allow_hp), ptr(out), threads)
+    return out
