@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py — RDO candidate blocks/s on the BASELINE.json workload (configs[1]).
+
+Workload "1080p-8bit-speed6-me16x16" (one *step* = one pass of the hot path over one batch):
+  a lookahead batch of F 1920x1080 8-bit frame pairs (cur, ref) resident in HBM; for every
+  16x16 block (8160 per frame)
+    * SAD  over CAND_SAD  full-pel MV candidates (get_fullpel_mv_rd, me.rs:1386) + per-block
+      first-min winner (me.rs:898),
+    * SATD over CAND_SATD candidates (the sub-pel / mode-pruning distortion, dist.rs:156),
+    * forward DCT_DCT 16x16 of the winner's residual (forward_transform, forward.rs:71)
+      [added once the transform kernels land; reported in config.legs].
+  value = candidate blocks evaluated per second, whole job (all ranks).
+  F is sized so that planes + descriptors exceed the 126 MB L2 (config.l2: "inputs>L2").
+
+JSON contract: see the task statement; extra objects `roofline`, `cpu_baseline`, `e2e`,
+`clocks`, `gpu_launches`.  `--impl reference` times the CPU oracle (the reference's
+algorithm restated in C; rav1e itself cannot be built here: no rustc/nasm) with all host
+threads on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, PAD = 1920, 1080, 96
+BW = BH = 16
+CAND_SAD = 64     # full-pel candidates per block and reference (predictors + diamond + UMH head)
+CAND_SATD = 8     # sub-pel diamond / mode-pruning SATD candidates per block
+MV_RANGE_PX = 64  # candidates uniform in +-64 px (SURVEY §8d cfg 2b)
+LAMBDA = 6400
+FRAMES_PER_GPU = 32
+METRIC = "RDO candidate blocks/s (SAD+SATD+fwd-txfm) 1080p speed-6"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks/throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def synth_frame_pair(seed):
+    """cur(x,y) = ref(x+dx, y+dy) + noise on a padded canvas (borders carry real pixels)."""
+    rng = np.random.default_rng(seed)
+    ref = rng.integers(0, 256, (H + 2 * PAD, W + 2 * PAD), dtype=np.uint8)
+    dx, dy = int(rng.integers(-8, 9)), int(rng.integers(-8, 9))
+    cur = np.roll(ref, (-dy, -dx), axis=(0, 1)).astype(np.int16)
+    cur += rng.integers(-2, 3, cur.shape, dtype=np.int16)
+    return np.clip(cur, 0, 255).astype(np.uint8), ref
+
+
+def grid_blocks():
+    from rav1e_b200 import backend as B
+    xs = np.arange(0, W - BW + 1, BW)
+    ys = np.arange(0, H - BH + 1, BH)     # 67 full rows; the 16x8 bottom strip is a different size
+    b = np.zeros(len(xs) * len(ys), B.BLOCK_DTYPE)
+    b["x"] = np.tile(xs, len(ys))
+    b["y"] = np.repeat(ys, len(xs))
+    return b
+
+
+def cand_list(nblocks, per_block, seed):
+    from rav1e_b200 import backend as B
+    rng = np.random.default_rng(seed)
+    n = nblocks * per_block
+    c = np.zeros(n, B.CAND_DTYPE)
+    c["block"] = np.repeat(np.arange(nblocks, dtype=np.uint32), per_block)
+    mv = rng.integers(-MV_RANGE_PX, MV_RANGE_PX + 1, (n, 2), dtype=np.int16) * 8
+    c["mv_row"], c["mv_col"] = mv[:, 0], mv[:, 1]
+    offs = (np.arange(nblocks + 1, dtype=np.uint64) * per_block).astype(np.uint32)
+    return c, offs
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from tests import oracle_lib as O
+    threads = O.lib().orc_num_threads()
+    blocks = grid_blocks()
+    cur_img, ref_img = synth_frame_pair(0)
+    ocur, oref = O.Plane(W, H, PAD), O.Plane(W, H, PAD)
+    ocur.data[:], oref.data[:] = cur_img, ref_img
+    # bounded sample: one frame pair, 1/4 of its candidate lists per step
+    sad_c, _ = cand_list(len(blocks), CAND_SAD // 4, 100)
+    satd_c, _ = cand_list(len(blocks), CAND_SATD // 4, 200)
+    units = len(sad_c) + len(satd_c)
+
+    def step():
+        O.fullpel_candidates(ocur, oref, blocks, sad_c, BW, BH, False, LAMBDA, want_cost=True)
+        O.fullpel_candidates(ocur, oref, blocks, satd_c, BW, BH, True, LAMBDA, want_cost=True)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = units * args.steps / dt
+    sample = (f"1 of {FRAMES_PER_GPU} frame pairs, {CAND_SAD // 4} SAD + {CAND_SATD // 4} SATD "
+              f"candidates per 16x16 block ({units} blocks/step)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "blocks/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": "1080p-8bit-speed6-me16x16", "sample": sample,
+                   "note": "rav1e cannot be built here (no rustc/nasm); this is the C restatement "
+                           "of its rust:: kernels (oracle/), OpenMP over candidates"},
+        "cpu_baseline": {"value": v, "unit": "blocks/s", "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": v, "unit": "blocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from rav1e_b200 import backend as B
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # one side stream shared by torch (events, NCCL ordering) and the backend's launches
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    ctx = B.Context(local_rank, use_torch_stream=True)
+    assert ctx.L.b200_ctx_get_stream(ctx.h) == stream.cuda_stream
+
+    F = args.frames
+    blocks = grid_blocks()
+    nb = len(blocks)
+    d_blocks = torch.from_numpy(blocks.view(np.uint8)).cuda()
+    # 4 distinct synthetic frame pairs uploaded into F distinct device planes (addresses, not
+    # content, are what cache behaviour depends on); candidate lists are distinct per frame.
+    uniq = [synth_frame_pair(1000 * rank + i) for i in range(min(4, F))]
+    planes = []
+    import ctypes as C
+    for f in range(F):
+        cur_img, ref_img = uniq[f % len(uniq)]
+        pr = []
+        for img in (cur_img, ref_img):
+            p = B.Plane()
+            ctx.check(ctx.L.b200_plane_alloc(ctx.h, W + 2 * PAD, H + 2 * PAD, 0, 1, C.byref(p)))
+            ctx.check(ctx.L.b200_plane_upload(ctx.h, C.byref(p), img.ctypes.data, img.strides[0]))
+            q = B.Plane()
+            q.data = p.data + PAD * p.stride + PAD
+            q.stride, q.width, q.height, q.pad, q.bpp, q.alloc = p.stride, W, H, PAD, 1, None
+            pr.append(q)
+        planes.append(pr)
+    sad_lists, satd_lists = [], []
+    for f in range(F):
+        c, offs = cand_list(nb, CAND_SAD, 7 * f + 1 + 100000 * rank)
+        sad_lists.append(torch.from_numpy(c.view(np.uint8)).cuda())
+        c2, offs2 = cand_list(nb, CAND_SATD, 7 * f + 2 + 100000 * rank)
+        satd_lists.append(torch.from_numpy(c2.view(np.uint8)).cuda())
+    d_offs = torch.from_numpy(offs.view(np.uint8)).cuda()
+    d_offs2 = torch.from_numpy(offs2.view(np.uint8)).cuda()
+    n_sad, n_satd = nb * CAND_SAD, nb * CAND_SATD
+    d_sad = torch.empty(F * n_sad * 4, dtype=torch.uint8, device="cuda")
+    d_satd = torch.empty(F * n_satd * 4, dtype=torch.uint8, device="cuda")
+    d_best = torch.empty(F * nb * 16, dtype=torch.uint8, device="cuda")
+    d_best2 = torch.empty(F * nb * 16, dtype=torch.uint8, device="cuda")
+    gathered = torch.empty(world * F * nb * 16, dtype=torch.uint8, device="cuda") if world > 1 else None
+    p_sad = B.me_params(BW, BH, W, H, LAMBDA, window_hint_px=MV_RANGE_PX)
+    p_satd = B.me_params(BW, BH, W, H, LAMBDA, use_satd=True, window_hint_px=MV_RANGE_PX)
+
+    def sad_launch(f):
+        cur, ref = planes[f]
+        ctx.me_candidates_dev(cur, ref, d_blocks, nb, sad_lists[f], n_sad, p_sad, d_offs, None,
+                              d_sad[f * n_sad * 4:], None, d_best[f * nb * 16:])
+
+    def satd_launch(f):
+        cur, ref = planes[f]
+        ctx.me_candidates_dev(cur, ref, d_blocks, nb, satd_lists[f], n_satd, p_satd, d_offs2, None,
+                              d_satd[f * n_satd * 4:], None, d_best2[f * nb * 16:])
+
+    def step():
+        for f in range(F):
+            sad_launch(f)
+            satd_launch(f)
+        if world > 1:   # per-tile/frame winners to every rank (the entropy-coder owner)
+            dist.all_gather_into_tensor(gathered, d_best)
+
+    def timed(fn, reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    clk = ClockSampler(local_rank)
+    if rank == 0:
+        clk.start()
+    l0 = ctx.launches
+    ms = timed(step, args.steps)
+    launches = ctx.launches - l0
+    clocks = clk.stop() if rank == 0 else None
+    units_per_step = world * F * (n_sad + n_satd)
+    value = units_per_step * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (candidate-list SAD), timed alone on the same stream
+    def sad_only():
+        for f in range(F):
+            sad_launch(f)
+
+    def satd_only():
+        for f in range(F):
+            satd_launch(f)
+    sad_only()
+    ms_sad = timed(sad_only, args.steps) / (args.steps * F)      # ms per launch
+    satd_only()
+    ms_satd = timed(satd_only, args.steps) / (args.steps * F)
+    alg_bytes = n_sad * (BW * BH + 4) + nb * BW * BH             # 260 B/cand + 256 B/block
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (ms_sad * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as fh:
+            traffic = json.load(fh).get("me_cand_smem_u8_16x16_dram_bytes_per_launch")
+
+    out = None
+    if rank == 0:
+        # ---- e2e: same metric through the host-buffer C ABI (H2D + kernels + D2H per frame)
+        e2e = run_e2e(ctx, blocks, args)
+        cpu = run_cpu_baseline(blocks)
+        out = {
+            "metric": METRIC, "value": value, "unit": "blocks/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": "1080p-8bit-speed6-me16x16", "frames_per_gpu": F,
+                       "blocks_per_frame": nb, "block": "16x16",
+                       "legs": {"sad_candidates_per_block": CAND_SAD,
+                                "satd_candidates_per_block": CAND_SATD},
+                       "mv_range_px": MV_RANGE_PX, "lambda": LAMBDA,
+                       "l2": "inputs>L2 (planes %.0f MB + descriptors %.0f MB per GPU)" % (
+                           F * 2 * (W + 2 * PAD) * (H + 2 * PAD) / 1e6, F * (n_sad + n_satd) * 8 / 1e6),
+                       "parallelism": f"frames sharded over {world} GPU(s); all-gather of winners"
+                       if world > 1 else "1 GPU",
+                       "per_launch_ms": {"sad_cand": ms_sad, "satd_cand": ms_satd}},
+            "roofline": {"kernel": "me_cand_smem_u8<16,16> (candidate-list SAD + cost + argmin)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "launch_ms": ms_sad},
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(ctx, blocks, args):
+    """Host buffers in, host results out, per frame, through b200_me_candidates_batch."""
+    import torch
+    from rav1e_b200 import backend as B
+    nb = len(blocks)
+    Fe = 8
+    pinned = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    frames = []
+    for f in range(Fe):
+        cur_img, ref_img = synth_frame_pair(5000 + (f % 2))
+        hc = pinned(cur_img.shape, torch.uint8)
+        hr = pinned(ref_img.shape, torch.uint8)
+        hc[:], hr[:] = cur_img, ref_img
+        c, offs = cand_list(nb, CAND_SAD, 900 + f)
+        c2, offs2 = cand_list(nb, CAND_SATD, 1900 + f)
+        hcand = pinned(c.nbytes, torch.uint8)
+        hcand[:] = c.view(np.uint8)
+        hcand2 = pinned(c2.nbytes, torch.uint8)
+        hcand2[:] = c2.view(np.uint8)
+        outs = (pinned(len(c) * 4, torch.uint8).view(np.uint32), None,
+                pinned(nb * 16, torch.uint8).view(B.ME_RESULT_DTYPE))
+        outs2 = (pinned(len(c2) * 4, torch.uint8).view(np.uint32), None,
+                 pinned(nb * 16, torch.uint8).view(B.ME_RESULT_DTYPE))
+        frames.append((B.host_plane(hc, PAD), B.host_plane(hr, PAD), hcand.view(B.CAND_DTYPE),
+                       hcand2.view(B.CAND_DTYPE), outs, outs2))
+    p_sad = B.me_params(BW, BH, W, H, LAMBDA, window_hint_px=MV_RANGE_PX)
+    p_satd = B.me_params(BW, BH, W, H, LAMBDA, use_satd=True, window_hint_px=MV_RANGE_PX)
+    h2d = d2h = 0
+
+    def step():
+        nonlocal h2d, d2h
+        h2d = d2h = 0
+        for hc, hr, c, c2, outs, outs2 in frames:
+            sad, _, best = ctx.me_candidates_batch(hc, hr, blocks, c, p_sad, offs, None, out=outs)
+            sad2, _, best2 = ctx.me_candidates_batch(hc, hr, blocks, c2, p_satd, offs2, None, out=outs2)
+            plane_bytes = 2 * (W + 2 * PAD) * (H + 2 * PAD)
+            h2d += 2 * plane_bytes + c.nbytes + c2.nbytes + 2 * blocks.nbytes + offs.nbytes + offs2.nbytes
+            d2h += sad.nbytes + sad2.nbytes + best.nbytes + best2.nbytes
+    for _ in range(2):
+        step()
+    t0 = time.perf_counter()
+    reps = max(2, min(args.steps, 5))
+    for _ in range(reps):
+        step()
+    ctx.synchronize()
+    dt = time.perf_counter() - t0
+    units = Fe * nb * (CAND_SAD + CAND_SATD)
+    return {"value": units * reps / dt, "unit": "blocks/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "frames_per_step": Fe,
+            "api": "b200_me_candidates_batch (host planes + descriptors in, SADs + winners out)"}
+
+
+def run_cpu_baseline(blocks):
+    from tests import oracle_lib as O
+    threads = O.lib().orc_num_threads()
+    cur_img, ref_img = synth_frame_pair(0)
+    ocur, oref = O.Plane(W, H, PAD), O.Plane(W, H, PAD)
+    ocur.data[:], oref.data[:] = cur_img, ref_img
+    sad_c, _ = cand_list(len(blocks), CAND_SAD, 100)
+    satd_c, _ = cand_list(len(blocks), CAND_SATD, 200)
+    O.fullpel_candidates(ocur, oref, blocks, sad_c[:65536], BW, BH, False, LAMBDA)   # warm
+    t0 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t0 < 3.0:
+        O.fullpel_candidates(ocur, oref, blocks, sad_c, BW, BH, False, LAMBDA)
+        O.fullpel_candidates(ocur, oref, blocks, satd_c, BW, BH, True, LAMBDA)
+        reps += 1
+    dt = time.perf_counter() - t0
+    units = (len(sad_c) + len(satd_c)) * reps
+    return {"value": units / dt, "unit": "blocks/s", "cores": threads, "kind": "port",
+            "sample": f"1 frame pair x {reps} passes ({CAND_SAD} SAD + {CAND_SATD} SATD cands/block), "
+                      f"{dt:.1f} s wall on {threads} threads; C restatement of rav1e rust:: kernels"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,192 @@
+/*
+ * b200rdo.h — C ABI of the B200-native backend for rav1e's RDO inner loop.
+ *
+ * Drop-in boundary: rav1e selects a kernel backend per file with a `cfg_if!` module swap
+ * (src/dist.rs:10-18, src/mc.rs:10-18, src/predict.rs:16-24, src/cdef.rs:20-28,
+ * src/transform/forward.rs:15-23) and, inside the wrapper module, a per-CpuFeatureLevel
+ * table of `unsafe extern fn` pointers (src/cpu_features/x86.rs:97-158,
+ * src/asm/x86/dist/mod.rs:483-729).  This header declares what such a wrapper module
+ * (`asm::cuda::*`) binds:
+ *
+ *   (1) per-call entry points with EXACTLY the signatures of the x86 asm symbols
+ *       (`rav1e_sad16x16_avx2(src, src_stride_bytes, dst, dst_stride_bytes) -> u32` ...),
+ *       suffix `_cuda`, host pointers in / scalar out — so they slot into the existing
+ *       SAD_FNS/SATD_FNS/... tables unchanged; and
+ *   (2) batched entry points (`*_batch` = host buffers, `*_dev` = device-resident) that
+ *       evaluate thousands of candidate blocks per launch — the form the north star asks
+ *       for, which the reference's one-block-per-call ABI cannot express.
+ *
+ * Conventions (same as the asm ABI, src/asm/x86/dist/mod.rs:130-133): per-call entry
+ * points take BYTE strides (ptrdiff_t); batched entry points take ELEMENT strides inside
+ * b200_plane.  No torch types.  Every function returning int returns a b200_status;
+ * b200_last_error() gives the message.  No entry point ever falls back to CPU code: if no
+ * CUDA device is usable the call fails with B200_ERR_NODEV (per-call scalar forms abort,
+ * mirroring the reference where a bad table entry is UB, not a silent wrong answer).
+ */
+#ifndef B200RDO_H
+#define B200RDO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RDO_ABI_VERSION 1
+
+typedef enum {
+  B200_OK = 0,
+  B200_ERR_CUDA = 1,  /* a CUDA runtime call failed */
+  B200_ERR_ARG = 2,   /* precondition violated (the reference would assert!/panic) */
+  B200_ERR_NODEV = 3, /* no usable sm_100 device */
+  B200_ERR_OOM = 4
+} b200_status;
+
+typedef struct b200_ctx b200_ctx; /* one per host thread / rayon worker (encoder.rs:3253) */
+
+int b200_abi_version(void);
+int b200_device_count(void);
+int b200_ctx_create(int device, b200_ctx **out);
+void b200_ctx_destroy(b200_ctx *ctx);
+const char *b200_last_error(const b200_ctx *ctx); /* ctx may be NULL: global last error */
+/* Enqueue on an externally owned cudaStream_t (e.g. the host framework's current stream;
+ * NULL = the CUDA default stream).  b200_ctx_reset_stream returns to the ctx's own stream. */
+int b200_ctx_set_stream(b200_ctx *ctx, void *cuda_stream);
+int b200_ctx_reset_stream(b200_ctx *ctx);
+void *b200_ctx_get_stream(b200_ctx *ctx);
+int b200_ctx_synchronize(b200_ctx *ctx);
+/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
+uint64_t b200_ctx_launch_count(const b200_ctx *ctx);
+
+/* Raw device memory helpers so non-torch hosts (the Rust shim) can keep data resident. */
+int b200_malloc(b200_ctx *ctx, size_t bytes, void **dptr);
+int b200_free(b200_ctx *ctx, void *dptr);
+int b200_memcpy_h2d(b200_ctx *ctx, void *dptr, const void *host, size_t bytes);
+int b200_memcpy_d2h(b200_ctx *ctx, void *host, const void *dptr, size_t bytes);
+
+/* ------------------------------------------------------------------ planes
+ * Device image of v_frame::Plane<T> as seen through PlaneRegion (tiling/plane_region.rs:
+ * 116-135): `data` addresses pixel (0,0); [-pad, width+pad) x [-pad, height+pad) is
+ * readable (frame/mod.rs:22-23 pads 88 luma px; regions may address the padding,
+ * plane_region.rs:164-172). */
+typedef struct {
+  void *data;     /* DEVICE pointer to pixel (0,0) */
+  int32_t stride; /* elements */
+  int32_t width, height;
+  int32_t pad; /* readable border on all four sides, pixels */
+  int32_t bpp; /* bytes per pixel: 1 (u8) or 2 (u16) */
+  void *alloc; /* allocation base (owned by b200_plane_alloc) */
+} b200_plane;
+
+int b200_plane_alloc(b200_ctx *ctx, int width, int height, int pad, int bpp, b200_plane *out);
+int b200_plane_free(b200_ctx *ctx, b200_plane *p);
+/* Upload the visible width x height area from host (row pitch host_stride_bytes) and
+ * replicate edges into the padding on-device (v_frame Plane::pad semantics). */
+int b200_plane_upload(b200_ctx *ctx, const b200_plane *p, const void *host,
+                      ptrdiff_t host_stride_bytes);
+int b200_plane_download(b200_ctx *ctx, const b200_plane *p, void *host,
+                        ptrdiff_t host_stride_bytes);
+
+/* --------------------------------------------------- SAD / SATD / ME (dist.rs, me.rs)
+ * Per-call, reference-signature entry points.  Replaces rav1e_sad{W}x{H}_{sse2,avx2},
+ * rav1e_satd_{W}x{H}_{ssse3,sse4,avx2} and the _hbd variants (asm/x86/dist/mod.rs:21-43,
+ * tables :483-729).  22 block sizes each: see B200_FOR_EACH_BLOCK_SIZE below. */
+#define B200_FOR_EACH_BLOCK_SIZE(X)                                                      \
+  X(4, 4) X(4, 8) X(4, 16) X(8, 4) X(8, 8) X(8, 16) X(8, 32) X(16, 4) X(16, 8) X(16, 16) \
+  X(16, 32) X(16, 64) X(32, 8) X(32, 16) X(32, 32) X(32, 64) X(64, 16) X(64, 32)         \
+  X(64, 64) X(64, 128) X(128, 64) X(128, 128)
+
+#define B200_DECL_DIST(W, H)                                                              \
+  uint32_t rav1e_sad##W##x##H##_cuda(const uint8_t *src, ptrdiff_t src_stride,            \
+                                     const uint8_t *dst, ptrdiff_t dst_stride);           \
+  uint32_t rav1e_sad_##W##x##H##_hbd_cuda(const uint16_t *src, ptrdiff_t src_stride,      \
+                                          const uint16_t *dst, ptrdiff_t dst_stride);     \
+  uint32_t rav1e_satd_##W##x##H##_cuda(const uint8_t *src, ptrdiff_t src_stride,          \
+                                       const uint8_t *dst, ptrdiff_t dst_stride);         \
+  uint32_t rav1e_satd_##W##x##H##_hbd_cuda(const uint16_t *src, ptrdiff_t src_stride,     \
+                                           const uint16_t *dst, ptrdiff_t dst_stride,     \
+                                           uint32_t bdmax);
+B200_FOR_EACH_BLOCK_SIZE(B200_DECL_DIST)
+#undef B200_DECL_DIST
+
+/* Generic w x h (the `rust::get_sad` fallback for non-canonical crops,
+ * asm/x86/dist/mod.rs:299) — host pointers, byte strides, bpp 1|2. */
+uint32_t b200_get_sad(const void *org, ptrdiff_t org_stride, const void *ref,
+                      ptrdiff_t ref_stride, int w, int h, int bpp);
+uint32_t b200_get_satd(const void *org, ptrdiff_t org_stride, const void *ref,
+                       ptrdiff_t ref_stride, int w, int h, int bpp);
+
+/* Batched motion-estimation distortion.  One launch = all candidates of all blocks. */
+typedef struct {
+  int16_t x, y; /* luma px of the block's top-left (PlaneBlockOffset << 2) */
+} b200_block;
+
+typedef struct {
+  uint32_t block;         /* index into blocks[] */
+  int16_t mv_row, mv_col; /* MotionVector, 1/8 pel (mc.rs:29-32); fullpel offset = mv/8 */
+} b200_cand;
+
+typedef struct {
+  uint64_t cost; /* 256*sad + rate*lambda (me.rs:1460); UINT64_MAX = empty (me.rs:139-146) */
+  uint32_t sad;
+  int16_t mv_row, mv_col;
+} b200_me_result;
+
+typedef struct {
+  int32_t w, h;                       /* block size in px (<= 128) */
+  int32_t frame_w_in_b, frame_h_in_b; /* fi.w_in_b / fi.h_in_b (4x4 units), for get_mv_range */
+  uint32_t lambda;                    /* me.rs:549-552 */
+  int32_t allow_high_precision_mv;
+  int32_t use_satd; /* 0: get_sad, 1: get_satd (me.rs:1450-1454) */
+  int32_t bit_depth;
+  int32_t window_hint_px; /* 0 = unknown; else bound on |mv|/8 of the candidates, used only to
+                             size the shared-memory window (wrong hints cost speed, not results) */
+} b200_me_params;
+
+/* get_fullpel_mv_rd (me.rs:1386-1409) over a candidate list, device-resident.
+ * d_pmv: NULL (both predictors zero) or 2 MotionVectors (row,col int16) per block.
+ * d_cand_offsets: NULL, or nblocks+1 CSR offsets when cands are grouped by block in
+ *   ascending block order — required for d_best (per-block first-minimum winner in list
+ *   order, the serial scan's tie-break, me.rs:898,974).
+ * Outputs (each may be NULL): d_sad[ncands], d_cost[ncands], d_best[nblocks]. */
+int b200_me_candidates_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                           const b200_block *d_blocks, size_t nblocks, const b200_cand *d_cands,
+                           size_t ncands, const uint32_t *d_cand_offsets, const int16_t *d_pmv,
+                           const b200_me_params *params, uint32_t *d_sad, uint64_t *d_cost,
+                           b200_me_result *d_best);
+
+/* full_search (me.rs:1464-1509) as called from full_pixel_me (me.rs:822-846) for every
+ * block: window po +- (range_x, range_y) px clamped to get_mv_range, positions every
+ * `step` px, pmv = 0, first-minimum winner in row-major scan order. */
+int b200_me_full_search_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                            const b200_block *d_blocks, size_t nblocks,
+                            const b200_me_params *params, int range_x, int range_y, int step,
+                            b200_me_result *d_best);
+
+/* Host-buffer forms (what a Rust caller holding Plane<T> memory calls): planes are given
+ * as host pointers to pixel (0,0) + byte strides and must be readable over the padding the
+ * candidates can reach; everything is copied H2D, computed, and copied back before return. */
+typedef struct {
+  const void *data;    /* HOST pointer to pixel (0,0) */
+  ptrdiff_t stride;    /* bytes */
+  int32_t width, height;
+  int32_t pad;         /* readable border present in host memory, pixels */
+  int32_t bpp;
+} b200_host_plane;
+
+int b200_me_candidates_batch(b200_ctx *ctx, const b200_host_plane *cur,
+                             const b200_host_plane *ref, const b200_block *blocks,
+                             size_t nblocks, const b200_cand *cands, size_t ncands,
+                             const uint32_t *cand_offsets, const int16_t *pmv,
+                             const b200_me_params *params, uint32_t *sad, uint64_t *cost,
+                             b200_me_result *best);
+int b200_me_full_search_batch(b200_ctx *ctx, const b200_host_plane *cur,
+                              const b200_host_plane *ref, const b200_block *blocks,
+                              size_t nblocks, const b200_me_params *params, int range_x,
+                              int range_y, int step, b200_me_result *best);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RDO_H */

@@ -1,0 +1,224 @@
+"""ctypes binding of libb200rdo.so (include/b200rdo.h) + torch device-memory helpers.
+
+Fails loudly: `lib()` raises if the shared library is missing; `Context()` raises if no
+CUDA device is usable.  Nothing here computes on the CPU.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libb200rdo.so")
+_LIB = None
+
+OK, ERR_CUDA, ERR_ARG, ERR_NODEV, ERR_OOM = range(5)
+
+
+class B200Error(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"b200rdo status {status}: {msg}")
+        self.status = status
+
+
+class Plane(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("stride", C.c_int32), ("width", C.c_int32),
+                ("height", C.c_int32), ("pad", C.c_int32), ("bpp", C.c_int32),
+                ("alloc", C.c_void_p)]
+
+
+class HostPlane(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("stride", C.c_ssize_t), ("width", C.c_int32),
+                ("height", C.c_int32), ("pad", C.c_int32), ("bpp", C.c_int32)]
+
+
+class MeParams(C.Structure):
+    _fields_ = [("w", C.c_int32), ("h", C.c_int32), ("frame_w_in_b", C.c_int32),
+                ("frame_h_in_b", C.c_int32), ("lambda_", C.c_uint32),
+                ("allow_high_precision_mv", C.c_int32), ("use_satd", C.c_int32),
+                ("bit_depth", C.c_int32), ("window_hint_px", C.c_int32)]
+
+
+BLOCK_DTYPE = np.dtype([("x", "<i2"), ("y", "<i2")])
+CAND_DTYPE = np.dtype([("block", "<u4"), ("mv_row", "<i2"), ("mv_col", "<i2")])
+ME_RESULT_DTYPE = np.dtype(
+    {"names": ["cost", "sad", "mv_row", "mv_col"],
+     "formats": ["<u8", "<u4", "<i2", "<i2"], "offsets": [0, 8, 12, 14], "itemsize": 16})
+
+BLOCK_SIZES = [(4, 4), (4, 8), (4, 16), (8, 4), (8, 8), (8, 16), (8, 32), (16, 4), (16, 8),
+               (16, 16), (16, 32), (16, 64), (32, 8), (32, 16), (32, 32), (32, 64), (64, 16),
+               (64, 32), (64, 64), (64, 128), (128, 64), (128, 128)]
+
+
+def lib():
+    """Load the CUDA backend.  Raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m rav1e_b200.build` "
+            "(or __graft_entry__.build()); rav1e_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, i32, u32 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32
+    pp = C.POINTER(Plane)
+    php = C.POINTER(HostPlane)
+    pmp = C.POINTER(MeParams)
+    L.b200_abi_version.restype = i32
+    L.b200_device_count.restype = i32
+    L.b200_ctx_create.argtypes = [i32, C.POINTER(vp)]
+    L.b200_ctx_destroy.argtypes = [vp]
+    L.b200_ctx_destroy.restype = None
+    L.b200_last_error.argtypes = [vp]
+    L.b200_last_error.restype = C.c_char_p
+    L.b200_ctx_set_stream.argtypes = [vp, vp]
+    L.b200_ctx_reset_stream.argtypes = [vp]
+    L.b200_ctx_get_stream.argtypes = [vp]
+    L.b200_ctx_get_stream.restype = vp
+    L.b200_ctx_synchronize.argtypes = [vp]
+    L.b200_ctx_launch_count.argtypes = [vp]
+    L.b200_ctx_launch_count.restype = C.c_uint64
+    L.b200_malloc.argtypes = [vp, sz, C.POINTER(vp)]
+    L.b200_free.argtypes = [vp, vp]
+    L.b200_memcpy_h2d.argtypes = [vp, vp, vp, sz]
+    L.b200_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+    L.b200_plane_alloc.argtypes = [vp, i32, i32, i32, i32, pp]
+    L.b200_plane_free.argtypes = [vp, pp]
+    L.b200_plane_upload.argtypes = [vp, pp, vp, C.c_ssize_t]
+    L.b200_plane_download.argtypes = [vp, pp, vp, C.c_ssize_t]
+    L.b200_get_sad.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t, i32, i32, i32]
+    L.b200_get_sad.restype = u32
+    L.b200_get_satd.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t, i32, i32, i32]
+    L.b200_get_satd.restype = u32
+    for w, h in BLOCK_SIZES:
+        for name, extra in ((f"rav1e_sad{w}x{h}_cuda", []), (f"rav1e_sad_{w}x{h}_hbd_cuda", []),
+                            (f"rav1e_satd_{w}x{h}_cuda", []),
+                            (f"rav1e_satd_{w}x{h}_hbd_cuda", [u32])):
+            f = getattr(L, name)
+            f.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t] + extra
+            f.restype = u32
+    L.b200_me_candidates_dev.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
+    L.b200_me_full_search_dev.argtypes = [vp, pp, pp, vp, sz, pmp, i32, i32, i32, vp]
+    L.b200_me_candidates_batch.argtypes = [vp, php, php, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
+    L.b200_me_full_search_batch.argtypes = [vp, php, php, vp, sz, pmp, i32, i32, i32, vp]
+    _LIB = L
+    return L
+
+
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _dev_ptr(t):
+    """torch CUDA tensor -> raw device pointer (None passes through)."""
+    return None if t is None else t.data_ptr()
+
+
+class Context:
+    """One b200_ctx (one per process/GPU; the Rust side would hold one per rayon worker)."""
+
+    def __init__(self, device=0, use_torch_stream=False):
+        self.L = lib()
+        h = C.c_void_p()
+        st = self.L.b200_ctx_create(device, C.byref(h))
+        if st != OK:
+            raise B200Error(st, self.L.b200_last_error(None).decode())
+        self.h = h
+        self.device = device
+        if use_torch_stream:
+            import torch
+            self.check(self.L.b200_ctx_set_stream(h, torch.cuda.current_stream(device).cuda_stream))
+
+    def check(self, st):
+        if st != OK:
+            raise B200Error(st, self.L.b200_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.L.b200_ctx_destroy(self.h)
+            self.h = None
+
+    def synchronize(self):
+        self.check(self.L.b200_ctx_synchronize(self.h))
+
+    @property
+    def launches(self):
+        return int(self.L.b200_ctx_launch_count(self.h))
+
+    # ---- planes
+    def plane_from_host(self, img, pad):
+        """Upload a 2-D numpy array (u8/u16) as a padded device plane (edges replicated)."""
+        img = np.ascontiguousarray(img)
+        assert img.ndim == 2 and img.dtype in (np.uint8, np.uint16)
+        p = Plane()
+        self.check(self.L.b200_plane_alloc(self.h, img.shape[1], img.shape[0], pad, img.itemsize,
+                                           C.byref(p)))
+        self.check(self.L.b200_plane_upload(self.h, C.byref(p), img.ctypes.data, img.strides[0]))
+        return p
+
+    def plane_free(self, p):
+        self.check(self.L.b200_plane_free(self.h, C.byref(p)))
+
+    # ---- ME, device resident (torch tensors hold descriptors/results)
+    def me_candidates_dev(self, cur, ref, d_blocks, nblocks, d_cands, ncands, params, d_offsets=None,
+                          d_pmv=None, d_sad=None, d_cost=None, d_best=None):
+        self.check(self.L.b200_me_candidates_dev(
+            self.h, C.byref(cur), C.byref(ref), _dev_ptr(d_blocks), nblocks, _dev_ptr(d_cands),
+            ncands, _dev_ptr(d_offsets), _dev_ptr(d_pmv), C.byref(params), _dev_ptr(d_sad),
+            _dev_ptr(d_cost), _dev_ptr(d_best)))
+
+    def me_full_search_dev(self, cur, ref, d_blocks, nblocks, params, range_x, range_y, step, d_best):
+        self.check(self.L.b200_me_full_search_dev(
+            self.h, C.byref(cur), C.byref(ref), _dev_ptr(d_blocks), nblocks, C.byref(params),
+            range_x, range_y, step, _dev_ptr(d_best)))
+
+    # ---- ME, host buffers (numpy in / numpy out; copies inside)
+    def me_candidates_batch(self, cur_hp, ref_hp, blocks, cands, params, offsets=None, pmv=None,
+                            want_sad=True, want_cost=False, want_best=False, out=None):
+        """`out` = optional (sad, cost, best) preallocated (e.g. pinned) numpy arrays."""
+        n, nb = len(cands), len(blocks)
+        if out is not None:
+            sad, cost, best = out
+        else:
+            sad = np.empty(n, np.uint32) if want_sad else None
+            cost = np.empty(n, np.uint64) if want_cost else None
+            best = np.empty(nb, ME_RESULT_DTYPE) if want_best else None
+        self.check(self.L.b200_me_candidates_batch(
+            self.h, C.byref(cur_hp), C.byref(ref_hp), _np_ptr(blocks), nb, _np_ptr(cands), n,
+            _np_ptr(offsets), _np_ptr(pmv), C.byref(params), _np_ptr(sad), _np_ptr(cost),
+            _np_ptr(best)))
+        return sad, cost, best
+
+    def me_full_search_batch(self, cur_hp, ref_hp, blocks, params, range_x, range_y, step):
+        best = np.empty(len(blocks), ME_RESULT_DTYPE)
+        self.check(self.L.b200_me_full_search_batch(
+            self.h, C.byref(cur_hp), C.byref(ref_hp), _np_ptr(blocks), len(blocks),
+            C.byref(params), range_x, range_y, step, _np_ptr(best)))
+        return best
+
+
+def host_plane(arr2d_full, pad):
+    """HostPlane over a numpy array that already contains `pad` border pixels on each side."""
+    a = arr2d_full
+    assert a.ndim == 2 and a.flags.c_contiguous
+    h, w = a.shape[0] - 2 * pad, a.shape[1] - 2 * pad
+    hp = HostPlane()
+    hp.data = a.ctypes.data + pad * a.strides[0] + pad * a.itemsize
+    hp.stride = a.strides[0]
+    hp.width, hp.height, hp.pad, hp.bpp = w, h, pad, a.itemsize
+    hp._keep = a
+    return hp
+
+
+def me_params(w, h, frame_w, frame_h, lambda_=0, allow_hp=False, use_satd=False, bit_depth=8,
+              window_hint_px=0):
+    p = MeParams()
+    p.w, p.h = w, h
+    p.frame_w_in_b = 2 * ((frame_w + 7) >> 3)   # encoder.rs:852
+    p.frame_h_in_b = 2 * ((frame_h + 7) >> 3)
+    p.lambda_ = lambda_
+    p.allow_high_precision_mv = int(allow_hp)
+    p.use_satd = int(use_satd)
+    p.bit_depth = bit_depth
+    p.window_hint_px = window_hint_px
+    return p

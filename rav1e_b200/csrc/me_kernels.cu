@@ -1,0 +1,821 @@
+// me_kernels.cu — batched motion-estimation distortion for sm_100a.
+//
+// Replaces, for thousands of candidates per launch, the serial loop
+//   get_fullpel_mv_rd -> compute_mv_rd -> get_sad / get_satd     (rav1e src/me.rs:1386-1461,
+//                                                                  src/dist.rs:31-52, :156-221)
+// and full_search (src/me.rs:1464-1509) incl. its first-minimum argmin.
+//
+// Kernels
+//   me_cand_generic<T>      any w x h <= 128, u8/u16, SAD or SATD.  One warp per candidate.
+//   me_cand_smem_u8<W,H>    8-bit SAD fast path: one CTA per block, the bounding window of the
+//                           block's candidates is staged once in shared memory with 16-byte
+//                           loads, then one thread per candidate walks it with aligned LDS.32 +
+//                           funnel shift + VABSDIFF4-accumulate.  Fused cost + first-min argmin.
+//   me_best_from_cost       segmented first-min argmin over a CSR candidate list.
+//   me_full_search_generic<T>  any size / depth, one CTA per block, warp per position.
+//   me_full_search_u8<W,H>  8-bit fast path: window staged in smem so that every candidate
+//                           column is word aligned; each thread evaluates NP adjacent positions
+//                           sharing their loaded words.
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr unsigned long long kEmptyCost = ~0ull;  // MVCandidateRD::empty(), me.rs:139-146
+constexpr uint32_t kEmptySad = ~0u;
+
+struct PlaneView {
+  const void *data;  // pixel (0,0)
+  int stride;        // elements
+};
+
+template <typename T>
+__device__ __forceinline__ const T *px(const PlaneView &p, int x, int y) {
+  return (const T *)p.data + (long long)y * p.stride + x;
+}
+
+struct MeArgs {
+  PlaneView cur, ref;
+  const b200_block *blocks;
+  const b200_cand *cands;
+  const uint32_t *cand_offsets;  // CSR or null
+  const short *pmv;              // 4 shorts per block (row0,col0,row1,col1) or null
+  uint32_t *out_sad;
+  unsigned long long *out_cost;
+  b200_me_result *out_best;
+  size_t ncands;
+  size_t nblocks;
+  int w, h;
+  int w_in_b, h_in_b;
+  uint32_t lambda;
+  int allow_hp;
+  int use_satd;
+  int smem_bytes;  // dynamic smem given to the staged kernels
+};
+
+// ---------------------------------------------------------------- Hadamard (dist.rs:55-149)
+// In-register butterflies on an array the compiler keeps in registers (fully unrolled).
+
+__device__ __forceinline__ void bfly(int &a, int &b) {
+  int s = a + b, t = a - b;
+  a = s;
+  b = t;
+}
+
+// 4x4: vertical (stride1 = 4 over rows) then horizontal, dist.rs:125-143.  The butterfly
+// network output order (b0,b1,b2,b3) matches hadamard4_1d; since only sum|.| is consumed the
+// order inside a vector is irrelevant, but it is kept identical anyway.
+__device__ __forceinline__ uint32_t hadamard4x4_abs_sum(int (&d)[16]) {
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int s0 = pass == 0 ? 1 : 4, s1 = pass == 0 ? 4 : 1;
+      int a0 = d[i * s0 + 0 * s1], a1 = d[i * s0 + 1 * s1], a2 = d[i * s0 + 2 * s1],
+          a3 = d[i * s0 + 3 * s1];
+      bfly(a0, a1);
+      bfly(a2, a3);
+      bfly(a0, a2);
+      bfly(a1, a3);
+      d[i * s0 + 0 * s1] = a0;
+      d[i * s0 + 1 * s1] = a1;
+      d[i * s0 + 2 * s1] = a2;
+      d[i * s0 + 3 * s1] = a3;
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += (uint32_t)abs(d[i]);
+  return s;
+}
+
+__device__ __forceinline__ uint32_t hadamard8x8_abs_sum(int (&d)[64]) {
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int s0 = pass == 0 ? 1 : 8, s1 = pass == 0 ? 8 : 1;
+      int a[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) a[k] = d[i * s0 + k * s1];
+      bfly(a[0], a[1]);
+      bfly(a[2], a[3]);
+      bfly(a[4], a[5]);
+      bfly(a[6], a[7]);
+      bfly(a[0], a[2]);
+      bfly(a[1], a[3]);
+      bfly(a[4], a[6]);
+      bfly(a[5], a[7]);
+      bfly(a[0], a[4]);
+      bfly(a[1], a[5]);
+      bfly(a[2], a[6]);
+      bfly(a[3], a[7]);
+#pragma unroll
+      for (int k = 0; k < 8; k++) d[i * s0 + k * s1] = a[k];
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 64; i++) s += (uint32_t)abs(d[i]);
+  return s;
+}
+
+// Warp-cooperative distortion of one w x h block pair (any size).  All 32 lanes call it
+// with the same arguments; every lane returns the final value.
+template <typename T>
+__device__ uint32_t warp_block_dist(const T *org, int os, const T *ref, int rs, int w, int h,
+                                    int use_satd, int lane) {
+  if (!use_satd) {
+    uint32_t s = 0;
+    const int n = w * h;
+    for (int i = lane; i < n; i += 32) {
+      int y = i / w, x = i - y * w;
+      int d = (int)org[(long long)y * os + x] - (int)ref[(long long)y * rs + x];
+      s += (uint32_t)abs(d);
+    }
+    return warp_sum_u32(s);
+  }
+  // dist.rs:166: size = min(w, h, 8): 4x4 transform when either side is 4, else 8x8
+  const int size = min(min(w, h), 8);
+  const int nx = (w + size - 1) / size, ny = (h + size - 1) / size;
+  unsigned long long sum = 0;
+  for (int c = lane; c < nx * ny; c += 32) {
+    const int cy = (c / nx) * size, cx = (c % nx) * size;
+    const int cw = min(size, w - cx), ch = min(size, h - cy);
+    const T *o = org + (long long)cy * os + cx;
+    const T *r = ref + (long long)cy * rs + cx;
+    if (cw != size || ch != size) {  // dist.rs:185-191: partial chunk -> SAD
+      uint32_t s = 0;
+      for (int y = 0; y < ch; y++)
+        for (int x = 0; x < cw; x++)
+          s += (uint32_t)abs((int)o[(long long)y * os + x] - (int)r[(long long)y * rs + x]);
+      sum += s;
+    } else if (size == 4) {
+      int d[16];
+#pragma unroll
+      for (int y = 0; y < 4; y++)
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+          d[y * 4 + x] = (int)o[(long long)y * os + x] - (int)r[(long long)y * rs + x];
+      sum += hadamard4x4_abs_sum(d);
+    } else {
+      int d[64];
+#pragma unroll
+      for (int y = 0; y < 8; y++)
+#pragma unroll
+        for (int x = 0; x < 8; x++)
+          d[y * 8 + x] = (int)o[(long long)y * os + x] - (int)r[(long long)y * rs + x];
+      sum += hadamard8x8_abs_sum(d);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const int ln = size == 4 ? 2 : 3;  // msb(size)
+  return (uint32_t)((sum + ((1ull << ln) >> 1)) >> ln);
+}
+
+// ---------------------------------------------------------------- generic candidate list
+template <typename T>
+__global__ void __launch_bounds__(256) me_cand_generic(MeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+  for (size_t i = warp0; i < a.ncands; i += nwarps) {
+    const b200_cand c = a.cands[i];
+    const b200_block b = a.blocks[c.block];
+    const MvRange r = b200_mv_range(a.w_in_b, a.h_in_b, b.x / MI_SIZE, b.y / MI_SIZE, a.w, a.h);
+    uint32_t sad = kEmptySad;
+    unsigned long long cost = kEmptyCost;
+    if (!(c.mv_col < r.x_min || c.mv_col > r.x_max || c.mv_row < r.y_min || c.mv_row > r.y_max)) {
+      const int rx = b.x + c.mv_col / 8, ry = b.y + c.mv_row / 8;  // trunc toward zero
+      sad = warp_block_dist<T>(px<T>(a.cur, b.x, b.y), a.cur.stride, px<T>(a.ref, rx, ry),
+                               a.ref.stride, a.w, a.h, a.use_satd, lane);
+      int p0r = 0, p0c = 0, p1r = 0, p1c = 0;
+      if (a.pmv) {
+        const short *p = a.pmv + 4 * (size_t)c.block;
+        p0r = p[0], p0c = p[1], p1r = p[2], p1c = p[3];
+      }
+      cost = b200_mv_cost(sad, c.mv_row, c.mv_col, p0r, p0c, p1r, p1c, a.lambda, a.allow_hp);
+    }
+    if (lane == 0) {
+      if (a.out_sad) a.out_sad[i] = sad;
+      if (a.out_cost) a.out_cost[i] = cost;
+    }
+  }
+}
+
+// Lexicographic (cost, index) min == "first minimum in scan order" (me.rs:898, :1501).
+struct Best {
+  unsigned long long cost;
+  uint32_t idx;
+};
+__device__ __forceinline__ Best best_min(Best a, Best b) {
+  return (b.cost < a.cost || (b.cost == a.cost && b.idx < a.idx)) ? b : a;
+}
+__device__ __forceinline__ Best warp_best(Best v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Best t;
+    t.cost = __shfl_xor_sync(0xffffffffu, v.cost, o);
+    t.idx = __shfl_xor_sync(0xffffffffu, v.idx, o);
+    v = best_min(v, t);
+  }
+  return v;
+}
+// Block-wide reduction; result valid in thread 0.  `red` holds >= 32 entries.
+__device__ __forceinline__ Best block_best(Best v, Best *red) {
+  v = warp_best(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    Best t = lane < nw ? red[lane] : Best{kEmptyCost, 0xffffffffu};
+    v = warp_best(t);
+  }
+  return v;
+}
+
+// One warp per block: first-min over its CSR range of precomputed costs.
+__global__ void me_best_from_cost(const unsigned long long *cost, const uint32_t *sad,
+                                  const b200_cand *cands, const uint32_t *offs, size_t nblocks,
+                                  b200_me_result *out) {
+  const int lane = threadIdx.x & 31;
+  const size_t blk = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (blk >= nblocks) return;
+  const uint32_t lo = offs[blk], hi = offs[blk + 1];
+  Best v{kEmptyCost, 0xffffffffu};
+  for (uint32_t i = lo + lane; i < hi; i += 32) v = best_min(v, Best{cost[i], i});
+  v = warp_best(v);
+  if (lane == 0) {
+    b200_me_result r;
+    r.cost = kEmptyCost;
+    r.sad = kEmptySad;
+    r.mv_row = 0;
+    r.mv_col = 0;  // MotionSearchResult::empty(), me.rs:111-116
+    if (v.cost != kEmptyCost) {
+      r.cost = v.cost;
+      r.sad = sad[v.idx];
+      r.mv_row = cands[v.idx].mv_row;
+      r.mv_col = cands[v.idx].mv_col;
+    }
+    out[blk] = r;
+  }
+}
+
+// ---------------------------------------------------------------- 8-bit SAD fast path
+// VABSDIFF4.U8.ACC with the accumulator fused (nvcc's __vsadu4(a,b)+c emits a separate IADD3).
+__device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// Row of W pixels at byte offset `off` (arbitrary alignment) inside a word-addressed shared
+// window row; org row as W/4 packed words.  Returns sum |org - ref| over the row.
+template <int W>
+__device__ __forceinline__ uint32_t row_sad_u8(const uint32_t *__restrict__ wrow, int word0,
+                                               int shift_bits, const uint32_t *__restrict__ orow,
+                                               uint32_t acc) {
+  uint32_t lo = wrow[word0];
+#pragma unroll
+  for (int k = 0; k < W / 4; k++) {
+    const uint32_t hi = wrow[word0 + k + 1];
+    const uint32_t v = __funnelshift_r(lo, hi, shift_bits);
+    acc = sad4_acc(v, orow[k], acc);
+    lo = hi;
+  }
+  return acc;
+}
+
+// Stage `rows` x `row_bytes` (row_bytes multiple of 16, src 16-byte aligned) into smem.
+__device__ __forceinline__ void stage_window(uint32_t *smem, int pitch_words, const uint8_t *src,
+                                             long long src_stride, int rows, int row_bytes) {
+  const int vec_per_row = row_bytes >> 4;
+  for (int i = threadIdx.x; i < rows * vec_per_row; i += blockDim.x) {
+    const int y = i / vec_per_row, v = i - y * vec_per_row;
+    const uint4 q = __ldg((const uint4 *)(src + (long long)y * src_stride) + v);
+    *(uint4 *)(smem + y * pitch_words + v * 4) = q;
+  }
+}
+
+constexpr int kCandSmemBytes = 96 * 1024;  // dynamic smem budget for the candidate window
+
+template <int W, int H>
+__global__ void __launch_bounds__(128) me_cand_smem_u8(MeArgs a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ uint32_t s_org[H * W / 4];
+  __shared__ int s_box[4];
+  __shared__ Best s_red[32];
+
+  for (size_t blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x) {
+    const uint32_t lo = a.cand_offsets[blk], hi = a.cand_offsets[blk + 1];
+    const b200_block b = a.blocks[blk];
+    const MvRange r = b200_mv_range(a.w_in_b, a.h_in_b, b.x / MI_SIZE, b.y / MI_SIZE, W, H);
+    __syncthreads();  // previous iteration's smem readers are done
+    if (threadIdx.x == 0) {
+      s_box[0] = INT_MAX;
+      s_box[1] = INT_MIN;
+      s_box[2] = INT_MAX;
+      s_box[3] = INT_MIN;
+    }
+    // org block -> smem (packed words); cur rows may be unaligned, go through bytes
+    {
+      const uint8_t *o = px<uint8_t>(a.cur, b.x, b.y);
+      for (int i = threadIdx.x; i < H * W / 4; i += blockDim.x) {
+        const int y = i / (W / 4), k = i - y * (W / 4);
+        const uint8_t *p = o + (long long)y * a.cur.stride + 4 * k;
+        s_org[i] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) |
+                   ((uint32_t)p[3] << 24);
+      }
+    }
+    __syncthreads();
+    // bounding box of the in-range candidates (ref px coordinates of the block's top-left)
+    int bx0 = INT_MAX, bx1 = INT_MIN, by0 = INT_MAX, by1 = INT_MIN;
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      const b200_cand c = a.cands[i];
+      if (c.mv_col < r.x_min || c.mv_col > r.x_max || c.mv_row < r.y_min || c.mv_row > r.y_max)
+        continue;
+      const int rx = b.x + c.mv_col / 8, ry = b.y + c.mv_row / 8;
+      bx0 = min(bx0, rx), bx1 = max(bx1, rx), by0 = min(by0, ry), by1 = max(by1, ry);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
+      bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+      by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+      by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+    }
+    if ((threadIdx.x & 31) == 0 && bx0 != INT_MAX) {
+      atomicMin(&s_box[0], bx0);
+      atomicMax(&s_box[1], bx1);
+      atomicMin(&s_box[2], by0);
+      atomicMax(&s_box[3], by1);
+    }
+    __syncthreads();
+    // 16-byte aligned column, whatever the alignment of pixel (0,0) (row pitch is a multiple
+    // of 16 bytes, checked on the host)
+    const int mis = (int)((uintptr_t)a.ref.data & 15);
+    const int wx0 = s_box[0] == INT_MAX ? 0 : (((s_box[0] + mis) & ~15) - mis);
+    const int wy0 = s_box[2];
+    const int have = s_box[0] != INT_MAX;
+    // +4 bytes: the funnel shift reads one word past the last pixel
+    const int row_bytes = have ? (int)b200_align_up((size_t)(s_box[1] + W + 4 - wx0), 16) : 0;
+    const int rows = have ? s_box[3] - wy0 + H : 0;
+    // pitch in words: odd multiple of 4 words keeps 16-byte alignment and spreads rows over banks
+    const int pitch_words = (row_bytes >> 2) | 4;
+    const bool staged = have && (size_t)rows * pitch_words * 4 <= (size_t)a.smem_bytes;
+    if (staged)
+      stage_window(smem, pitch_words, px<uint8_t>(a.ref, wx0, wy0), a.ref.stride, rows, row_bytes);
+    __syncthreads();
+
+    int p0r = 0, p0c = 0, p1r = 0, p1c = 0;
+    if (a.pmv) {
+      const short *p = a.pmv + 4 * blk;
+      p0r = p[0], p0c = p[1], p1r = p[2], p1c = p[3];
+    }
+    Best best{kEmptyCost, 0xffffffffu};
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      const b200_cand c = a.cands[i];
+      uint32_t sad = kEmptySad;
+      unsigned long long cost = kEmptyCost;
+      if (!(c.mv_col < r.x_min || c.mv_col > r.x_max || c.mv_row < r.y_min ||
+            c.mv_row > r.y_max)) {
+        const int rx = b.x + c.mv_col / 8, ry = b.y + c.mv_row / 8;
+        uint32_t acc = 0;
+        if (staged) {
+          const int off = rx - wx0;
+          const int word0 = off >> 2, sh = (off & 3) * 8;
+          const uint32_t *wrow = smem + (ry - wy0) * pitch_words;
+#pragma unroll 4
+          for (int y = 0; y < H; y++)
+            acc = row_sad_u8<W>(wrow + y * pitch_words, word0, sh, s_org + y * (W / 4), acc);
+        } else {  // window too large for smem: byte loads straight from L1/L2
+          const uint8_t *rp = px<uint8_t>(a.ref, rx, ry);
+          for (int y = 0; y < H; y++) {
+            const uint8_t *q = rp + (long long)y * a.ref.stride;
+            const uint8_t *o = (const uint8_t *)(s_org + y * (W / 4));
+#pragma unroll
+            for (int x = 0; x < W; x++) acc += (uint32_t)abs((int)q[x] - (int)o[x]);
+          }
+        }
+        sad = acc;
+        cost = b200_mv_cost(sad, c.mv_row, c.mv_col, p0r, p0c, p1r, p1c, a.lambda, a.allow_hp);
+      }
+      if (a.out_sad) a.out_sad[i] = sad;
+      if (a.out_cost) a.out_cost[i] = cost;
+      best = best_min(best, Best{cost, i});
+    }
+    if (a.out_best) {
+      // sad/mv of the winner: recompute from the winner's index by its owner is awkward;
+      // keep (cost, idx) and let thread 0 re-derive mv from cands[] and sad from the cost.
+      best = block_best(best, s_red);
+      if (threadIdx.x == 0) {
+        b200_me_result res;
+        res.cost = kEmptyCost;
+        res.sad = kEmptySad;
+        res.mv_row = 0;
+        res.mv_col = 0;
+        if (best.cost != kEmptyCost) {
+          const b200_cand c = a.cands[best.idx];
+          // cost = 256*sad + rate*lambda  =>  sad = (cost - rate*lambda) / 256
+          uint32_t r1 = b200_mv_rate(c.mv_row, c.mv_col, p0r, p0c, a.allow_hp);
+          uint32_t r2 = b200_mv_rate(c.mv_row, c.mv_col, p1r, p1c, a.allow_hp) + 1;
+          uint32_t rate = r1 < r2 ? r1 : r2;
+          res.cost = best.cost;
+          res.sad = (uint32_t)((best.cost - (unsigned long long)rate * a.lambda) >> 8);
+          res.mv_row = c.mv_row;
+          res.mv_col = c.mv_col;
+        }
+        a.out_best[blk] = res;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- full search
+struct FsArgs {
+  PlaneView cur, ref;
+  const b200_block *blocks;
+  b200_me_result *out;
+  size_t nblocks;
+  int w, h;
+  int w_in_b, h_in_b;
+  uint32_t lambda;
+  int allow_hp;
+  int range_x, range_y, step;
+};
+
+struct FsWindow {
+  int x_lo, x_hi, y_lo, y_hi, nx, ny;
+};
+
+// me.rs:822-846: window = po +- range, clamped to the mv range (in full pel, trunc /8).
+__device__ __forceinline__ FsWindow fs_window(const FsArgs &a, b200_block b) {
+  const MvRange r = b200_mv_range(a.w_in_b, a.h_in_b, b.x / MI_SIZE, b.y / MI_SIZE, a.w, a.h);
+  FsWindow w;
+  w.x_lo = b.x + max(-a.range_x, r.x_min / 8);
+  w.x_hi = b.x + min(a.range_x, r.x_max / 8);
+  w.y_lo = b.y + max(-a.range_y, r.y_min / 8);
+  w.y_hi = b.y + min(a.range_y, r.y_max / 8);
+  w.nx = w.x_hi >= w.x_lo ? (w.x_hi - w.x_lo) / a.step + 1 : 0;
+  w.ny = w.y_hi >= w.y_lo ? (w.y_hi - w.y_lo) / a.step + 1 : 0;
+  return w;
+}
+
+__device__ __forceinline__ void fs_write(const FsArgs &a, size_t blk, b200_block b,
+                                         const FsWindow &w, Best best, uint32_t sad_of_best) {
+  b200_me_result res;
+  res.cost = kEmptyCost;
+  res.sad = kEmptySad;
+  res.mv_row = 0;
+  res.mv_col = 0;
+  if (best.cost != kEmptyCost) {
+    const int py = best.idx / w.nx, pxi = best.idx - py * w.nx;
+    const int x = w.x_lo + pxi * a.step, y = w.y_lo + py * a.step;
+    res.cost = best.cost;
+    res.sad = sad_of_best;
+    res.mv_row = (short)(8 * (short)(y - b.y));  // me.rs:1482-1485
+    res.mv_col = (short)(8 * (short)(x - b.x));
+  }
+  a.out[blk] = res;
+}
+
+__device__ __forceinline__ uint32_t fs_sad_from_cost(const FsArgs &a, b200_block b,
+                                                     const FsWindow &w, Best best) {
+  if (best.cost == kEmptyCost) return kEmptySad;
+  const int py = best.idx / w.nx, pxi = best.idx - py * w.nx;
+  const int mvr = (short)(8 * (short)(w.y_lo + py * a.step - b.y));
+  const int mvc = (short)(8 * (short)(w.x_lo + pxi * a.step - b.x));
+  uint32_t r1 = b200_mv_rate(mvr, mvc, 0, 0, a.allow_hp);
+  uint32_t rate = r1 < r1 + 1 ? r1 : r1 + 1;  // min(rate1, rate2 + 1) with pmv0 == pmv1 == 0
+  return (uint32_t)((best.cost - (unsigned long long)rate * a.lambda) >> 8);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) me_full_search_generic(FsArgs a) {
+  __shared__ Best s_red[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (size_t blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x) {
+    const b200_block b = a.blocks[blk];
+    const FsWindow w = fs_window(a, b);
+    Best best{kEmptyCost, 0xffffffffu};
+    const int npos = w.nx * w.ny;
+    for (int p = wid; p < npos; p += nw) {
+      const int py = p / w.nx, pxi = p - py * w.nx;
+      const int x = w.x_lo + pxi * a.step, y = w.y_lo + py * a.step;
+      const uint32_t sad = warp_block_dist<T>(px<T>(a.cur, b.x, b.y), a.cur.stride,
+                                              px<T>(a.ref, x, y), a.ref.stride, a.w, a.h, 0, lane);
+      const int mvr = (short)(8 * (short)(y - b.y)), mvc = (short)(8 * (short)(x - b.x));
+      const unsigned long long cost =
+          b200_mv_cost(sad, mvr, mvc, 0, 0, 0, 0, a.lambda, a.allow_hp);
+      best = best_min(best, Best{cost, (uint32_t)p});
+    }
+    best = block_best(best, s_red);
+    if (threadIdx.x == 0) fs_write(a, blk, b, w, best, fs_sad_from_cost(a, b, w, best));
+    __syncthreads();
+  }
+}
+
+// 8-bit fast path.  The window is staged so that smem column 0 == x_lo: with the reference's
+// step (4 at full resolution, me.rs:840-844) every candidate then starts on a word boundary
+// and needs no byte shifting; other steps use the funnel-shift form.  Each thread evaluates
+// NP horizontally adjacent positions per task, sharing the loaded reference words.
+constexpr int kFsSmemBytes = 200 * 1024;
+
+template <int W, int H, int NP>
+__global__ void __launch_bounds__(256) me_full_search_u8(FsArgs a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ uint32_t s_org[H * W / 4];
+  __shared__ Best s_red[32];
+  const int step = a.step;
+  for (size_t blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x) {
+    const b200_block b = a.blocks[blk];
+    const FsWindow w = fs_window(a, b);
+    __syncthreads();
+    {
+      const uint8_t *o = px<uint8_t>(a.cur, b.x, b.y);
+      for (int i = threadIdx.x; i < H * W / 4; i += blockDim.x) {
+        const int y = i / (W / 4), k = i - y * (W / 4);
+        const uint8_t *p = o + (long long)y * a.cur.stride + 4 * k;
+        s_org[i] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) |
+                   ((uint32_t)p[3] << 24);
+      }
+    }
+    // stage [x_lo, x_hi + W + 4) x [y_lo, y_hi + H) with column 0 = x_lo (byte-realigned)
+    const int npos = w.nx * w.ny;
+    const int row_px = npos ? (w.x_hi - w.x_lo) + W : 0;
+    // words per row incl. the NP-1 extra positions a task may touch, rounded to 16 bytes so
+    // rows stay uint4-aligned (LDS.128); +4 words slack for the funnel-shift form
+    const int row_words = ((row_px + 3) / 4 + NP + 4 + 3) & ~3;
+    const int pitch_words = row_words;
+    const int rows = npos ? (w.y_hi - w.y_lo) + H : 0;
+    {
+      const int mis = (int)((uintptr_t)a.ref.data & 3);
+      const int ax = ((w.x_lo + mis) & ~3) - mis;  // word-aligned source column
+      const int sh = (w.x_lo - ax) * 8;         // byte realignment
+      const uint8_t *src = px<uint8_t>(a.ref, ax, w.y_lo);
+      for (int i = threadIdx.x; i < rows * row_words; i += blockDim.x) {
+        const int y = i / row_words, k = i - y * row_words;
+        const uint32_t *s = (const uint32_t *)(src + (long long)y * a.ref.stride) + k;
+        const uint32_t lo = __ldg(s), hi = __ldg(s + 1);
+        smem[y * pitch_words + k] = __funnelshift_r(lo, hi, sh);
+      }
+    }
+    __syncthreads();
+    Best best{kEmptyCost, 0xffffffffu};
+    const int groups_x = (w.nx + NP - 1) / NP;
+    const int ntasks = groups_x * w.ny;
+    for (int t = threadIdx.x; t < ntasks; t += blockDim.x) {
+      const int py = t / groups_x, g = t - py * groups_x;
+      const int px0 = g * NP;                      // first position index in this row
+      const int off = px0 * step;                  // byte offset of that position
+      const int word0 = off >> 2;
+      const uint32_t *wrow = smem + (py * step) * pitch_words + word0;
+      uint32_t acc[NP];
+#pragma unroll
+      for (int p = 0; p < NP; p++) acc[p] = 0;
+      if (step == 4 && NP == 4) {
+        // word0 = 4*g: 16-byte aligned -> the W/4 + 3 words come in as uint4 (LDS.128),
+        // consecutive threads read consecutive 16-byte chunks (conflict free)
+        constexpr int NV = (W / 4 + NP - 1 + 3) / 4;
+#pragma unroll 2
+        for (int y = 0; y < H; y++) {
+          uint32_t rw[NV * 4];
+          const uint4 *v = (const uint4 *)(wrow + y * pitch_words);
+#pragma unroll
+          for (int k = 0; k < NV; k++) {
+            const uint4 q = v[k];
+            rw[4 * k] = q.x, rw[4 * k + 1] = q.y, rw[4 * k + 2] = q.z, rw[4 * k + 3] = q.w;
+          }
+#pragma unroll
+          for (int k = 0; k < W / 4; k++) {
+            const uint32_t o = s_org[y * (W / 4) + k];
+#pragma unroll
+            for (int p = 0; p < NP; p++) acc[p] = sad4_acc(rw[k + p], o, acc[p]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+          const int o2 = (px0 + p) * step;
+          const int w0 = (o2 >> 2) - word0, s2 = (o2 & 3) * 8;
+          for (int y = 0; y < H; y++)
+            acc[p] = row_sad_u8<W>(wrow + y * pitch_words, w0, s2, s_org + y * (W / 4), acc[p]);
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < NP; p++) {
+        if (px0 + p < w.nx) {
+          const int x = w.x_lo + (px0 + p) * step, y = w.y_lo + py * step;
+          const int mvr = (short)(8 * (short)(y - b.y)), mvc = (short)(8 * (short)(x - b.x));
+          const unsigned long long cost =
+              b200_mv_cost(acc[p], mvr, mvc, 0, 0, 0, 0, a.lambda, a.allow_hp);
+          best = best_min(best, Best{cost, (uint32_t)(py * w.nx + px0 + p)});
+        }
+      }
+    }
+    best = block_best(best, s_red);
+    if (threadIdx.x == 0) fs_write(a, blk, b, w, best, fs_sad_from_cost(a, b, w, best));
+  }
+}
+
+// ---------------------------------------------------------------- host-side dispatch
+template <int W, int H>
+int launch_cand_smem(b200_ctx *ctx, MeArgs a, int window_hint_px) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(ctx, cudaFuncSetAttribute(me_cand_smem_u8<W, H>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kCandSmemBytes));
+    attr_set = true;
+  }
+  // Shared window sized from the caller's search-range hint (blocks whose candidate bounding
+  // box does not fit fall back to direct loads inside the kernel).
+  const int hint = window_hint_px > 0 ? window_hint_px : 32;
+  size_t pitch = (b200_align_up((size_t)(2 * hint + W + 4 + 15), 16) >> 2) | 4;
+  size_t smem = pitch * 4 * (size_t)(2 * hint + H);
+  smem = std::min<size_t>(std::max<size_t>(smem, 8 * 1024), (size_t)kCandSmemBytes);
+  a.smem_bytes = (int)smem;
+  const int grid = (int)std::min<size_t>(a.nblocks, (size_t)ctx->num_sms * 64);
+  me_cand_smem_u8<W, H><<<grid, 128, smem, ctx->stream>>>(a);
+  B200_LAUNCH_CHECK(ctx);
+  return B200_OK;
+}
+
+template <int W, int H>
+int launch_fs_u8(b200_ctx *ctx, const FsArgs &a, size_t smem_bytes) {
+  constexpr int NP = W >= 8 ? 4 : 2;
+  static size_t attr = 0;
+  if (smem_bytes > attr) {
+    B200_CUDA(ctx, cudaFuncSetAttribute(me_full_search_u8<W, H, NP>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_bytes));
+    attr = smem_bytes;
+  }
+  const int grid = (int)std::min<size_t>(a.nblocks, (size_t)ctx->num_sms * 32);
+  me_full_search_u8<W, H, NP><<<grid, 256, smem_bytes, ctx->stream>>>(a);
+  B200_LAUNCH_CHECK(ctx);
+  return B200_OK;
+}
+
+int check_planes(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                 const b200_me_params *p) {
+  B200_REQUIRE(ctx, cur && ref && p, "NULL plane/params");
+  B200_REQUIRE(ctx, cur->data && ref->data, "plane has no device memory");
+  B200_REQUIRE(ctx, cur->bpp == ref->bpp && (cur->bpp == 1 || cur->bpp == 2),
+               "planes must share bpp (1 or 2), got %d / %d", cur->bpp, ref->bpp);
+  // dist.rs:35 / :160: w and h can be at most 128
+  B200_REQUIRE(ctx, p->w > 0 && p->h > 0 && p->w <= 128 && p->h <= 128,
+               "block size %dx%d out of range (<= 128)", p->w, p->h);
+  // dist.rs:166-167: the transform is 4x4 iff min(w,h) == 4, else 8x8; any other minimum < 8
+  // makes the reference run an 8x8 transform over a short buffer (UB) - reject it.
+  B200_REQUIRE(ctx, !p->use_satd || std::min(p->w, p->h) >= 8 || std::min(p->w, p->h) == 4,
+               "get_satd: min(w,h) must be 4 or >= 8, got %dx%d", p->w, p->h);
+  return B200_OK;
+}
+
+}  // namespace
+
+extern "C" int b200_me_candidates_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                                      const b200_block *d_blocks, size_t nblocks,
+                                      const b200_cand *d_cands, size_t ncands,
+                                      const uint32_t *d_cand_offsets, const int16_t *d_pmv,
+                                      const b200_me_params *p, uint32_t *d_sad, uint64_t *d_cost,
+                                      b200_me_result *d_best) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  if (int st = check_planes(ctx, cur, ref, p)) return st;
+  B200_REQUIRE(ctx, d_best == nullptr || d_cand_offsets != nullptr,
+               "d_best needs CSR d_cand_offsets (candidates grouped by block)");
+  B200_REQUIRE(ctx, ncands < (1ull << 32), "ncands must fit 32 bits");
+  if (ncands == 0 && (nblocks == 0 || !d_best)) return B200_OK;
+  B200_REQUIRE(ctx, d_blocks && (d_cands || ncands == 0), "NULL blocks/cands");
+  B200_CUDA(ctx, cudaSetDevice(ctx->device));
+
+  MeArgs a;
+  a.cur = {cur->data, cur->stride};
+  a.ref = {ref->data, ref->stride};
+  a.blocks = d_blocks;
+  a.cands = d_cands;
+  a.cand_offsets = d_cand_offsets;
+  a.pmv = d_pmv;
+  a.out_sad = d_sad;
+  a.out_cost = (unsigned long long *)d_cost;
+  a.out_best = d_best;
+  a.ncands = ncands;
+  a.nblocks = nblocks;
+  a.w = p->w;
+  a.h = p->h;
+  a.w_in_b = p->frame_w_in_b;
+  a.h_in_b = p->frame_h_in_b;
+  a.lambda = p->lambda;
+  a.allow_hp = p->allow_high_precision_mv;
+  a.use_satd = p->use_satd;
+  a.smem_bytes = 0;
+
+  // Fast path: 8-bit SAD, candidates grouped by block, canonical block size.
+  if (cur->bpp == 1 && !p->use_satd && d_cand_offsets && nblocks > 0 && (ref->stride & 15) == 0) {
+#define B200_CASE(W_, H_) \
+  if (p->w == W_ && p->h == H_) return launch_cand_smem<W_, H_>(ctx, a, p->window_hint_px);
+    B200_CASE(8, 8)
+    B200_CASE(16, 16)
+    B200_CASE(32, 32)
+    B200_CASE(8, 16)
+    B200_CASE(16, 8)
+    B200_CASE(16, 32)
+    B200_CASE(32, 16)
+#undef B200_CASE
+  }
+
+  // Generic path: per-candidate values, then (optionally) the segmented argmin.
+  unsigned long long *cost_buf = a.out_cost;
+  uint32_t *sad_buf = a.out_sad;
+  if (d_best && ncands) {
+    size_t need = 0;
+    if (!cost_buf) need += ncands * 8;
+    if (!sad_buf) need += ncands * 4;
+    if (need) {
+      if (int st = b200_reserve_dwork(ctx, need)) return st;
+      uint8_t *wsp = (uint8_t *)ctx->dwork;
+      if (!cost_buf) {
+        cost_buf = (unsigned long long *)wsp;
+        wsp += ncands * 8;
+      }
+      if (!sad_buf) sad_buf = (uint32_t *)wsp;
+    }
+  }
+  if (ncands) {
+    a.out_cost = cost_buf;
+    a.out_sad = sad_buf;
+    const int warps_per_cta = 8;
+    const size_t want = (ncands + warps_per_cta - 1) / warps_per_cta;
+    const int grid = (int)std::min<size_t>(want, (size_t)ctx->num_sms * 16);
+    if (cur->bpp == 1)
+      me_cand_generic<uint8_t><<<grid, warps_per_cta * 32, 0, ctx->stream>>>(a);
+    else
+      me_cand_generic<uint16_t><<<grid, warps_per_cta * 32, 0, ctx->stream>>>(a);
+    B200_LAUNCH_CHECK(ctx);
+  }
+  if (d_best && nblocks) {
+    const int wpc = 8;
+    const int grid = (int)((nblocks + wpc - 1) / wpc);
+    me_best_from_cost<<<grid, wpc * 32, 0, ctx->stream>>>(cost_buf, sad_buf, d_cands,
+                                                          d_cand_offsets, nblocks, d_best);
+    B200_LAUNCH_CHECK(ctx);
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_me_full_search_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                                       const b200_block *d_blocks, size_t nblocks,
+                                       const b200_me_params *p, int range_x, int range_y, int step,
+                                       b200_me_result *d_best) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  if (int st = check_planes(ctx, cur, ref, p)) return st;
+  B200_REQUIRE(ctx, range_x >= 0 && range_y >= 0 && step >= 1, "bad range/step %d %d %d", range_x,
+               range_y, step);
+  B200_REQUIRE(ctx, !p->use_satd, "full_search always uses SAD (me.rs:1489)");
+  if (nblocks == 0) return B200_OK;
+  B200_REQUIRE(ctx, d_blocks && d_best, "NULL blocks/out");
+  B200_CUDA(ctx, cudaSetDevice(ctx->device));
+
+  FsArgs a;
+  a.cur = {cur->data, cur->stride};
+  a.ref = {ref->data, ref->stride};
+  a.blocks = d_blocks;
+  a.out = d_best;
+  a.nblocks = nblocks;
+  a.w = p->w;
+  a.h = p->h;
+  a.w_in_b = p->frame_w_in_b;
+  a.h_in_b = p->frame_h_in_b;
+  a.lambda = p->lambda;
+  a.allow_hp = p->allow_high_precision_mv;
+  a.range_x = range_x;
+  a.range_y = range_y;
+  a.step = step;
+
+  if (cur->bpp == 1 && (ref->stride & 3) == 0) {
+    const int np = p->w >= 8 ? 4 : 2;  // must match launch_fs_u8 / the kernel's row_words
+    const size_t row_words = (size_t)(((2 * range_x + p->w + 3) / 4 + np + 4 + 3) & ~3);
+    const size_t smem_bytes = row_words * 4 * (size_t)(2 * range_y + p->h);
+    if (smem_bytes <= (size_t)kFsSmemBytes) {
+#define B200_CASE(W_, H_) \
+  if (p->w == W_ && p->h == H_) return launch_fs_u8<W_, H_>(ctx, a, smem_bytes);
+      B200_CASE(8, 8)
+      B200_CASE(16, 16)
+      B200_CASE(32, 32)
+      B200_CASE(64, 64)
+#undef B200_CASE
+    }
+  }
+  const int grid = (int)std::min<size_t>(nblocks, (size_t)ctx->num_sms * 16);
+  if (cur->bpp == 1)
+    me_full_search_generic<uint8_t><<<grid, 256, 0, ctx->stream>>>(a);
+  else
+    me_full_search_generic<uint16_t><<<grid, 256, 0, ctx->stream>>>(a);
+  B200_LAUNCH_CHECK(ctx);
+  return B200_OK;
+}

@@ -1,0 +1,262 @@
+"""GPU parity tests for the SAD/SATD/ME path: CUDA (through the C ABI) == oracle, bit exact.
+
+Mirrors the reference's own test layout: the KATs of src/dist.rs:416-533 run against the
+per-call `rav1e_*_cuda` symbols (the table entries a Rust wrapper would call), and the
+asm==rust random-input equivalence tests of src/asm/x86/dist/mod.rs:738-969 become
+CUDA==oracle tests over candidate batches.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from rav1e_b200 import backend as B
+from tests import gpu_util as G
+from tests import oracle_lib as O
+from tests.test_oracle_dist import SAD_KAT, SATD_KAT, setup_planes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+def test_percall_kats(dtype):
+    """dist.rs:418-441 / :477-500 through rav1e_sad{W}x{H}_cuda etc. (byte strides)."""
+    L = B.lib()
+    (inp, xo, yo, st), (rec, xr, yr, sr) = setup_planes(dtype)
+    isz = inp.itemsize
+    hbd = dtype == np.uint16
+    for kind, table in (("sad", SAD_KAT), ("satd", SATD_KAT)):
+        for w, h, want in table:
+            if kind == "sad":
+                name = f"rav1e_sad_{w}x{h}_hbd_cuda" if hbd else f"rav1e_sad{w}x{h}_cuda"
+            else:
+                name = f"rav1e_satd_{w}x{h}_hbd_cuda" if hbd else f"rav1e_satd_{w}x{h}_cuda"
+            f = getattr(L, name)
+            args = [O.ptr(inp, (yo + 40) * st + xo + 32), st * isz,
+                    O.ptr(rec, (yr + 40) * sr + xr + 32), sr * isz]
+            if kind == "satd" and hbd:
+                args.append(255)
+            assert f(*args) == want, (name, want)
+
+
+def test_percall_noncanonical_size():
+    """Frame-edge crops (e.g. 16x12) go to the generic path (asm/x86/dist/mod.rs:299)."""
+    L = B.lib()
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, (40, 48), dtype=np.uint8)
+    b = rng.integers(0, 256, (40, 64), dtype=np.uint8)
+    for w, h in ((16, 12), (12, 8), (20, 20), (8, 12)):
+        want = O.lib().orc_get_sad_u8(O.ptr(a), 48, O.ptr(b), 64, w, h)
+        assert L.b200_get_sad(O.ptr(a), 48, O.ptr(b), 64, w, h, 1) == want
+        want = O.lib().orc_get_satd_u8(O.ptr(a), 48, O.ptr(b), 64, w, h)
+        assert L.b200_get_satd(O.ptr(a), 48, O.ptr(b), 64, w, h, 1) == want
+
+
+CAND_CASES = [
+    # (w, h, dtype, bit_depth, use_satd, per_block, max_px)
+    (16, 16, np.uint8, 8, False, 40, 40),    # some candidates fall outside get_mv_range
+    (16, 16, np.uint8, 8, True, 12, 24),
+    (8, 8, np.uint8, 8, False, 30, 16),
+    (32, 32, np.uint8, 8, False, 20, 40),
+    (4, 4, np.uint8, 8, False, 9, 12),
+    (4, 8, np.uint8, 8, True, 9, 12),
+    (64, 64, np.uint8, 8, False, 6, 70),
+    (128, 128, np.uint8, 8, True, 2, 8),
+    (16, 8, np.uint8, 8, False, 17, 30),
+    (16, 12, np.uint8, 8, True, 5, 10),      # non-canonical crop: partial chunks -> SAD
+    (16, 16, np.uint16, 10, False, 25, 24),
+    (16, 16, np.uint16, 10, True, 10, 24),
+    (32, 16, np.uint16, 12, True, 7, 24),
+    (64, 64, np.uint16, 12, False, 3, 24),
+]
+
+
+@pytest.mark.parametrize("w,h,dtype,bd,use_satd,per_block,max_px", CAND_CASES)
+def test_candidate_list_matches_oracle(w, h, dtype, bd, use_satd, per_block, max_px):
+    W, H, PAD = 352, 288, 160
+    cur, ref = G.make_planes(W, H, PAD, dtype, seed=w * 131 + h, bit_depth=bd)
+    ocur, dcur = G.both_planes(cur, PAD)
+    oref, dref = G.both_planes(ref, PAD)
+    blocks = G.grid_blocks(W, H, w, h)
+    cands, offs = G.random_cands(len(blocks), per_block, max_px, seed=7, fullpel=(w != 8))
+    rng = np.random.default_rng(11)
+    pmv = (rng.integers(-64, 65, (len(blocks), 4)) * 4).astype(np.int16)
+    lam = 1234
+    want_sad, want_cost = O.fullpel_candidates(ocur, oref, blocks, cands, w, h, use_satd, lam, pmv)
+
+    c = G.ctx()
+    p = B.me_params(w, h, W, H, lam, use_satd=use_satd, bit_depth=bd, window_hint_px=max_px)
+    d_blocks, d_cands, d_offs, d_pmv = map(G.to_dev, (blocks, cands, offs, pmv))
+    d_sad, d_cost = G.dev_empty(4 * len(cands)), G.dev_empty(8 * len(cands))
+    d_best = G.dev_empty(16 * len(blocks))
+    c.me_candidates_dev(dcur, dref, d_blocks, len(blocks), d_cands, len(cands), p, d_offs, d_pmv,
+                        d_sad, d_cost, d_best)
+    c.synchronize()
+    got_sad = G.from_dev(d_sad, np.uint32)[:len(cands)]
+    got_cost = G.from_dev(d_cost, np.uint64)[:len(cands)]
+    np.testing.assert_array_equal(got_sad, want_sad)
+    np.testing.assert_array_equal(got_cost, want_cost)
+    best = G.from_dev(d_best, B.ME_RESULT_DTYPE)[:len(blocks)]
+    for b in range(len(blocks)):
+        lo, hi = int(offs[b]), int(offs[b + 1])
+        if lo == hi or want_cost[lo:hi].min() == np.uint64(2**64 - 1):
+            assert best[b]["cost"] == np.uint64(2**64 - 1) and best[b]["sad"] == 0xFFFFFFFF
+            continue
+        k = lo + int(np.argmin(want_cost[lo:hi]))      # numpy argmin = first minimum
+        assert best[b]["cost"] == want_cost[k]
+        assert best[b]["sad"] == want_sad[k]
+        assert (best[b]["mv_row"], best[b]["mv_col"]) == (cands[k]["mv_row"], cands[k]["mv_col"])
+    # ungrouped call (no CSR): per-candidate outputs only, same values
+    d_sad2 = G.dev_empty(4 * len(cands))
+    perm = np.random.default_rng(1).permutation(len(cands))
+    c.me_candidates_dev(dcur, dref, d_blocks, len(blocks), G.to_dev(cands[perm]), len(cands), p,
+                        None, d_pmv, d_sad2, None, None)
+    c.synchronize()
+    np.testing.assert_array_equal(G.from_dev(d_sad2, np.uint32)[:len(cands)], want_sad[perm])
+    for pl in (dcur, dref):
+        c.plane_free(pl)
+
+
+def test_candidate_list_host_buffers():
+    """The `_batch` form (host pointers, copies inside) gives the same numbers."""
+    W, H, PAD, w, h = 320, 192, 96, 16, 16
+    cur, ref = G.make_planes(W, H, PAD, np.uint8, seed=3)
+    ocur = O.Plane(W, H, PAD)
+    ocur.fill_from(cur)
+    oref = O.Plane(W, H, PAD)
+    oref.fill_from(ref)
+    blocks = G.grid_blocks(W, H, w, h)
+    cands, offs = G.random_cands(len(blocks), 33, 20, seed=9)
+    want_sad, want_cost = O.fullpel_candidates(ocur, oref, blocks, cands, w, h, False, 77)
+    c = G.ctx()
+    p = B.me_params(w, h, W, H, 77, window_hint_px=20)
+    sad, cost, best = c.me_candidates_batch(B.host_plane(ocur.data, PAD), B.host_plane(oref.data, PAD),
+                                            blocks, cands, p, offs, None, True, True, True)
+    np.testing.assert_array_equal(sad, want_sad)
+    np.testing.assert_array_equal(cost, want_cost)
+    for b in range(len(blocks)):
+        lo, hi = int(offs[b]), int(offs[b + 1])
+        if lo < hi:
+            assert best[b]["cost"] == want_cost[lo:hi].min()
+
+
+FS_CASES = [
+    # (w, h, dtype, bd, range_x, range_y, step, lambda)
+    (16, 16, np.uint8, 8, 48, 16, 4, 0),
+    (16, 16, np.uint8, 8, 48, 16, 4, 3200),
+    (16, 16, np.uint8, 8, 24, 8, 2, 500),      # hres level: step 2
+    (16, 16, np.uint8, 8, 12, 4, 1, 500),      # qres level: step 1
+    (8, 8, np.uint8, 8, 20, 12, 4, 100),
+    (32, 32, np.uint8, 8, 32, 16, 4, 100),
+    (64, 64, np.uint8, 8, 16, 8, 4, 100),
+    (16, 8, np.uint8, 8, 16, 8, 4, 100),       # generic path
+    (16, 16, np.uint16, 10, 16, 8, 4, 900),
+    (16, 16, np.uint8, 8, 192, 64, 4, 6400),   # full-resolution lookahead window
+]
+
+
+@pytest.mark.parametrize("w,h,dtype,bd,rx,ry,step,lam", FS_CASES)
+def test_full_search_matches_oracle(w, h, dtype, bd, rx, ry, step, lam):
+    big = rx > 100
+    W, H, PAD = (256, 128, 96) if big else (192, 128, 96)
+    cur, ref = G.make_planes(W, H, PAD, dtype, seed=rx + ry + step, bit_depth=bd, shift=(5, -3))
+    ocur, dcur = G.both_planes(cur, PAD)
+    oref, dref = G.both_planes(ref, PAD)
+    blocks = G.grid_blocks(W, H, w, h)
+    if big:
+        blocks = np.ascontiguousarray(blocks[::5])
+    want = O.full_search_blocks(ocur, oref, blocks, w, h, rx, ry, step, lam)
+    c = G.ctx()
+    p = B.me_params(w, h, W, H, lam, bit_depth=bd)
+    d_best = G.dev_empty(16 * len(blocks))
+    c.me_full_search_dev(dcur, dref, G.to_dev(blocks), len(blocks), p, rx, ry, step, d_best)
+    c.synchronize()
+    got = G.from_dev(d_best, B.ME_RESULT_DTYPE)[:len(blocks)]
+    for f in ("cost", "sad", "mv_row", "mv_col"):
+        np.testing.assert_array_equal(got[f], want[f], err_msg=f)
+    for pl in (dcur, dref):
+        c.plane_free(pl)
+
+
+def test_full_search_flat_ties_pick_first_position():
+    """me.rs:1501: strict `<` => first scanned position wins on a flat reference."""
+    W, H, PAD = 128, 96, 96
+    cur = np.full((H, W), 7, np.uint8)
+    ref = np.full((H, W), 9, np.uint8)
+    ocur, dcur = G.both_planes(cur, PAD)
+    oref, dref = G.both_planes(ref, PAD)
+    blocks = G.grid_blocks(W, H, 16, 16)
+    want = O.full_search_blocks(ocur, oref, blocks, 16, 16, 48, 16, 4, 0)
+    c = G.ctx()
+    d_best = G.dev_empty(16 * len(blocks))
+    c.me_full_search_dev(dcur, dref, G.to_dev(blocks), len(blocks), B.me_params(16, 16, W, H, 0),
+                         48, 16, 4, d_best)
+    c.synchronize()
+    got = G.from_dev(d_best, B.ME_RESULT_DTYPE)[:len(blocks)]
+    for f in ("cost", "sad", "mv_row", "mv_col"):
+        np.testing.assert_array_equal(got[f], want[f], err_msg=f)
+    assert (got["sad"] == 512).all()
+
+
+def test_1080p_properties():
+    """Full BASELINE size: size-independent properties instead of a full oracle pass.
+    (1) cur == ref shifted by a known vector => full search finds it with sad 0;
+    (2) zero-mv candidates on identical planes => sad 0;
+    (3) a 1/64 sample of candidates equals the oracle."""
+    W, H, PAD = 1920, 1080, 96
+    rng = np.random.default_rng(0)
+    base = rng.integers(0, 256, (H + 2 * PAD, W + 2 * PAD), dtype=np.uint8)
+    dx, dy = 8, -4
+    ref_full = base
+    cur_full = np.roll(base, (-dy, -dx), axis=(0, 1))   # cur(x,y) = ref(x+dx, y+dy)
+    c = G.ctx()
+    L = c.L
+    # device planes carrying their own (non-replicated) border: upload the padded arrays whole
+    def dev_plane(full):
+        p = B.Plane()
+        c.check(L.b200_plane_alloc(c.h, W + 2 * PAD, H + 2 * PAD, 0, 1, C.byref(p)))
+        c.check(L.b200_plane_upload(c.h, C.byref(p), full.ctypes.data, full.strides[0]))
+        q = B.Plane()
+        q.data = p.data + PAD * p.stride + PAD
+        q.stride, q.width, q.height, q.pad, q.bpp, q.alloc = p.stride, W, H, PAD, 1, None
+        return p, q
+    pc, dcur = dev_plane(cur_full)
+    pr, dref = dev_plane(ref_full)
+    blocks = G.grid_blocks(W, H, 16, 16)
+    # keep blocks whose displaced window stays clear of the wrap-around of np.roll
+    inner = (blocks["x"] >= 64) & (blocks["x"] < W - 80) & (blocks["y"] >= 64) & (blocks["y"] < H - 80)
+    d_best = G.dev_empty(16 * len(blocks))
+    p = B.me_params(16, 16, W, H, 0)
+    c.me_full_search_dev(dcur, dref, G.to_dev(blocks), len(blocks), p, 48, 16, 4, d_best)
+    c.synchronize()
+    got = G.from_dev(d_best, B.ME_RESULT_DTYPE)[:len(blocks)]
+    assert (got["sad"][inner] == 0).all()
+    assert (got["mv_col"][inner] == 8 * dx).all() and (got["mv_row"][inner] == 8 * dy).all()
+    # (2)
+    cands = np.zeros(len(blocks), B.CAND_DTYPE)
+    cands["block"] = np.arange(len(blocks))
+    d_sad = G.dev_empty(4 * len(cands))
+    c.me_candidates_dev(dref, dref, G.to_dev(blocks), len(blocks), G.to_dev(cands), len(cands), p,
+                        None, None, d_sad, None, None)
+    c.synchronize()
+    assert (G.from_dev(d_sad, np.uint32)[:len(cands)] == 0).all()
+    # (3)
+    cands, offs = G.random_cands(len(blocks), 64, 48, seed=2, jitter=False)
+    d_sad = G.dev_empty(4 * len(cands))
+    p = B.me_params(16, 16, W, H, 0, window_hint_px=48)
+    c.me_candidates_dev(dcur, dref, G.to_dev(blocks), len(blocks), G.to_dev(cands), len(cands), p,
+                        G.to_dev(offs), None, d_sad, None, None)
+    c.synchronize()
+    got_sad = G.from_dev(d_sad, np.uint32)[:len(cands)]
+    ocur = O.Plane(W, H, PAD)
+    ocur.data[:] = cur_full
+    oref = O.Plane(W, H, PAD)
+    oref.data[:] = ref_full
+    sel = np.arange(0, len(cands), 64)
+    want, _ = O.fullpel_candidates(ocur, oref, blocks, cands[sel], 16, 16, False, 0, want_cost=False)
+    np.testing.assert_array_equal(got_sad[sel], want)
+    # checksum-of-everything against a full (threaded) oracle pass: 522k candidates, ~1 s of CPU
+    want_all, _ = O.fullpel_candidates(ocur, oref, blocks, cands, 16, 16, False, 0, want_cost=False)
+    np.testing.assert_array_equal(got_sad, want_all)
+    c.check(L.b200_plane_free(c.h, C.byref(pc)))
+    c.check(L.b200_plane_free(c.h, C.byref(pr)))
