@@ -7,10 +7,10 @@
 //
 // Kernels
 //   me_cand_generic<T>      any w x h <= 128, u8/u16, SAD or SATD.  One warp per candidate.
-//   me_cand_smem_u8<W,H>    8-bit SAD fast path: one CTA per block, the bounding window of the
-//                           block's candidates is staged once in shared memory with 16-byte
-//                           loads, then one thread per candidate walks it with aligned LDS.32 +
-//                           funnel shift + VABSDIFF4-accumulate.  Fused cost + first-min argmin.
+//   me_cand_group_u8<W,H,SATD>  8-bit fast path: a CTA takes a group of consecutive blocks, stages
+//                           one shared-memory window covering all their candidates with 16-byte
+//                           loads, then evaluates candidates from smem (SAD: VABSDIFF4.ACC;
+//                           SATD: IDP.4A Hadamard rows + butterflies).  Fused cost + argmin.
 //   me_best_from_cost       segmented first-min argmin over a CSR candidate list.
 //   me_full_search_generic<T>  any size / depth, one CTA per block, warp per position.
 //   me_full_search_u8<W,H>  8-bit fast path: window staged in smem so that every candidate
@@ -291,146 +291,367 @@ __device__ __forceinline__ uint32_t row_sad_u8(const uint32_t *__restrict__ wrow
 }
 
 // Stage `rows` x `row_bytes` (row_bytes multiple of 16, src 16-byte aligned) into smem.
+// Incremental (row, vec) stepping: no per-element integer division.
 __device__ __forceinline__ void stage_window(uint32_t *smem, int pitch_words, const uint8_t *src,
                                              long long src_stride, int rows, int row_bytes) {
-  const int vec_per_row = row_bytes >> 4;
-  for (int i = threadIdx.x; i < rows * vec_per_row; i += blockDim.x) {
-    const int y = i / vec_per_row, v = i - y * vec_per_row;
+  const int vpr = row_bytes >> 4;
+  const int nthr = blockDim.x;
+  int y = threadIdx.x / vpr, v = threadIdx.x - y * vpr;
+  const int dy = nthr / vpr, dv = nthr - dy * vpr;
+  while (y < rows) {
     const uint4 q = __ldg((const uint4 *)(src + (long long)y * src_stride) + v);
     *(uint4 *)(smem + y * pitch_words + v * 4) = q;
+    y += dy;
+    v += dv;
+    if (v >= vpr) {
+      v -= vpr;
+      y++;
+    }
   }
 }
 
-constexpr int kCandSmemBytes = 96 * 1024;  // dynamic smem budget for the candidate window
+// ---- SATD of one S x S chunk straight from packed bytes (dist.rs:55-149 restated for dp4a).
+// The 2-D Hadamard is exact integer and separable, and only sum|coeff| is consumed, so the
+// pass order (reference: vertical then horizontal) and the order of outputs inside a vector
+// do not change the result.  Horizontal pass: rows of 4 packed u8 times the +-1 rows of H4 as
+// signed-byte dot products (IDP.4A), org minus ref folded in by negating the coefficients.
+// d = sum_i a.u8[i] * b.s8[i] + c   (IDP.4A.U8.S8)
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ void h4_rows_dp4a(uint32_t o, uint32_t r, int (&out)[4]) {
+  out[0] = dp4a_us(o, 0x01010101u, dp4a_us(r, 0xFFFFFFFFu, 0));  // + + + +
+  out[1] = dp4a_us(o, 0xFF01FF01u, dp4a_us(r, 0x01FF01FFu, 0));  // + - + -
+  out[2] = dp4a_us(o, 0xFFFF0101u, dp4a_us(r, 0x0101FFFFu, 0));  // + + - -
+  out[3] = dp4a_us(o, 0x01FFFF01u, dp4a_us(r, 0xFF0101FFu, 0));  // + - - +
+}
 
-template <int W, int H>
-__global__ void __launch_bounds__(128) me_cand_smem_u8(MeArgs a) {
-  extern __shared__ __align__(16) uint32_t smem[];
-  __shared__ uint32_t s_org[H * W / 4];
-  __shared__ int s_box[4];
-  __shared__ Best s_red[32];
+__device__ __forceinline__ uint32_t abs_acc(int v, uint32_t acc) { return acc + (uint32_t)abs(v); }
 
-  for (size_t blk = blockIdx.x; blk < a.nblocks; blk += gridDim.x) {
-    const uint32_t lo = a.cand_offsets[blk], hi = a.cand_offsets[blk + 1];
-    const b200_block b = a.blocks[blk];
-    const MvRange r = b200_mv_range(a.w_in_b, a.h_in_b, b.x / MI_SIZE, b.y / MI_SIZE, W, H);
-    __syncthreads();  // previous iteration's smem readers are done
-    if (threadIdx.x == 0) {
-      s_box[0] = INT_MAX;
-      s_box[1] = INT_MIN;
-      s_box[2] = INT_MAX;
-      s_box[3] = INT_MIN;
+// wrow: window row 0 of the chunk; word0/sh locate the chunk's first pixel; orow: org chunk
+// row 0 (word aligned), org pitch in words.
+template <int S>
+__device__ __forceinline__ uint32_t chunk_satd_u8(const uint32_t *wrow, int pitch_words, int word0,
+                                                  int sh, const uint32_t *orow, int org_pitch) {
+  if (S == 4) {
+    int t[4][4];
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+      const uint32_t *w = wrow + y * pitch_words + word0;
+      const uint32_t r = __funnelshift_r(w[0], w[1], sh);
+      h4_rows_dp4a(orow[y * org_pitch], r, t[y]);
     }
-    // org block -> smem (packed words); cur rows may be unaligned, go through bytes
-    {
-      const uint8_t *o = px<uint8_t>(a.cur, b.x, b.y);
-      for (int i = threadIdx.x; i < H * W / 4; i += blockDim.x) {
-        const int y = i / (W / 4), k = i - y * (W / 4);
-        const uint8_t *p = o + (long long)y * a.cur.stride + 4 * k;
-        s_org[i] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) |
-                   ((uint32_t)p[3] << 24);
+    uint32_t s = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      int a0 = t[0][c], a1 = t[1][c], a2 = t[2][c], a3 = t[3][c];
+      bfly(a0, a1);
+      bfly(a2, a3);
+      bfly(a0, a2);
+      bfly(a1, a3);
+      s = abs_acc(a0, abs_acc(a1, abs_acc(a2, abs_acc(a3, s))));
+    }
+    return s;
+  } else {
+    int t[8][8];
+#pragma unroll
+    for (int y = 0; y < 8; y++) {
+      const uint32_t *w = wrow + y * pitch_words + word0;
+      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+      const uint32_t r0 = __funnelshift_r(w0, w1, sh), r1 = __funnelshift_r(w1, w2, sh);
+      int A[4], B[4];
+      h4_rows_dp4a(orow[y * org_pitch], r0, A);
+      h4_rows_dp4a(orow[y * org_pitch + 1], r1, B);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        t[y][j] = A[j] + B[j];
+        t[y][j + 4] = A[j] - B[j];
       }
     }
-    __syncthreads();
-    // bounding box of the in-range candidates (ref px coordinates of the block's top-left)
-    int bx0 = INT_MAX, bx1 = INT_MIN, by0 = INT_MAX, by1 = INT_MIN;
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-      const b200_cand c = a.cands[i];
-      if (c.mv_col < r.x_min || c.mv_col > r.x_max || c.mv_row < r.y_min || c.mv_row > r.y_max)
-        continue;
-      const int rx = b.x + c.mv_col / 8, ry = b.y + c.mv_row / 8;
-      bx0 = min(bx0, rx), bx1 = max(bx1, rx), by0 = min(by0, ry), by1 = max(by1, ry);
-    }
+    uint32_t s = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
-      bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
-      by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
-      by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+    for (int c = 0; c < 8; c++) {
+      int a[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) a[k] = t[k][c];
+      bfly(a[0], a[1]);
+      bfly(a[2], a[3]);
+      bfly(a[4], a[5]);
+      bfly(a[6], a[7]);
+      bfly(a[0], a[2]);
+      bfly(a[1], a[3]);
+      bfly(a[4], a[6]);
+      bfly(a[5], a[7]);
+      bfly(a[0], a[4]);
+      bfly(a[1], a[5]);
+      bfly(a[2], a[6]);
+      bfly(a[3], a[7]);
+#pragma unroll
+      for (int k = 0; k < 8; k++) s = abs_acc(a[k], s);
     }
-    if ((threadIdx.x & 31) == 0 && bx0 != INT_MAX) {
-      atomicMin(&s_box[0], bx0);
-      atomicMax(&s_box[1], bx1);
-      atomicMin(&s_box[2], by0);
-      atomicMax(&s_box[3], by1);
-    }
-    __syncthreads();
-    // 16-byte aligned column, whatever the alignment of pixel (0,0) (row pitch is a multiple
-    // of 16 bytes, checked on the host)
-    const int mis = (int)((uintptr_t)a.ref.data & 15);
-    const int wx0 = s_box[0] == INT_MAX ? 0 : (((s_box[0] + mis) & ~15) - mis);
-    const int wy0 = s_box[2];
-    const int have = s_box[0] != INT_MAX;
-    // +4 bytes: the funnel shift reads one word past the last pixel
-    const int row_bytes = have ? (int)b200_align_up((size_t)(s_box[1] + W + 4 - wx0), 16) : 0;
-    const int rows = have ? s_box[3] - wy0 + H : 0;
-    // pitch in words: odd multiple of 4 words keeps 16-byte alignment and spreads rows over banks
-    const int pitch_words = (row_bytes >> 2) | 4;
-    const bool staged = have && (size_t)rows * pitch_words * 4 <= (size_t)a.smem_bytes;
-    if (staged)
-      stage_window(smem, pitch_words, px<uint8_t>(a.ref, wx0, wy0), a.ref.stride, rows, row_bytes);
-    __syncthreads();
+    return s;
+  }
+}
 
-    int p0r = 0, p0c = 0, p1r = 0, p1c = 0;
-    if (a.pmv) {
-      const short *p = a.pmv + 4 * blk;
-      p0r = p[0], p0c = p[1], p1r = p[2], p1c = p[3];
-    }
-    Best best{kEmptyCost, 0xffffffffu};
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-      const b200_cand c = a.cands[i];
-      uint32_t sad = kEmptySad;
-      unsigned long long cost = kEmptyCost;
-      if (!(c.mv_col < r.x_min || c.mv_col > r.x_max || c.mv_row < r.y_min ||
-            c.mv_row > r.y_max)) {
-        const int rx = b.x + c.mv_col / 8, ry = b.y + c.mv_row / 8;
-        uint32_t acc = 0;
-        if (staged) {
-          const int off = rx - wx0;
-          const int word0 = off >> 2, sh = (off & 3) * 8;
-          const uint32_t *wrow = smem + (ry - wy0) * pitch_words;
-#pragma unroll 4
-          for (int y = 0; y < H; y++)
-            acc = row_sad_u8<W>(wrow + y * pitch_words, word0, sh, s_org + y * (W / 4), acc);
-        } else {  // window too large for smem: byte loads straight from L1/L2
-          const uint8_t *rp = px<uint8_t>(a.ref, rx, ry);
-          for (int y = 0; y < H; y++) {
-            const uint8_t *q = rp + (long long)y * a.ref.stride;
-            const uint8_t *o = (const uint8_t *)(s_org + y * (W / 4));
+constexpr int kCandSmemBytes = 160 * 1024;  // upper bound of the dynamic smem (window + org)
+constexpr int kMaxGroup = 8;                // blocks sharing one staged window
+constexpr int kKeyIdxBits = 24;             // packed argmin key: cost << 24 | index in block
+
+// cost < 2^39 always (256*sad <= 2^34 for 128x128x12 bit, rate <= 61, lambda < 2^32), so
+// (cost << 24 | idx) orders exactly like (cost, idx): first minimum in list order.
+__device__ __forceinline__ unsigned long long pack_key(unsigned long long cost, uint32_t idx) {
+  return cost == kEmptyCost ? ~0ull : ((cost << kKeyIdxBits) | idx);
+}
+
+// 8-bit candidate-list kernel.  A CTA takes `G` consecutive blocks of the (block-grouped)
+// candidate list, stages ONE window covering all their in-range candidates (neighbouring
+// blocks overlap almost completely) plus their org pixels, then evaluates candidates from
+// shared memory: SAD = one thread per candidate (aligned LDS.32 + funnel shift + VABSDIFF4.ACC),
+// SATD = TPC threads per candidate, one Hadamard chunk each.  Cost (me.rs:1455-1460) and the
+// per-block first-minimum (me.rs:898) are fused: REDUX over a packed (cost, index) key, one
+// shared atomicMin per warp.  Windows that do not fit fall back to one block per pass, and a
+// single block that still does not fit reads the reference plane directly.
+template <int W, int H, bool SATD>
+__global__ void __launch_bounds__(256) me_cand_group_u8(MeArgs a, int G) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ int s_box[4];
+  __shared__ unsigned long long s_key[kMaxGroup];
+  __shared__ b200_block s_blk[kMaxGroup];
+  __shared__ MvRange s_rng[kMaxGroup];
+  __shared__ uint32_t s_off[kMaxGroup + 1];
+  __shared__ short s_pmv[kMaxGroup][4];
+
+  constexpr int S = (W < 8 || H < 8) ? 4 : 8;                 // dist.rs:166
+  constexpr int NCH = SATD ? (W / S) * (H / S) : 1;           // chunks per candidate
+  constexpr int TPC = NCH < 32 ? NCH : 32;                    // threads per candidate
+  constexpr int ORGW = H * W / 4;                             // org words per block
+  const int nthr = blockDim.x;
+  const int lane = threadIdx.x & 31;
+  uint32_t *const s_org = smem;                               // [G][ORGW]
+  uint32_t *const win = smem + G * ORGW;
+  const int win_bytes = a.smem_bytes - G * ORGW * 4;
+  const size_t ngroups = (a.nblocks + G - 1) / G;
+
+  for (size_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const size_t gb0 = grp * G, gb1 = min(gb0 + (size_t)G, a.nblocks);
+    // pass 0 tries the whole group; if its window does not fit, passes 1.. take one block each
+    bool whole = true;
+    size_t b0 = gb0, b1 = gb1;
+    while (b0 < gb1) {
+      const int nb = (int)(b1 - b0);
+      __syncthreads();  // previous pass is done with shared memory
+      if (threadIdx.x < nb) {
+        const size_t blk = b0 + threadIdx.x;
+        const b200_block b = a.blocks[blk];
+        s_blk[threadIdx.x] = b;
+        s_rng[threadIdx.x] =
+            b200_mv_range(a.w_in_b, a.h_in_b, b.x / MI_SIZE, b.y / MI_SIZE, W, H);
+        s_key[threadIdx.x] = ~0ull;
+        s_off[threadIdx.x] = a.cand_offsets[blk];
+        if (threadIdx.x == nb - 1) s_off[nb] = a.cand_offsets[blk + 1];
 #pragma unroll
-            for (int x = 0; x < W; x++) acc += (uint32_t)abs((int)q[x] - (int)o[x]);
+        for (int k = 0; k < 4; k++) s_pmv[threadIdx.x][k] = a.pmv ? a.pmv[4 * blk + k] : (short)0;
+      }
+      if (threadIdx.x == 32) {
+        s_box[0] = INT_MAX;
+        s_box[1] = INT_MIN;
+        s_box[2] = INT_MAX;
+        s_box[3] = INT_MIN;
+      }
+      __syncthreads();
+      const uint32_t lo = s_off[0], hi = s_off[nb];
+      // ---- bounding box of the in-range candidates (reference coordinates of block top-left)
+      {
+        int bx0 = INT_MAX, bx1 = INT_MIN, by0 = INT_MAX, by1 = INT_MIN;
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += nthr) {
+          const b200_cand c = a.cands[i];
+          const int lb = (int)(c.block - (uint32_t)b0);
+          const MvRange r = s_rng[lb];
+          if (c.mv_col < r.x_min || c.mv_col > r.x_max || c.mv_row < r.y_min || c.mv_row > r.y_max)
+            continue;
+          const int rx = s_blk[lb].x + c.mv_col / 8, ry = s_blk[lb].y + c.mv_row / 8;
+          bx0 = min(bx0, rx), bx1 = max(bx1, rx), by0 = min(by0, ry), by1 = max(by1, ry);
+        }
+        bx0 = __reduce_min_sync(0xffffffffu, bx0);
+        bx1 = __reduce_max_sync(0xffffffffu, bx1);
+        by0 = __reduce_min_sync(0xffffffffu, by0);
+        by1 = __reduce_max_sync(0xffffffffu, by1);
+        if (lane == 0 && bx0 != INT_MAX) {
+          atomicMin(&s_box[0], bx0);
+          atomicMax(&s_box[1], bx1);
+          atomicMin(&s_box[2], by0);
+          atomicMax(&s_box[3], by1);
+        }
+      }
+      __syncthreads();
+      const bool have = s_box[0] != INT_MAX;
+      // 16-byte aligned window origin whatever the alignment of pixel (0,0)
+      const int mis = (int)((uintptr_t)a.ref.data & 15);
+      const int wx0 = have ? (((s_box[0] + mis) & ~15) - mis) : 0;
+      const int wy0 = have ? s_box[2] : 0;
+      // +4 bytes: the funnel shift reads one word past the last pixel
+      const int row_bytes = have ? (int)b200_align_up((size_t)(s_box[1] + W + 4 - wx0), 16) : 0;
+      const int rows = have ? s_box[3] - wy0 + H : 0;
+      const int pitch_words = (row_bytes >> 2) | 4;  // 16-byte aligned rows, odd multiple of 4 words
+      const bool fits = (long long)rows * pitch_words * 4 <= (long long)win_bytes;
+      if (!fits && nb > 1) {  // uniform: derived from shared state
+        whole = false;
+        b1 = b0 + 1;
+        continue;
+      }
+      const bool staged = have && fits;
+      if (staged)
+        stage_window(win, pitch_words, px<uint8_t>(a.ref, wx0, wy0), a.ref.stride, rows, row_bytes);
+      // org blocks -> packed words
+      for (int i = threadIdx.x; i < nb * ORGW; i += nthr) {
+        const int lb = i / ORGW, wi = i - lb * ORGW;
+        const int y = wi / (W / 4), k = wi - y * (W / 4);
+        const uint8_t *p = px<uint8_t>(a.cur, s_blk[lb].x + 4 * k, s_blk[lb].y + y);
+        uint32_t v;
+        if (((uintptr_t)p & 3) == 0)
+          v = __ldg((const uint32_t *)p);
+        else
+          v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+        s_org[i] = v;
+      }
+      __syncthreads();
+
+      // ---- evaluate: each slot of TPC threads takes candidates lo+slot, lo+slot+nslots, ...
+      const int nslots = nthr / TPC;
+      const int slot = threadIdx.x / TPC, sub = threadIdx.x - slot * TPC;
+      const uint32_t ntrip = (hi - lo + nslots - 1) / nslots;
+      for (uint32_t t = 0; t < ntrip; t++) {
+        const uint32_t i = lo + t * nslots + slot;
+        const bool valid = i < hi;
+        uint32_t sad = kEmptySad;
+        unsigned long long cost = kEmptyCost;
+        int lb = -1;
+        b200_cand c;
+        c.block = 0;
+        c.mv_row = 0;
+        c.mv_col = 0;
+        bool inr = false;
+        if (valid) {
+          c = a.cands[i];
+          lb = (int)(c.block - (uint32_t)b0);
+          const MvRange r = s_rng[lb];
+          inr = !(c.mv_col < r.x_min || c.mv_col > r.x_max || c.mv_row < r.y_min ||
+                  c.mv_row > r.y_max);
+        }
+        uint32_t acc = 0;
+        if (inr) {
+          const int rx = s_blk[lb].x + c.mv_col / 8, ry = s_blk[lb].y + c.mv_row / 8;
+          const uint32_t *org = s_org + lb * ORGW;
+          if (staged) {
+            const int off = rx - wx0;
+            const uint32_t *wrow = win + (ry - wy0) * pitch_words;
+            if (!SATD) {
+              const int word0 = off >> 2, sh = (off & 3) * 8;
+#pragma unroll 4
+              for (int y = 0; y < H; y++)
+                acc = row_sad_u8<W>(wrow + y * pitch_words, word0, sh, org + y * (W / 4), acc);
+            } else {
+              for (int ch = sub; ch < NCH; ch += TPC) {
+                const int cy = (ch / (W / S)) * S, cx = (ch % (W / S)) * S;
+                const int o2 = off + cx;
+                acc += chunk_satd_u8<S>(wrow + cy * pitch_words, pitch_words, o2 >> 2, (o2 & 3) * 8,
+                                        org + cy * (W / 4) + cx / 4, W / 4);
+              }
+            }
+          } else {  // window too large for shared memory: bytes straight from L1/L2
+            const uint8_t *rp = px<uint8_t>(a.ref, rx, ry);
+            if (!SATD) {
+              for (int y = 0; y < H; y++) {
+                const uint8_t *q = rp + (long long)y * a.ref.stride;
+                const uint8_t *o = (const uint8_t *)(org + y * (W / 4));
+#pragma unroll
+                for (int x = 0; x < W; x++) acc += (uint32_t)abs((int)q[x] - (int)o[x]);
+              }
+            } else {
+              for (int ch = sub; ch < NCH; ch += TPC) {
+                const int cy = (ch / (W / S)) * S, cx = (ch % (W / S)) * S;
+                int d[S * S];
+#pragma unroll
+                for (int y = 0; y < S; y++)
+#pragma unroll
+                  for (int x = 0; x < S; x++)
+                    d[y * S + x] = (int)((const uint8_t *)(org + (cy + y) * (W / 4)))[cx + x] -
+                                   (int)rp[(long long)(cy + y) * a.ref.stride + cx + x];
+                if (S == 4)
+                  acc += hadamard4x4_abs_sum(*(int(*)[16])d);
+                else
+                  acc += hadamard8x8_abs_sum(*(int(*)[64])d);
+              }
+            }
           }
         }
-        sad = acc;
-        cost = b200_mv_cost(sad, c.mv_row, c.mv_col, p0r, p0c, p1r, p1c, a.lambda, a.allow_hp);
-      }
-      if (a.out_sad) a.out_sad[i] = sad;
-      if (a.out_cost) a.out_cost[i] = cost;
-      best = best_min(best, Best{cost, i});
-    }
-    if (a.out_best) {
-      // sad/mv of the winner: recompute from the winner's index by its owner is awkward;
-      // keep (cost, idx) and let thread 0 re-derive mv from cands[] and sad from the cost.
-      best = block_best(best, s_red);
-      if (threadIdx.x == 0) {
-        b200_me_result res;
-        res.cost = kEmptyCost;
-        res.sad = kEmptySad;
-        res.mv_row = 0;
-        res.mv_col = 0;
-        if (best.cost != kEmptyCost) {
-          const b200_cand c = a.cands[best.idx];
-          // cost = 256*sad + rate*lambda  =>  sad = (cost - rate*lambda) / 256
-          uint32_t r1 = b200_mv_rate(c.mv_row, c.mv_col, p0r, p0c, a.allow_hp);
-          uint32_t r2 = b200_mv_rate(c.mv_row, c.mv_col, p1r, p1c, a.allow_hp) + 1;
-          uint32_t rate = r1 < r2 ? r1 : r2;
-          res.cost = best.cost;
-          res.sad = (uint32_t)((best.cost - (unsigned long long)rate * a.lambda) >> 8);
-          res.mv_row = c.mv_row;
-          res.mv_col = c.mv_col;
+        if (SATD) {
+#pragma unroll
+          for (int o = TPC >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+          constexpr int ln = S == 4 ? 2 : 3;
+          acc = (acc + ((1u << ln) >> 1)) >> ln;  // dist.rs:219-220, single final rounding
         }
-        a.out_best[blk] = res;
+        unsigned long long key = ~0ull;
+        if (inr && sub == 0) {
+          sad = acc;
+          cost = b200_mv_cost(sad, c.mv_row, c.mv_col, s_pmv[lb][0], s_pmv[lb][1], s_pmv[lb][2],
+                              s_pmv[lb][3], a.lambda, a.allow_hp);
+          key = pack_key(cost, i - s_off[lb]);
+        }
+        if (valid && sub == 0) {
+          if (a.out_sad) a.out_sad[i] = sad;
+          if (a.out_cost) a.out_cost[i] = cost;
+        }
+        if (a.out_best) {
+          // warp argmin over the packed key; fast path when the warp holds a single block
+          const int lb0 = __shfl_sync(0xffffffffu, lb, 0);
+          const bool uni = __all_sync(0xffffffffu, lb == lb0 || key == ~0ull);
+          if (uni) {
+            const uint32_t khi = (uint32_t)(key >> 32);
+            const uint32_t mh = __reduce_min_sync(0xffffffffu, khi);
+            const uint32_t klo = khi == mh ? (uint32_t)key : 0xffffffffu;
+            const uint32_t ml = __reduce_min_sync(0xffffffffu, klo);
+            // the owner block: any lane with a real key; lanes with lb == -1 carry ~0 keys
+            const int owner = __reduce_max_sync(0xffffffffu, key == ~0ull ? -1 : lb);
+            if (lane == 0 && owner >= 0)
+              atomicMin(&s_key[owner], ((unsigned long long)mh << 32) | ml);
+          } else if (key != ~0ull) {
+            atomicMin(&s_key[lb], key);
+          }
+        }
       }
+      if (a.out_best) {
+        __syncthreads();
+        if (threadIdx.x < nb) {
+          const int lb = threadIdx.x;
+          const unsigned long long key = s_key[lb];
+          b200_me_result res;
+          res.cost = kEmptyCost;
+          res.sad = kEmptySad;
+          res.mv_row = 0;
+          res.mv_col = 0;  // MotionSearchResult::empty(), me.rs:111-116
+          if (key != ~0ull) {
+            const uint32_t idx = (uint32_t)(key & ((1u << kKeyIdxBits) - 1));
+            const unsigned long long cost = key >> kKeyIdxBits;
+            const b200_cand c = a.cands[s_off[lb] + idx];
+            const uint32_t r1 = b200_mv_rate(c.mv_row, c.mv_col, s_pmv[lb][0], s_pmv[lb][1], a.allow_hp);
+            const uint32_t r2 =
+                b200_mv_rate(c.mv_row, c.mv_col, s_pmv[lb][2], s_pmv[lb][3], a.allow_hp) + 1;
+            const uint32_t rate = r1 < r2 ? r1 : r2;
+            res.cost = cost;
+            res.sad = (uint32_t)((cost - (unsigned long long)rate * a.lambda) >> 8);
+            res.mv_row = c.mv_row;
+            res.mv_col = c.mv_col;
+          }
+          a.out_best[b0 + lb] = res;
+        }
+      }
+      // next pass
+      if (whole) break;
+      b0 = b1;
+      b1 = b0 + 1;
     }
   }
 }
@@ -623,24 +844,32 @@ __global__ void __launch_bounds__(256) me_full_search_u8(FsArgs a) {
 }
 
 // ---------------------------------------------------------------- host-side dispatch
-template <int W, int H>
-int launch_cand_smem(b200_ctx *ctx, MeArgs a, int window_hint_px) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA(ctx, cudaFuncSetAttribute(me_cand_smem_u8<W, H>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kCandSmemBytes));
-    attr_set = true;
-  }
-  // Shared window sized from the caller's search-range hint (blocks whose candidate bounding
-  // box does not fit fall back to direct loads inside the kernel).
+template <int W, int H, bool SATD>
+int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px) {
+  static int attr_bytes = 0;
+  // Group size: enough candidates to fill a CTA, bounded by the org tile budget.
+  const size_t avg = a.nblocks ? a.ncands / a.nblocks : 0;
+  constexpr int S = (W < 8 || H < 8) ? 4 : 8;
+  constexpr int NCH = SATD ? (W / S) * (H / S) : 1;
+  constexpr int TPC = NCH < 32 ? NCH : 32;
+  const int threads = 256;
+  int G = (int)std::min<size_t>(kMaxGroup, std::max<size_t>(1, (threads / TPC) / std::max<size_t>(avg, 1)));
+  G = std::max(1, std::min(G, 16384 / (W * H)));  // org tiles <= 16 KB
+  // Shared window sized from the caller's search-range hint (+ the group's extent along x);
+  // groups/blocks that do not fit degrade inside the kernel, never fail.
   const int hint = window_hint_px > 0 ? window_hint_px : 32;
-  size_t pitch = (b200_align_up((size_t)(2 * hint + W + 4 + 15), 16) >> 2) | 4;
-  size_t smem = pitch * 4 * (size_t)(2 * hint + H);
-  smem = std::min<size_t>(std::max<size_t>(smem, 8 * 1024), (size_t)kCandSmemBytes);
+  const size_t pitch = (b200_align_up((size_t)(2 * hint + G * W + 4 + 15), 16) >> 2) | 4;
+  size_t smem = pitch * 4 * (size_t)(2 * hint + H) + (size_t)G * W * H;
+  smem = std::min<size_t>(std::max<size_t>(smem, 16 * 1024), (size_t)kCandSmemBytes);
+  if ((int)smem > attr_bytes) {
+    B200_CUDA(ctx, cudaFuncSetAttribute(me_cand_group_u8<W, H, SATD>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_bytes = (int)smem;
+  }
   a.smem_bytes = (int)smem;
-  const int grid = (int)std::min<size_t>(a.nblocks, (size_t)ctx->num_sms * 64);
-  me_cand_smem_u8<W, H><<<grid, 128, smem, ctx->stream>>>(a);
+  const size_t ngroups = (a.nblocks + G - 1) / G;
+  const int grid = (int)std::min<size_t>(ngroups, (size_t)ctx->num_sms * 32);
+  me_cand_group_u8<W, H, SATD><<<grid, threads, smem, ctx->stream>>>(a, G);
   B200_LAUNCH_CHECK(ctx);
   return B200_OK;
 }
@@ -715,17 +944,26 @@ extern "C" int b200_me_candidates_dev(b200_ctx *ctx, const b200_plane *cur, cons
   a.use_satd = p->use_satd;
   a.smem_bytes = 0;
 
-  // Fast path: 8-bit SAD, candidates grouped by block, canonical block size.
-  if (cur->bpp == 1 && !p->use_satd && d_cand_offsets && nblocks > 0 && (ref->stride & 15) == 0) {
-#define B200_CASE(W_, H_) \
-  if (p->w == W_ && p->h == H_) return launch_cand_smem<W_, H_>(ctx, a, p->window_hint_px);
+  // Fast path: 8-bit, candidates grouped by block (CSR), block sizes up to 64x64.
+  if (cur->bpp == 1 && d_cand_offsets && nblocks > 0 && (ref->stride & 15) == 0 &&
+      ncands <= (1ull << kKeyIdxBits)) {
+#define B200_CASE(W_, H_)                                                            \
+  if (p->w == W_ && p->h == H_)                                                      \
+    return p->use_satd ? launch_cand_group<W_, H_, true>(ctx, a, p->window_hint_px)  \
+                       : launch_cand_group<W_, H_, false>(ctx, a, p->window_hint_px);
+    B200_CASE(4, 4)
     B200_CASE(8, 8)
     B200_CASE(16, 16)
     B200_CASE(32, 32)
+    B200_CASE(64, 64)
+    B200_CASE(4, 8)
+    B200_CASE(8, 4)
     B200_CASE(8, 16)
     B200_CASE(16, 8)
     B200_CASE(16, 32)
     B200_CASE(32, 16)
+    B200_CASE(32, 64)
+    B200_CASE(64, 32)
 #undef B200_CASE
   }
 
