@@ -186,6 +186,29 @@ int b200_me_full_search_batch(b200_ctx *ctx, const b200_host_plane *cur,
                               size_t nblocks, const b200_me_params *params, int range_x,
                               int range_y, int step, b200_me_result *best);
 
+/* ------------------------------------------------ forward transform (transform/forward.rs)
+ * The reference has no extern-C symbol here: the boundary is the generic Rust fn
+ *   forward_transform<T: Coefficient>(input: &[i16], output: &mut [MaybeUninit<T>],
+ *                                     stride, tx_size: TxSize, tx_type: TxType, bd, cpu)
+ * (asm/x86/transform/forward.rs:444-447).  tx_size / tx_type are the enum discriminants
+ * (transform/mod.rs:56-74 and :101-123); coeff_is_i32 selects T::Coeff (0: i16 for 8-bit
+ * pixels, 1: i32 for HBD).  Output order is the reference's: column-major within 32x32
+ * chunks (forward.rs:135-159).  Invalid (size, type) pairs: the reference panics
+ * (forward.rs:75); the status-returning forms return B200_ERR_ARG, the per-call form aborts. */
+int b200_valid_av1_transform(int tx_size, int tx_type);
+int b200_tx_width(int tx_size);
+int b200_tx_height(int tx_size);
+void b200_forward_transform(const int16_t *input, void *output, size_t stride, int tx_size,
+                            int tx_type, int bd, int coeff_is_i32);
+/* Batched: block i reads input[i*in_block_stride + r*in_row_stride + c] and writes
+ * output[i*w*h ...].  `_dev`: device pointers, asynchronous on the ctx stream. */
+int b200_fwd_txfm_dev(b200_ctx *ctx, const int16_t *d_input, size_t in_block_stride,
+                      size_t in_row_stride, void *d_output, size_t nblocks, int tx_size,
+                      int tx_type, int bd, int coeff_is_i32);
+int b200_fwd_txfm_batch(b200_ctx *ctx, const int16_t *input, size_t in_block_stride,
+                        size_t in_row_stride, void *output, size_t nblocks, int tx_size,
+                        int tx_type, int bd, int coeff_is_i32);
+
 #ifdef __cplusplus
 }
 #endif

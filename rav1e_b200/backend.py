@@ -101,6 +101,13 @@ def lib():
     L.b200_me_full_search_dev.argtypes = [vp, pp, pp, vp, sz, pmp, i32, i32, i32, vp]
     L.b200_me_candidates_batch.argtypes = [vp, php, php, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
     L.b200_me_full_search_batch.argtypes = [vp, php, php, vp, sz, pmp, i32, i32, i32, vp]
+    L.b200_valid_av1_transform.argtypes = [i32, i32]
+    L.b200_tx_width.argtypes = [i32]
+    L.b200_tx_height.argtypes = [i32]
+    L.b200_forward_transform.argtypes = [vp, vp, sz, i32, i32, i32, i32]
+    L.b200_forward_transform.restype = None
+    L.b200_fwd_txfm_dev.argtypes = [vp, vp, sz, sz, vp, sz, i32, i32, i32, i32]
+    L.b200_fwd_txfm_batch.argtypes = [vp, vp, sz, sz, vp, sz, i32, i32, i32, i32]
     _LIB = L
     return L
 
@@ -171,6 +178,25 @@ class Context:
         self.check(self.L.b200_me_full_search_dev(
             self.h, C.byref(cur), C.byref(ref), _dev_ptr(d_blocks), nblocks, C.byref(params),
             range_x, range_y, step, _dev_ptr(d_best)))
+
+    # ---- forward transform
+    def fwd_txfm_dev(self, d_in, in_block_stride, in_row_stride, d_out, n, tx_size, tx_type, bd,
+                     coeff_i32):
+        self.check(self.L.b200_fwd_txfm_dev(self.h, _dev_ptr(d_in), in_block_stride, in_row_stride,
+                                            _dev_ptr(d_out), n, tx_size, tx_type, bd, int(coeff_i32)))
+
+    def fwd_txfm_batch(self, residual, tx_size, tx_type, bd=8, coeff_i32=None, out=None):
+        """residual: int16 (n, h, w) numpy -> (n, w*h) coefficients (host buffers, copies inside)."""
+        residual = np.ascontiguousarray(residual, dtype=np.int16)
+        n, h, w = residual.shape
+        if coeff_i32 is None:
+            coeff_i32 = bd > 8
+        if out is None:
+            out = np.empty((n, w * h), np.int32 if coeff_i32 else np.int16)
+        self.check(self.L.b200_fwd_txfm_batch(self.h, residual.ctypes.data, h * w, w,
+                                              out.ctypes.data, n, tx_size, tx_type, bd,
+                                              int(coeff_i32)))
+        return out
 
     # ---- ME, host buffers (numpy in / numpy out; copies inside)
     def me_candidates_batch(self, cur_hp, ref_hp, blocks, cands, params, offsets=None, pmv=None,

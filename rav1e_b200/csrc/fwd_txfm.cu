@@ -1,0 +1,264 @@
+// fwd_txfm.cu — batched 2-D forward transforms (rav1e src/transform/forward.rs:71-161) for sm_100a.
+//
+// One thread owns one whole column (pass 1) and then one whole row (pass 2) of a block in
+// registers and runs the straight-line lifting network on it (txfm_networks.cuh); the
+// transposition between the passes goes through a padded shared-memory tile, so both the
+// int16 residual loads and the coefficient stores (the reference's transposed, 32x32-chunked
+// order, forward.rs:135-159) are coalesced.  A CTA of 128 threads carries 128/max(W,H) blocks
+// at a time.  Warp shuffles are deliberately NOT used for the butterflies: the Daala networks
+// are irregular lifting ladders with per-node constants, so a lane-per-coefficient layout
+// would diverge on every step, while a thread-per-vector layout needs no communication at all
+// inside a 1-D pass.
+#include "common.cuh"
+#include "txfm_networks.cuh"
+
+namespace {
+
+enum { T1_DCT = 0, T1_ADST = 1, T1_FLIPADST = 2, T1_IDTX = 3, T1_WHT = 4 };
+enum { TX_DCT_DCT = 0, TX_IDTX = 9, TX_WHT_WHT = 16 };
+
+// transform/mod.rs:101-123 (declaration order)
+const uint8_t kTxW[19] = {4, 8, 16, 32, 64, 4, 8, 8, 16, 16, 32, 32, 64, 4, 16, 8, 32, 16, 64};
+const uint8_t kTxH[19] = {4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16};
+// transform/mod.rs:364-402
+const uint8_t kVtx[17] = {T1_DCT, T1_ADST, T1_DCT, T1_ADST, T1_FLIPADST, T1_DCT, T1_FLIPADST,
+                          T1_ADST, T1_FLIPADST, T1_IDTX, T1_DCT, T1_IDTX, T1_ADST, T1_IDTX,
+                          T1_FLIPADST, T1_IDTX, T1_WHT};
+const uint8_t kHtx[17] = {T1_DCT, T1_DCT, T1_ADST, T1_ADST, T1_DCT, T1_FLIPADST, T1_FLIPADST,
+                          T1_FLIPADST, T1_ADST, T1_IDTX, T1_IDTX, T1_DCT, T1_IDTX, T1_ADST,
+                          T1_IDTX, T1_FLIPADST, T1_WHT};
+// forward_shared.rs:22-64, indexed [class][(bd-8)/2][stage]
+const int8_t kShift4x4[3][3] = {{3, 0, 0}, {2, 0, 1}, {0, 0, 3}};
+const int8_t kShiftA[3][3] = {{4, -1, 0}, {2, 0, 1}, {0, 0, 3}};    // 8x8,16x16,4x8,...,32x8
+const int8_t kShiftB[3][3] = {{4, -2, 0}, {2, 0, 0}, {0, 0, 2}};    // 32x32,16x32,32x16,16x64,64x16
+const int8_t kShiftC[3][3] = {{4, -1, -2}, {2, 0, -1}, {0, 0, 1}};  // 64x64,32x64,64x32
+const int8_t kShiftWht[3] = {0, 0, 2};
+// class per TxSize: 0 = 4x4, 1 = A, 2 = B, 3 = C
+const uint8_t kShiftClass[19] = {0, 1, 1, 2, 3, 1, 1, 1, 1, 2, 2, 3, 3, 1, 1, 1, 1, 2, 2};
+
+int size_index(int n) { return n == 4 ? 0 : n == 8 ? 1 : n == 16 ? 2 : n == 32 ? 3 : 4; }
+
+// mod.rs:405-417 plus the `.unwrap()`s of Txfm2DFlipCfg::fwd (forward_shared.rs:128-134)
+bool valid_transform(int tx_size, int tx_type) {
+  if (tx_size < 0 || tx_size >= 19 || tx_type < 0 || tx_type > 16) return false;
+  const int w = kTxW[tx_size], h = kTxH[tx_size], m = w > h ? w : h;
+  if (m == 64 && tx_type != TX_DCT_DCT) return false;
+  if (m == 32 && tx_type != TX_DCT_DCT && tx_type != TX_IDTX) return false;
+  const int t1[2] = {kVtx[tx_type], kHtx[tx_type]}, n[2] = {h, w};
+  for (int k = 0; k < 2; k++) {
+    const int idx = size_index(n[k]);
+    if (t1[k] == T1_WHT && idx != 0) return false;
+    if ((t1[k] == T1_ADST || t1[k] == T1_FLIPADST) && idx > 2) return false;
+    if (t1[k] == T1_IDTX && idx > 3) return false;
+  }
+  return true;
+}
+
+struct TxArgs {
+  const int16_t *in;
+  void *out;
+  size_t n;
+  size_t in_block_stride;  // elements between consecutive blocks
+  int in_row_stride;       // elements between rows of a block
+  int col_type, row_type;
+  int ud_flip, lr_flip;
+  int bit0, bit1, bit2;    // av1_round_shift_array `bit` = -shift[k]: >0 round-shift right, <0 left
+};
+
+// mod.rs:320-336
+__device__ __forceinline__ int round_shift_bit(int v, int bit) {
+  if (bit > 0) return (v + ((1 << bit) >> 1)) >> bit;
+  return (int)((unsigned)v << (-bit));
+}
+
+template <int N>
+__device__ __forceinline__ void run_1d(int type, TXV (&c)[N]) {
+  if (type == T1_IDTX) return;  // fidentity, forward_shared.rs:1775
+  if constexpr (N == 4) {
+    if (type == T1_DCT) tx_fdct4(c);
+    else if (type == T1_WHT) tx_fwht4(c);
+    else tx_fdst_vii_4(c);
+  } else if constexpr (N == 8) {
+    if (type == T1_DCT) tx_fdct8(c);
+    else tx_fdst8(c);
+  } else if constexpr (N == 16) {
+    if (type == T1_DCT) tx_fdct16(c);
+    else tx_fdst16(c);
+  } else if constexpr (N == 32) {
+    tx_fdct32(c);
+  } else {
+    tx_fdct64(c);
+  }
+}
+
+constexpr int kTxThreads = 128;
+
+template <int W, int H, typename CoefT>
+__global__ void __launch_bounds__(kTxThreads) fwd_txfm_kernel(TxArgs a) {
+  constexpr int T = W > H ? W : H;       // threads per block-transform
+  constexpr int PER = kTxThreads / T;    // transforms in flight per CTA
+  constexpr int PITCH = W + 1;           // padded row pitch: conflict-free transposition
+  constexpr int REGION = H * PITCH + ((H * PITCH) % 2 == 0 ? 1 : 0);
+  __shared__ int buf[PER * REGION];
+  const int slot = threadIdx.x / T, t = threadIdx.x - slot * T;
+  int *tile = buf + slot * REGION;
+  const size_t stride_blk = (size_t)gridDim.x * PER;
+  for (size_t base = (size_t)blockIdx.x * PER; base < a.n; base += stride_blk) {
+    const size_t blk = base + slot;
+    const bool valid = blk < a.n;
+    // ---- columns (forward.rs:95-126)
+    if (valid && t < W) {
+      TXV c[H];
+      const int16_t *src = a.in + blk * a.in_block_stride + t;
+#pragma unroll
+      for (int r = 0; r < H; r++) {
+        const int rr = a.ud_flip ? H - 1 - r : r;
+        c[r] = round_shift_bit((int)src[(size_t)rr * a.in_row_stride], a.bit0);
+      }
+      run_1d<H>(a.col_type, c);
+      const int cc = a.lr_flip ? W - 1 - t : t;
+#pragma unroll
+      for (int r = 0; r < H; r++) tile[r * PITCH + cc] = round_shift_bit(c[r], a.bit1);
+    }
+    __syncthreads();
+    // ---- rows (forward.rs:131-160)
+    if (valid && t < H) {
+      TXV c[W];
+#pragma unroll
+      for (int k = 0; k < W; k++) c[k] = tile[t * PITCH + k];
+      run_1d<W>(a.row_type, c);
+      constexpr int HS = H < 32 ? H : 32, WC = W < 32 ? W : 32;
+      CoefT *dst = (CoefT *)a.out + blk * (size_t)(W * H) + (t >= 32 ? HS * WC : 0) + (t & 31);
+#pragma unroll
+      for (int k = 0; k < W; k++)
+        dst[(size_t)H * 32 * (k >= 32) + (k & 31) * HS] = (CoefT)round_shift_bit(c[k], a.bit2);
+    }
+    __syncthreads();
+  }
+}
+
+template <int W, int H>
+int launch_txfm(b200_ctx *ctx, const TxArgs &a, int coeff_is_i32) {
+  constexpr int T = W > H ? W : H;
+  constexpr int PER = kTxThreads / T;
+  const size_t ctas = (a.n + PER - 1) / PER;
+  const int grid = (int)std::min<size_t>(ctas, (size_t)ctx->num_sms * 32);
+  if (coeff_is_i32)
+    fwd_txfm_kernel<W, H, int32_t><<<grid, kTxThreads, 0, ctx->stream>>>(a);
+  else
+    fwd_txfm_kernel<W, H, int16_t><<<grid, kTxThreads, 0, ctx->stream>>>(a);
+  B200_LAUNCH_CHECK(ctx);
+  return B200_OK;
+}
+
+}  // namespace
+
+extern "C" int b200_valid_av1_transform(int tx_size, int tx_type) {
+  return valid_transform(tx_size, tx_type) ? 1 : 0;
+}
+extern "C" int b200_tx_width(int tx_size) { return tx_size >= 0 && tx_size < 19 ? kTxW[tx_size] : 0; }
+extern "C" int b200_tx_height(int tx_size) { return tx_size >= 0 && tx_size < 19 ? kTxH[tx_size] : 0; }
+
+extern "C" int b200_fwd_txfm_dev(b200_ctx *ctx, const int16_t *d_input, size_t in_block_stride,
+                                 size_t in_row_stride, void *d_output, size_t nblocks, int tx_size,
+                                 int tx_type, int bd, int coeff_is_i32) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  // forward.rs:75: assert!(valid_av1_transform(tx_size, tx_type))
+  B200_REQUIRE(ctx, valid_transform(tx_size, tx_type), "invalid transform: tx_size %d tx_type %d",
+               tx_size, tx_type);
+  B200_REQUIRE(ctx, bd == 8 || bd == 10 || bd == 12, "bit depth %d not in {8,10,12}", bd);
+  if (nblocks == 0) return B200_OK;
+  B200_REQUIRE(ctx, d_input && d_output, "NULL input/output");
+  const int w = kTxW[tx_size], h = kTxH[tx_size];
+  B200_REQUIRE(ctx, in_row_stride >= (size_t)w, "row stride %zu < width %d", in_row_stride, w);
+  B200_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int8_t *sh;
+  if (tx_type == TX_WHT_WHT) {
+    sh = kShiftWht;
+  } else {
+    const int cls = kShiftClass[tx_size], b = (bd - 8) / 2;
+    sh = cls == 0 ? kShift4x4[b] : cls == 1 ? kShiftA[b] : cls == 2 ? kShiftB[b] : kShiftC[b];
+  }
+  TxArgs a;
+  a.in = d_input;
+  a.out = d_output;
+  a.n = nblocks;
+  a.in_block_stride = in_block_stride;
+  a.in_row_stride = (int)in_row_stride;
+  a.col_type = kVtx[tx_type];
+  a.row_type = kHtx[tx_type];
+  a.ud_flip = a.col_type == T1_FLIPADST;  // forward_shared.rs:155-164
+  a.lr_flip = a.row_type == T1_FLIPADST;
+  a.bit0 = -sh[0];
+  a.bit1 = -sh[1];
+  a.bit2 = -sh[2];
+  switch (tx_size) {
+#define B200_TX(ID, W_, H_) \
+  case ID:                  \
+    return launch_txfm<W_, H_>(ctx, a, coeff_is_i32);
+    B200_TX(0, 4, 4)
+    B200_TX(1, 8, 8)
+    B200_TX(2, 16, 16)
+    B200_TX(3, 32, 32)
+    B200_TX(4, 64, 64)
+    B200_TX(5, 4, 8)
+    B200_TX(6, 8, 4)
+    B200_TX(7, 8, 16)
+    B200_TX(8, 16, 8)
+    B200_TX(9, 16, 32)
+    B200_TX(10, 32, 16)
+    B200_TX(11, 32, 64)
+    B200_TX(12, 64, 32)
+    B200_TX(13, 4, 16)
+    B200_TX(14, 16, 4)
+    B200_TX(15, 8, 32)
+    B200_TX(16, 32, 8)
+    B200_TX(17, 16, 64)
+    B200_TX(18, 64, 16)
+#undef B200_TX
+  }
+  return b200_fail(ctx, B200_ERR_ARG, "unreachable tx_size %d", tx_size);
+}
+
+// Host-buffer form: packed residual blocks in, coefficients out.
+extern "C" int b200_fwd_txfm_batch(b200_ctx *ctx, const int16_t *input, size_t in_block_stride,
+                                   size_t in_row_stride, void *output, size_t nblocks, int tx_size,
+                                   int tx_type, int bd, int coeff_is_i32) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  B200_REQUIRE(ctx, valid_transform(tx_size, tx_type), "invalid transform: tx_size %d tx_type %d",
+               tx_size, tx_type);
+  if (nblocks == 0) return B200_OK;
+  B200_REQUIRE(ctx, input && output, "NULL input/output");
+  const int w = kTxW[tx_size], h = kTxH[tx_size];
+  const size_t in_elems = (nblocks - 1) * in_block_stride + (size_t)(h - 1) * in_row_stride + w;
+  const size_t out_bytes = nblocks * (size_t)w * h * (coeff_is_i32 ? 4 : 2);
+  B200_CUDA(ctx, cudaSetDevice(ctx->device));
+  void *dbase = nullptr;
+  const size_t in_bytes = b200_align_up(in_elems * 2, 256);
+  B200_CUDA(ctx, cudaMallocAsync(&dbase, in_bytes + out_bytes, ctx->stream));
+  int st = B200_OK;
+  if (cudaMemcpyAsync(dbase, input, in_elems * 2, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+    st = b200_fail(ctx, B200_ERR_CUDA, "H2D copy failed");
+  uint8_t *d_out = (uint8_t *)dbase + in_bytes;
+  if (!st)
+    st = b200_fwd_txfm_dev(ctx, (const int16_t *)dbase, in_block_stride, in_row_stride, d_out,
+                           nblocks, tx_size, tx_type, bd, coeff_is_i32);
+  if (!st && cudaMemcpyAsync(output, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+    st = b200_fail(ctx, B200_ERR_CUDA, "D2H copy failed");
+  cudaFreeAsync(dbase, ctx->stream);
+  if (st) return st;
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+// Per-call form with the reference's signature (asm/x86/transform/forward.rs:444-447):
+// forward_transform(input: &[i16], output: &mut [T::Coeff], stride, tx_size, tx_type, bd, cpu).
+extern "C" void b200_forward_transform(const int16_t *input, void *output, size_t stride,
+                                       int tx_size, int tx_type, int bd, int coeff_is_i32) {
+  b200_ctx *ctx = b200_default_ctx();
+  int st = b200_fwd_txfm_batch(ctx, input, 0, stride, output, 1, tx_size, tx_type, bd, coeff_is_i32);
+  if (st != B200_OK) {
+    fprintf(stderr, "b200rdo: FATAL: forward_transform failed: %s\n", b200_last_error(ctx));
+    abort();  // the reference panics on an invalid (size, type) pair (forward.rs:75)
+  }
+}

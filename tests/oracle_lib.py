@@ -63,6 +63,16 @@ def lib():
     L.orc_full_search_blocks.argtypes = [vp, pd, vp, pd, i32, i32, i32, vp, sz, i32, i32, i32, i32,
                                          i32, u32, i32, vp, i32]
     L.orc_num_threads.restype = i32
+    L.orc_valid_av1_transform.restype = i32
+    L.orc_valid_av1_transform.argtypes = [i32, i32]
+    L.orc_tx_width.restype = i32
+    L.orc_tx_width.argtypes = [i32]
+    L.orc_tx_height.restype = i32
+    L.orc_tx_height.argtypes = [i32]
+    L.orc_forward_transform.restype = None
+    L.orc_forward_transform.argtypes = [vp, vp, sz, i32, i32, i32, i32]
+    L.orc_forward_transform_batch.restype = None
+    L.orc_forward_transform_batch.argtypes = [vp, vp, sz, i32, i32, i32, i32, i32]
     _LIB = L
     return L
 
@@ -137,4 +147,38 @@ def full_search_blocks(cur: Plane, ref: Plane, blocks, w, h, range_x, range_y, s
     L.orc_full_search_blocks(cur.origin_ptr(), cur.stride, ref.origin_ptr(), ref.stride, cur.bpp,
                              w_in_b, h_in_b, ptr(blocks), len(blocks), w, h, range_x, range_y,
                              step, int(lambda_), int(allow_hp), ptr(out), threads)
+    return out
+
+
+# ---------------------------------------------------------------- forward transform
+TX_SIZES = [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (4, 8), (8, 4), (8, 16), (16, 8),
+            (16, 32), (32, 16), (32, 64), (64, 32), (4, 16), (16, 4), (8, 32), (32, 8),
+            (16, 64), (64, 16)]                      # (w, h) in TxSize order, transform/mod.rs:101
+TX_TYPE_NAMES = ["DCT_DCT", "ADST_DCT", "DCT_ADST", "ADST_ADST", "FLIPADST_DCT", "DCT_FLIPADST",
+                 "FLIPADST_FLIPADST", "ADST_FLIPADST", "FLIPADST_ADST", "IDTX", "V_DCT", "H_DCT",
+                 "V_ADST", "H_ADST", "V_FLIPADST", "H_FLIPADST", "WHT_WHT"]
+
+
+def valid_txfm(tx_size, tx_type):
+    return bool(lib().orc_valid_av1_transform(tx_size, tx_type))
+
+
+def valid_txfm_combos():
+    """The reference's sweep set (transform/mod.rs:420-467): 160 (size, type) pairs."""
+    return [(s, t) for s in range(19) for t in range(17) if valid_txfm(s, t)]
+
+
+def forward_transform_batch(residual, tx_size, tx_type, bd=8, coeff_i32=None, threads=0):
+    """residual: int16 array (n, h, w) contiguous -> coefficients (n, w*h) in the reference's
+    transposed / 32x32-chunked order; int16 for 8-bit pixels, int32 for HBD (T::Coeff)."""
+    L = lib()
+    w, h = TX_SIZES[tx_size]
+    residual = np.ascontiguousarray(residual, dtype=np.int16)
+    n = residual.shape[0]
+    assert residual.shape == (n, h, w)
+    if coeff_i32 is None:
+        coeff_i32 = bd > 8
+    out = np.empty((n, w * h), np.int32 if coeff_i32 else np.int16)
+    L.orc_forward_transform_batch(ptr(residual), ptr(out), n, tx_size, tx_type, bd, int(coeff_i32),
+                                  threads)
     return out
