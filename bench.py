@@ -144,11 +144,13 @@ def run_reference(args, rank, world):
     # bounded sample: one frame pair, 1/4 of its candidate lists per step
     sad_c, _ = cand_list(len(blocks), CAND_SAD // 4, 100)
     satd_c, _ = cand_list(len(blocks), CAND_SATD // 4, 200)
-    units = len(sad_c) + len(satd_c)
+    resid = np.random.default_rng(5).integers(-255, 256, (len(blocks) // 4, BH, BW)).astype(np.int16)
+    units = len(sad_c) + len(satd_c) + len(resid)
 
     def step():
         O.fullpel_candidates(ocur, oref, blocks, sad_c, BW, BH, False, LAMBDA, want_cost=True)
         O.fullpel_candidates(ocur, oref, blocks, satd_c, BW, BH, True, LAMBDA, want_cost=True)
+        O.forward_transform_batch(resid, 2, 0, 8)
 
     for _ in range(args.warmup):
         step()
@@ -158,7 +160,7 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     v = units * args.steps / dt
     sample = (f"1 of {FRAMES_PER_GPU} frame pairs, {CAND_SAD // 4} SAD + {CAND_SATD // 4} SATD "
-              f"candidates per 16x16 block ({units} blocks/step)")
+              f"candidates per 16x16 block + 1/4 of the 16x16 DCT_DCT transforms ({units} blocks/step)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "blocks/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -236,10 +238,21 @@ def run_b200(args, rank, world, local_rank):
         ctx.me_candidates_dev(cur, ref, d_blocks, nb, satd_lists[f], n_satd, p_satd, d_offs2, None,
                               d_satd[f * n_satd * 4:], None, d_best2[f * nb * 16:])
 
+    d_resid = torch.empty(F * nb * BW * BH, dtype=torch.int16, device="cuda")
+    d_coef = torch.empty(F * nb * BW * BH, dtype=torch.int16, device="cuda")
+
+    def txfm_launch(f):
+        cur, ref = planes[f]
+        ctx.block_residual_dev(cur, ref, d_blocks, nb, d_best[f * nb * 16:], BW, BH,
+                               d_resid[f * nb * BW * BH:])
+        ctx.fwd_txfm_dev(d_resid[f * nb * BW * BH:], BW * BH, BW, d_coef[f * nb * BW * BH:], nb,
+                         2, 0, 8, False)      # TX_16X16, DCT_DCT, 8-bit -> i16 coefficients
+
     def step():
         for f in range(F):
             sad_launch(f)
             satd_launch(f)
+            txfm_launch(f)
         if world > 1:   # per-tile/frame winners to every rank (the entropy-coder owner)
             dist.all_gather_into_tensor(gathered, d_best)
 
@@ -270,7 +283,7 @@ def run_b200(args, rank, world, local_rank):
     ms = timed(step, args.steps)
     launches = ctx.launches - l0
     clocks = clk.stop() if rank == 0 else None
-    units_per_step = world * F * (n_sad + n_satd)
+    units_per_step = world * F * (n_sad + n_satd + nb)
     value = units_per_step * args.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (candidate-list SAD), timed alone on the same stream
@@ -285,6 +298,12 @@ def run_b200(args, rank, world, local_rank):
     ms_sad = timed(sad_only, args.steps) / (args.steps * F)      # ms per launch
     satd_only()
     ms_satd = timed(satd_only, args.steps) / (args.steps * F)
+
+    def txfm_only():
+        for f in range(F):
+            txfm_launch(f)
+    txfm_only()
+    ms_txfm = timed(txfm_only, args.steps) / (args.steps * F)
     alg_bytes = n_sad * (BW * BH + 4) + nb * BW * BH             # 260 B/cand + 256 B/block
     peak, peak_src = peaks()
     achieved = alg_bytes / (ms_sad * 1e-3) / 1e9
@@ -307,13 +326,15 @@ def run_b200(args, rank, world, local_rank):
             "config": {"workload": "1080p-8bit-speed6-me16x16", "frames_per_gpu": F,
                        "blocks_per_frame": nb, "block": "16x16",
                        "legs": {"sad_candidates_per_block": CAND_SAD,
-                                "satd_candidates_per_block": CAND_SATD},
+                                "satd_candidates_per_block": CAND_SATD,
+                                "fwd_txfm_per_block": "1 x TX_16X16 DCT_DCT of the SAD winner's residual"},
                        "mv_range_px": MV_RANGE_PX, "lambda": LAMBDA,
                        "l2": "inputs>L2 (planes %.0f MB + descriptors %.0f MB per GPU)" % (
                            F * 2 * (W + 2 * PAD) * (H + 2 * PAD) / 1e6, F * (n_sad + n_satd) * 8 / 1e6),
                        "parallelism": f"frames sharded over {world} GPU(s); all-gather of winners"
                        if world > 1 else "1 GPU",
-                       "per_launch_ms": {"sad_cand": ms_sad, "satd_cand": ms_satd}},
+                       "per_launch_ms": {"sad_cand": ms_sad, "satd_cand": ms_satd,
+                                         "residual+fwd_txfm": ms_txfm}},
             "roofline": {"kernel": "me_cand_smem_u8<16,16> (candidate-list SAD + cost + argmin)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -350,8 +371,11 @@ def run_e2e(ctx, blocks, args):
                 pinned(nb * 16, torch.uint8).view(B.ME_RESULT_DTYPE))
         outs2 = (pinned(len(c2) * 4, torch.uint8).view(np.uint32), None,
                  pinned(nb * 16, torch.uint8).view(B.ME_RESULT_DTYPE))
+        hres = pinned(nb * BW * BH * 2, torch.uint8).view(np.int16).reshape(nb, BH, BW)
+        hres[:] = np.random.default_rng(f).integers(-255, 256, hres.shape)
+        hcoef = pinned(nb * BW * BH * 2, torch.uint8).view(np.int16).reshape(nb, BW * BH)
         frames.append((B.host_plane(hc, PAD), B.host_plane(hr, PAD), hcand.view(B.CAND_DTYPE),
-                       hcand2.view(B.CAND_DTYPE), outs, outs2))
+                       hcand2.view(B.CAND_DTYPE), outs, outs2, hres, hcoef))
     p_sad = B.me_params(BW, BH, W, H, LAMBDA, window_hint_px=MV_RANGE_PX)
     p_satd = B.me_params(BW, BH, W, H, LAMBDA, use_satd=True, window_hint_px=MV_RANGE_PX)
     h2d = d2h = 0
@@ -359,9 +383,12 @@ def run_e2e(ctx, blocks, args):
     def step():
         nonlocal h2d, d2h
         h2d = d2h = 0
-        for hc, hr, c, c2, outs, outs2 in frames:
+        for hc, hr, c, c2, outs, outs2, hres, hcoef in frames:
             sad, _, best = ctx.me_candidates_batch(hc, hr, blocks, c, p_sad, offs, None, out=outs)
             sad2, _, best2 = ctx.me_candidates_batch(hc, hr, blocks, c2, p_satd, offs2, None, out=outs2)
+            ctx.fwd_txfm_batch(hres, 2, 0, 8, False, out=hcoef)
+            h2d += hres.nbytes
+            d2h += hcoef.nbytes
             plane_bytes = 2 * (W + 2 * PAD) * (H + 2 * PAD)
             h2d += 2 * plane_bytes + c.nbytes + c2.nbytes + 2 * blocks.nbytes + offs.nbytes + offs2.nbytes
             d2h += sad.nbytes + sad2.nbytes + best.nbytes + best2.nbytes
@@ -373,10 +400,10 @@ def run_e2e(ctx, blocks, args):
         step()
     ctx.synchronize()
     dt = time.perf_counter() - t0
-    units = Fe * nb * (CAND_SAD + CAND_SATD)
+    units = Fe * nb * (CAND_SAD + CAND_SATD + 1)
     return {"value": units * reps / dt, "unit": "blocks/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "frames_per_step": Fe,
-            "api": "b200_me_candidates_batch (host planes + descriptors in, SADs + winners out)"}
+            "api": "b200_me_candidates_batch x2 + b200_fwd_txfm_batch per frame (host buffers in/out)"}
 
 
 def run_cpu_baseline(blocks):
@@ -387,17 +414,19 @@ def run_cpu_baseline(blocks):
     ocur.data[:], oref.data[:] = cur_img, ref_img
     sad_c, _ = cand_list(len(blocks), CAND_SAD, 100)
     satd_c, _ = cand_list(len(blocks), CAND_SATD, 200)
+    resid = np.random.default_rng(5).integers(-255, 256, (len(blocks), BH, BW)).astype(np.int16)
     O.fullpel_candidates(ocur, oref, blocks, sad_c[:65536], BW, BH, False, LAMBDA)   # warm
     t0 = time.perf_counter()
     reps = 0
     while time.perf_counter() - t0 < 3.0:
         O.fullpel_candidates(ocur, oref, blocks, sad_c, BW, BH, False, LAMBDA)
         O.fullpel_candidates(ocur, oref, blocks, satd_c, BW, BH, True, LAMBDA)
+        O.forward_transform_batch(resid, 2, 0, 8)
         reps += 1
     dt = time.perf_counter() - t0
-    units = (len(sad_c) + len(satd_c)) * reps
+    units = (len(sad_c) + len(satd_c) + len(resid)) * reps
     return {"value": units / dt, "unit": "blocks/s", "cores": threads, "kind": "port",
-            "sample": f"1 frame pair x {reps} passes ({CAND_SAD} SAD + {CAND_SATD} SATD cands/block), "
+            "sample": f"1 frame pair x {reps} passes ({CAND_SAD} SAD + {CAND_SATD} SATD cands + 1 fwd txfm per block), "
                       f"{dt:.1f} s wall on {threads} threads; C restatement of rav1e rust:: kernels"}
 
 

@@ -164,6 +164,14 @@ int b200_me_full_search_dev(b200_ctx *ctx, const b200_plane *cur, const b200_pla
                             const b200_me_params *params, int range_x, int range_y, int step,
                             b200_me_result *d_best);
 
+/* Residual of every block against the reference displaced by the full-pel part of the
+ * winners' motion vectors (the `diff` of encode_tx_block, encoder.rs:1533); d_mv_src may be
+ * NULL (zero motion).  d_out: nblocks packed w x h int16 blocks, the input layout of
+ * b200_fwd_txfm_dev with in_block_stride = w*h, in_row_stride = w. */
+int b200_block_residual_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                            const b200_block *d_blocks, size_t nblocks,
+                            const b200_me_result *d_mv_src, int w, int h, int16_t *d_out);
+
 /* Host-buffer forms (what a Rust caller holding Plane<T> memory calls): planes are given
  * as host pointers to pixel (0,0) + byte strides and must be readable over the padding the
  * candidates can reach; everything is copied H2D, computed, and copied back before return. */

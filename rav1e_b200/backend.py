@@ -99,6 +99,7 @@ def lib():
             f.restype = u32
     L.b200_me_candidates_dev.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
     L.b200_me_full_search_dev.argtypes = [vp, pp, pp, vp, sz, pmp, i32, i32, i32, vp]
+    L.b200_block_residual_dev.argtypes = [vp, pp, pp, vp, sz, vp, i32, i32, vp]
     L.b200_me_candidates_batch.argtypes = [vp, php, php, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
     L.b200_me_full_search_batch.argtypes = [vp, php, php, vp, sz, pmp, i32, i32, i32, vp]
     L.b200_valid_av1_transform.argtypes = [i32, i32]
@@ -178,6 +179,11 @@ class Context:
         self.check(self.L.b200_me_full_search_dev(
             self.h, C.byref(cur), C.byref(ref), _dev_ptr(d_blocks), nblocks, C.byref(params),
             range_x, range_y, step, _dev_ptr(d_best)))
+
+    def block_residual_dev(self, cur, ref, d_blocks, nblocks, d_mv_src, w, h, d_out):
+        self.check(self.L.b200_block_residual_dev(self.h, C.byref(cur), C.byref(ref),
+                                                  _dev_ptr(d_blocks), nblocks, _dev_ptr(d_mv_src),
+                                                  w, h, _dev_ptr(d_out)))
 
     # ---- forward transform
     def fwd_txfm_dev(self, d_in, in_block_stride, in_row_stride, d_out, n, tx_size, tx_type, bd,

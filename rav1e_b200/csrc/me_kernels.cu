@@ -1006,6 +1006,49 @@ extern "C" int b200_me_candidates_dev(b200_ctx *ctx, const b200_plane *cur, cons
   return B200_OK;
 }
 
+// Residual of each block against the reference displaced by a full-pel motion vector:
+// the `diff` step of encode_tx_block (encoder.rs:1533) for the full-pel winners of the ME
+// stage; feeds forward_transform.  out[i][r][c] = cur(bx+c, by+r) - ref(bx+mvx+c, by+mvy+r).
+template <typename T>
+__global__ void block_residual_kernel(PlaneView cur, PlaneView ref, const b200_block *blocks,
+                                      const b200_me_result *mv_src, size_t n, int w, int h,
+                                      int16_t *out) {
+  const size_t area = (size_t)w * h;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n * area;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t blk = i / area;
+    const int rem = (int)(i - blk * area), r = rem / w, c = rem - r * w;
+    const b200_block b = blocks[blk];
+    int dx = 0, dy = 0;
+    if (mv_src && mv_src[blk].cost != kEmptyCost) {
+      dx = mv_src[blk].mv_col / 8;
+      dy = mv_src[blk].mv_row / 8;
+    }
+    out[i] = (int16_t)((int)*px<T>(cur, b.x + c, b.y + r) - (int)*px<T>(ref, b.x + dx + c, b.y + dy + r));
+  }
+}
+
+extern "C" int b200_block_residual_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                                       const b200_block *d_blocks, size_t nblocks,
+                                       const b200_me_result *d_mv_src, int w, int h,
+                                       int16_t *d_out) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  B200_REQUIRE(ctx, cur && ref && cur->data && ref->data && cur->bpp == ref->bpp, "bad planes");
+  B200_REQUIRE(ctx, w > 0 && h > 0 && w <= 128 && h <= 128, "bad block size %dx%d", w, h);
+  if (nblocks == 0) return B200_OK;
+  B200_REQUIRE(ctx, d_blocks && d_out, "NULL blocks/out");
+  B200_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t total = nblocks * (size_t)w * h;
+  const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->num_sms * 32);
+  PlaneView c{cur->data, cur->stride}, r{ref->data, ref->stride};
+  if (cur->bpp == 1)
+    block_residual_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(c, r, d_blocks, d_mv_src, nblocks, w, h, d_out);
+  else
+    block_residual_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(c, r, d_blocks, d_mv_src, nblocks, w, h, d_out);
+  B200_LAUNCH_CHECK(ctx);
+  return B200_OK;
+}
+
 extern "C" int b200_me_full_search_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
                                        const b200_block *d_blocks, size_t nblocks,
                                        const b200_me_params *p, int range_x, int range_y, int step,
