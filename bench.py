@@ -238,15 +238,13 @@ def run_b200(args, rank, world, local_rank):
         ctx.me_candidates_dev(cur, ref, d_blocks, nb, satd_lists[f], n_satd, p_satd, d_offs2, None,
                               d_satd[f * n_satd * 4:], None, d_best2[f * nb * 16:])
 
-    d_resid = torch.empty(F * nb * BW * BH, dtype=torch.int16, device="cuda")
     d_coef = torch.empty(F * nb * BW * BH, dtype=torch.int16, device="cuda")
 
     def txfm_launch(f):
         cur, ref = planes[f]
-        ctx.block_residual_dev(cur, ref, d_blocks, nb, d_best[f * nb * 16:], BW, BH,
-                               d_resid[f * nb * BW * BH:])
-        ctx.fwd_txfm_dev(d_resid[f * nb * BW * BH:], BW * BH, BW, d_coef[f * nb * BW * BH:], nb,
-                         2, 0, 8, False)      # TX_16X16, DCT_DCT, 8-bit -> i16 coefficients
+        # fused diff + TX_16X16 DCT_DCT (8-bit -> i16 coefficients) of the SAD winners
+        ctx.fwd_txfm_residual_dev(cur, ref, d_blocks, nb, d_best[f * nb * 16:],
+                                  d_coef[f * nb * BW * BH:], 2, 0, 8)
 
     def step():
         for f in range(F):

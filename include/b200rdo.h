@@ -213,9 +213,40 @@ void b200_forward_transform(const int16_t *input, void *output, size_t stride, i
 int b200_fwd_txfm_dev(b200_ctx *ctx, const int16_t *d_input, size_t in_block_stride,
                       size_t in_row_stride, void *d_output, size_t nblocks, int tx_size,
                       int tx_type, int bd, int coeff_is_i32);
+/* Fused residual (`diff`, encoder.rs:1533) + forward transform: block i = cur(block) minus ref
+ * displaced by the full-pel part of d_mv_src[i] (NULL: zero motion).  u8 planes produce i16
+ * coefficients, u16 planes i32; bd must match the planes' depth. */
+int b200_fwd_txfm_residual_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                               const b200_block *d_blocks, size_t nblocks,
+                               const b200_me_result *d_mv_src, void *d_output, int tx_size,
+                               int tx_type, int bd);
 int b200_fwd_txfm_batch(b200_ctx *ctx, const int16_t *input, size_t in_block_stride,
                         size_t in_row_stride, void *output, size_t nblocks, int tx_size,
                         int tx_type, int bd, int coeff_is_i32);
+
+/* ------------------------------------------------ motion compensation (mc.rs, predict.rs)
+ * Per-call forms: the argument order of the dav1d-style symbols rav1e binds
+ * (`rav1e_put_8tap_regular_smooth_8bpc_avx2(dst, dst_stride, src, src_stride, w, h, mx, my)`,
+ * asm/x86/mc.rs:17-76, table index (fx + 4*fy)&15 :80-82) with the filter pair passed as
+ * arguments instead of being baked into the symbol name.  Host pointers, BYTE strides; src must
+ * be readable over [-3, w+4) x [-3, h+4) (asm/x86/mc.rs:122-123).  FilterMode: 0 REGULAR,
+ * 1 SMOOTH, 2 SHARP, 3 BILINEAR (mc.rs:98-106).  Preconditions as the reference asserts
+ * (mc.rs:256-257): even height, power-of-two width in 2..128; violations abort. */
+void b200_put_8tap(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride, int w,
+                   int h, int col_frac, int row_frac, int mode_x, int mode_y, int bit_depth);
+void b200_prep_8tap(int16_t *tmp, const void *src, ptrdiff_t src_stride, int w, int h,
+                    int col_frac, int row_frac, int mode_x, int mode_y, int bit_depth);
+void b200_mc_avg(void *dst, ptrdiff_t dst_stride, const int16_t *tmp1, const int16_t *tmp2, int w,
+                 int h, int bit_depth);
+/* Batched predict_inter_single (predict.rs:304-336): block i is predicted from `ref` at
+ * d_blocks[i] displaced by d_mvs[2i] (row), d_mvs[2i+1] (col) in 1/8 pel through get_mv_params
+ * (predict.rs:284-297; xdec/ydec = plane decimation).  kind 0 = put (packed w*h pixels per block),
+ * kind 1 = prep (packed w*h int16 per block, for b200_mc_avg_dev). */
+int b200_mc_blocks_dev(b200_ctx *ctx, const b200_plane *ref, const b200_block *d_blocks,
+                       const int16_t *d_mvs, size_t nblocks, int w, int h, int mode_x, int mode_y,
+                       int bit_depth, int xdec, int ydec, int kind, void *d_out);
+int b200_mc_avg_dev(b200_ctx *ctx, const int16_t *d_tmp1, const int16_t *d_tmp2, void *d_dst,
+                    size_t nblocks, int w, int h, int bit_depth);
 
 #ifdef __cplusplus
 }

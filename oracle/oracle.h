@@ -109,6 +109,12 @@ void orc_prep_8tap(int16_t *tmp, const void *src, ptrdiff_t src_stride, int bpp,
                    int col_frac, int row_frac, int mode_x, int mode_y, int bit_depth);
 void orc_mc_avg(void *dst, ptrdiff_t dst_stride, int bpp, const int16_t *tmp1, const int16_t *tmp2,
                 int w, int h, int bit_depth);
+void orc_get_filter(int mode, int frac, int length, int32_t out[8]);
+void orc_get_mv_params(int mv_row, int mv_col, int xdec, int ydec, int *row_off, int *col_off,
+                       int *row_frac, int *col_frac);
+void orc_mc_blocks(const void *ref0, ptrdiff_t ref_stride, int bpp, const orc_block *blocks,
+                   const orc_mv *mvs, size_t n, int w, int h, int mode_x, int mode_y, int bit_depth,
+                   int xdec, int ydec, int kind, void *out, int threads);
 
 /* -------------------------------------------------------------- predict.rs */
 /* dispatch_predict_intra predict.rs:705-784.  edge points at the top-left element of an

@@ -108,7 +108,16 @@ def lib():
     L.b200_forward_transform.argtypes = [vp, vp, sz, i32, i32, i32, i32]
     L.b200_forward_transform.restype = None
     L.b200_fwd_txfm_dev.argtypes = [vp, vp, sz, sz, vp, sz, i32, i32, i32, i32]
+    L.b200_fwd_txfm_residual_dev.argtypes = [vp, pp, pp, vp, sz, vp, vp, i32, i32, i32]
     L.b200_fwd_txfm_batch.argtypes = [vp, vp, sz, sz, vp, sz, i32, i32, i32, i32]
+    L.b200_put_8tap.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t] + [i32] * 7
+    L.b200_put_8tap.restype = None
+    L.b200_prep_8tap.argtypes = [vp, vp, C.c_ssize_t] + [i32] * 7
+    L.b200_prep_8tap.restype = None
+    L.b200_mc_avg.argtypes = [vp, C.c_ssize_t, vp, vp, i32, i32, i32]
+    L.b200_mc_avg.restype = None
+    L.b200_mc_blocks_dev.argtypes = [vp, pp, vp, vp, sz] + [i32] * 8 + [vp]
+    L.b200_mc_avg_dev.argtypes = [vp, vp, vp, vp, sz, i32, i32, i32]
     _LIB = L
     return L
 
@@ -185,11 +194,27 @@ class Context:
                                                   _dev_ptr(d_blocks), nblocks, _dev_ptr(d_mv_src),
                                                   w, h, _dev_ptr(d_out)))
 
+    # ---- motion compensation
+    def mc_blocks_dev(self, ref, d_blocks, d_mvs, n, w, h, mode_x, mode_y, bit_depth, xdec, ydec,
+                      kind, d_out):
+        self.check(self.L.b200_mc_blocks_dev(self.h, C.byref(ref), _dev_ptr(d_blocks), _dev_ptr(d_mvs),
+                                             n, w, h, mode_x, mode_y, bit_depth, xdec, ydec, kind,
+                                             _dev_ptr(d_out)))
+
+    def mc_avg_dev(self, d_t1, d_t2, d_dst, n, w, h, bit_depth):
+        self.check(self.L.b200_mc_avg_dev(self.h, _dev_ptr(d_t1), _dev_ptr(d_t2), _dev_ptr(d_dst),
+                                          n, w, h, bit_depth))
+
     # ---- forward transform
     def fwd_txfm_dev(self, d_in, in_block_stride, in_row_stride, d_out, n, tx_size, tx_type, bd,
                      coeff_i32):
         self.check(self.L.b200_fwd_txfm_dev(self.h, _dev_ptr(d_in), in_block_stride, in_row_stride,
                                             _dev_ptr(d_out), n, tx_size, tx_type, bd, int(coeff_i32)))
+
+    def fwd_txfm_residual_dev(self, cur, ref, d_blocks, nblocks, d_mv_src, d_out, tx_size, tx_type, bd):
+        self.check(self.L.b200_fwd_txfm_residual_dev(self.h, C.byref(cur), C.byref(ref),
+                                                     _dev_ptr(d_blocks), nblocks, _dev_ptr(d_mv_src),
+                                                     _dev_ptr(d_out), tx_size, tx_type, bd))
 
     def fwd_txfm_batch(self, residual, tx_size, tx_type, bd=8, coeff_i32=None, out=None):
         """residual: int16 (n, h, w) numpy -> (n, w*h) coefficients (host buffers, copies inside)."""

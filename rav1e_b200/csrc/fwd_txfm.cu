@@ -55,6 +55,11 @@ bool valid_transform(int tx_size, int tx_type) {
 }
 
 struct TxArgs {
+  // fused residual source (PLANES variants): cur - ref displaced by the full-pel winner mv
+  const void *cur, *ref;
+  int cur_stride, ref_stride;
+  const b200_block *blocks;
+  const b200_me_result *mv_src;
   const int16_t *in;
   void *out;
   size_t n;
@@ -93,7 +98,7 @@ __device__ __forceinline__ void run_1d(int type, TXV (&c)[N]) {
 
 constexpr int kTxThreads = 128;
 
-template <int W, int H, typename CoefT>
+template <int W, int H, typename CoefT, bool PLANES>
 __global__ void __launch_bounds__(kTxThreads) fwd_txfm_kernel(TxArgs a) {
   constexpr int T = W > H ? W : H;       // threads per block-transform
   constexpr int PER = kTxThreads / T;    // transforms in flight per CTA
@@ -109,11 +114,32 @@ __global__ void __launch_bounds__(kTxThreads) fwd_txfm_kernel(TxArgs a) {
     // ---- columns (forward.rs:95-126)
     if (valid && t < W) {
       TXV c[H];
-      const int16_t *src = a.in + blk * a.in_block_stride + t;
+      if constexpr (PLANES) {
+        // residual computed on the fly (encoder.rs:1533 `diff`): u8 planes pair with i16
+        // coefficients, u16 planes with i32 (T::Coeff)
+        using Px = typename std::conditional<sizeof(CoefT) == 2, uint8_t, uint16_t>::type;
+        const b200_block b = a.blocks[blk];
+        int dx = 0, dy = 0;
+        if (a.mv_src && a.mv_src[blk].cost != ~0ull) {
+          dx = a.mv_src[blk].mv_col / 8;
+          dy = a.mv_src[blk].mv_row / 8;
+        }
+        const Px *pc = (const Px *)a.cur + (long long)b.y * a.cur_stride + b.x + t;
+        const Px *pr = (const Px *)a.ref + (long long)(b.y + dy) * a.ref_stride + b.x + dx + t;
 #pragma unroll
-      for (int r = 0; r < H; r++) {
-        const int rr = a.ud_flip ? H - 1 - r : r;
-        c[r] = round_shift_bit((int)src[(size_t)rr * a.in_row_stride], a.bit0);
+        for (int r = 0; r < H; r++) {
+          const int rr = a.ud_flip ? H - 1 - r : r;
+          c[r] = round_shift_bit((int)pc[(long long)rr * a.cur_stride] -
+                                     (int)pr[(long long)rr * a.ref_stride],
+                                 a.bit0);
+        }
+      } else {
+        const int16_t *src = a.in + blk * a.in_block_stride + t;
+#pragma unroll
+        for (int r = 0; r < H; r++) {
+          const int rr = a.ud_flip ? H - 1 - r : r;
+          c[r] = round_shift_bit((int)src[(size_t)rr * a.in_row_stride], a.bit0);
+        }
       }
       run_1d<H>(a.col_type, c);
       const int cc = a.lr_flip ? W - 1 - t : t;
@@ -143,10 +169,16 @@ int launch_txfm(b200_ctx *ctx, const TxArgs &a, int coeff_is_i32) {
   constexpr int PER = kTxThreads / T;
   const size_t ctas = (a.n + PER - 1) / PER;
   const int grid = (int)std::min<size_t>(ctas, (size_t)ctx->num_sms * 32);
-  if (coeff_is_i32)
-    fwd_txfm_kernel<W, H, int32_t><<<grid, kTxThreads, 0, ctx->stream>>>(a);
-  else
-    fwd_txfm_kernel<W, H, int16_t><<<grid, kTxThreads, 0, ctx->stream>>>(a);
+  if (a.cur) {
+    if (coeff_is_i32)
+      fwd_txfm_kernel<W, H, int32_t, true><<<grid, kTxThreads, 0, ctx->stream>>>(a);
+    else
+      fwd_txfm_kernel<W, H, int16_t, true><<<grid, kTxThreads, 0, ctx->stream>>>(a);
+  } else if (coeff_is_i32) {
+    fwd_txfm_kernel<W, H, int32_t, false><<<grid, kTxThreads, 0, ctx->stream>>>(a);
+  } else {
+    fwd_txfm_kernel<W, H, int16_t, false><<<grid, kTxThreads, 0, ctx->stream>>>(a);
+  }
   B200_LAUNCH_CHECK(ctx);
   return B200_OK;
 }
@@ -159,18 +191,21 @@ extern "C" int b200_valid_av1_transform(int tx_size, int tx_type) {
 extern "C" int b200_tx_width(int tx_size) { return tx_size >= 0 && tx_size < 19 ? kTxW[tx_size] : 0; }
 extern "C" int b200_tx_height(int tx_size) { return tx_size >= 0 && tx_size < 19 ? kTxH[tx_size] : 0; }
 
-extern "C" int b200_fwd_txfm_dev(b200_ctx *ctx, const int16_t *d_input, size_t in_block_stride,
-                                 size_t in_row_stride, void *d_output, size_t nblocks, int tx_size,
-                                 int tx_type, int bd, int coeff_is_i32) {
+static int fwd_txfm_impl(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                         const b200_block *d_blocks, const b200_me_result *d_mv_src,
+                         const int16_t *d_input, size_t in_block_stride, size_t in_row_stride,
+                         void *d_output, size_t nblocks, int tx_size, int tx_type, int bd,
+                         int coeff_is_i32) {
   B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
   // forward.rs:75: assert!(valid_av1_transform(tx_size, tx_type))
   B200_REQUIRE(ctx, valid_transform(tx_size, tx_type), "invalid transform: tx_size %d tx_type %d",
                tx_size, tx_type);
   B200_REQUIRE(ctx, bd == 8 || bd == 10 || bd == 12, "bit depth %d not in {8,10,12}", bd);
   if (nblocks == 0) return B200_OK;
-  B200_REQUIRE(ctx, d_input && d_output, "NULL input/output");
+  B200_REQUIRE(ctx, (d_input || cur) && d_output, "NULL input/output");
   const int w = kTxW[tx_size], h = kTxH[tx_size];
-  B200_REQUIRE(ctx, in_row_stride >= (size_t)w, "row stride %zu < width %d", in_row_stride, w);
+  B200_REQUIRE(ctx, cur || in_row_stride >= (size_t)w, "row stride %zu < width %d", in_row_stride, w);
+  (void)h;
   B200_CUDA(ctx, cudaSetDevice(ctx->device));
   const int8_t *sh;
   if (tx_type == TX_WHT_WHT) {
@@ -180,6 +215,12 @@ extern "C" int b200_fwd_txfm_dev(b200_ctx *ctx, const int16_t *d_input, size_t i
     sh = cls == 0 ? kShift4x4[b] : cls == 1 ? kShiftA[b] : cls == 2 ? kShiftB[b] : kShiftC[b];
   }
   TxArgs a;
+  a.cur = cur ? cur->data : nullptr;
+  a.ref = ref ? ref->data : nullptr;
+  a.cur_stride = cur ? cur->stride : 0;
+  a.ref_stride = ref ? ref->stride : 0;
+  a.blocks = d_blocks;
+  a.mv_src = d_mv_src;
   a.in = d_input;
   a.out = d_output;
   a.n = nblocks;
@@ -218,6 +259,30 @@ extern "C" int b200_fwd_txfm_dev(b200_ctx *ctx, const int16_t *d_input, size_t i
 #undef B200_TX
   }
   return b200_fail(ctx, B200_ERR_ARG, "unreachable tx_size %d", tx_size);
+}
+
+extern "C" int b200_fwd_txfm_dev(b200_ctx *ctx, const int16_t *d_input, size_t in_block_stride,
+                                 size_t in_row_stride, void *d_output, size_t nblocks, int tx_size,
+                                 int tx_type, int bd, int coeff_is_i32) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  B200_REQUIRE(ctx, d_input || nblocks == 0, "NULL input");
+  return fwd_txfm_impl(ctx, nullptr, nullptr, nullptr, nullptr, d_input, in_block_stride,
+                       in_row_stride, d_output, nblocks, tx_size, tx_type, bd, coeff_is_i32);
+}
+
+// Fused `diff` + forward transform (encoder.rs:1533-1544): residual of each block against the
+// reference displaced by the full-pel part of d_mv_src (NULL = zero motion), transformed without
+// a round trip of the residual through HBM.  u8 planes give i16 coefficients, u16 planes i32.
+extern "C" int b200_fwd_txfm_residual_dev(b200_ctx *ctx, const b200_plane *cur,
+                                          const b200_plane *ref, const b200_block *d_blocks,
+                                          size_t nblocks, const b200_me_result *d_mv_src,
+                                          void *d_output, int tx_size, int tx_type, int bd) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  B200_REQUIRE(ctx, cur && ref && cur->data && ref->data && cur->bpp == ref->bpp, "bad planes");
+  B200_REQUIRE(ctx, (cur->bpp == 1) == (bd == 8), "bpp %d does not match bit depth %d", cur->bpp, bd);
+  B200_REQUIRE(ctx, d_blocks || nblocks == 0, "NULL blocks");
+  return fwd_txfm_impl(ctx, cur, ref, d_blocks, d_mv_src, nullptr, 0, 0, d_output, nblocks,
+                       tx_size, tx_type, bd, cur->bpp == 2);
 }
 
 // Host-buffer form: packed residual blocks in, coefficients out.

@@ -52,6 +52,7 @@ struct MeArgs {
   int allow_hp;
   int use_satd;
   int smem_bytes;  // dynamic smem given to the staged kernels
+  size_t ngroups;  // ceil(nblocks / G) for the grouped kernel
 };
 
 // ---------------------------------------------------------------- Hadamard (dist.rs:55-149)
@@ -291,22 +292,16 @@ __device__ __forceinline__ uint32_t row_sad_u8(const uint32_t *__restrict__ wrow
 }
 
 // Stage `rows` x `row_bytes` (row_bytes multiple of 16, src 16-byte aligned) into smem.
-// Incremental (row, vec) stepping: no per-element integer division.
+// Half-warps own rows: 16 lanes x 16 bytes cover a 256-byte row per step, no index division.
 __device__ __forceinline__ void stage_window(uint32_t *smem, int pitch_words, const uint8_t *src,
                                              long long src_stride, int rows, int row_bytes) {
   const int vpr = row_bytes >> 4;
-  const int nthr = blockDim.x;
-  int y = threadIdx.x / vpr, v = threadIdx.x - y * vpr;
-  const int dy = nthr / vpr, dv = nthr - dy * vpr;
-  while (y < rows) {
-    const uint4 q = __ldg((const uint4 *)(src + (long long)y * src_stride) + v);
-    *(uint4 *)(smem + y * pitch_words + v * 4) = q;
-    y += dy;
-    v += dv;
-    if (v >= vpr) {
-      v -= vpr;
-      y++;
-    }
+  const int l16 = threadIdx.x & 15;
+  const int nhw = blockDim.x >> 4;
+  for (int y = threadIdx.x >> 4; y < rows; y += nhw) {
+    const uint4 *s = (const uint4 *)(src + (long long)y * src_stride);
+    uint4 *d = (uint4 *)(smem + y * pitch_words);
+    for (int v = l16; v < vpr; v += 16) d[v] = __ldg(s + v);
   }
 }
 
@@ -427,12 +422,12 @@ __global__ void __launch_bounds__(256) me_cand_group_u8(MeArgs a, int G) {
   constexpr int NCH = SATD ? (W / S) * (H / S) : 1;           // chunks per candidate
   constexpr int TPC = NCH < 32 ? NCH : 32;                    // threads per candidate
   constexpr int ORGW = H * W / 4;                             // org words per block
-  const int nthr = blockDim.x;
+  constexpr int nthr = 256;  // launch_cand_group always uses 256 threads
   const int lane = threadIdx.x & 31;
   uint32_t *const s_org = smem;                               // [G][ORGW]
   uint32_t *const win = smem + G * ORGW;
   const int win_bytes = a.smem_bytes - G * ORGW * 4;
-  const size_t ngroups = (a.nblocks + G - 1) / G;
+  const size_t ngroups = a.ngroups;  // host-computed: no 64-bit division per thread
 
   for (size_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const size_t gb0 = grp * G, gb1 = min(gb0 + (size_t)G, a.nblocks);
@@ -868,6 +863,7 @@ int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px) {
   }
   a.smem_bytes = (int)smem;
   const size_t ngroups = (a.nblocks + G - 1) / G;
+  a.ngroups = ngroups;
   const int grid = (int)std::min<size_t>(ngroups, (size_t)ctx->num_sms * 32);
   me_cand_group_u8<W, H, SATD><<<grid, threads, smem, ctx->stream>>>(a, G);
   B200_LAUNCH_CHECK(ctx);
@@ -943,6 +939,7 @@ extern "C" int b200_me_candidates_dev(b200_ctx *ctx, const b200_plane *cur, cons
   a.allow_hp = p->allow_high_precision_mv;
   a.use_satd = p->use_satd;
   a.smem_bytes = 0;
+  a.ngroups = 0;
 
   // Fast path: 8-bit, candidates grouped by block (CSR), block sizes up to 64x64.
   if (cur->bpp == 1 && d_cand_offsets && nblocks > 0 && (ref->stride & 15) == 0 &&

@@ -63,6 +63,16 @@ def lib():
     L.orc_full_search_blocks.argtypes = [vp, pd, vp, pd, i32, i32, i32, vp, sz, i32, i32, i32, i32,
                                          i32, u32, i32, vp, i32]
     L.orc_num_threads.restype = i32
+    L.orc_put_8tap.restype = None
+    L.orc_put_8tap.argtypes = [vp, pd, vp, pd] + [i32] * 8
+    L.orc_prep_8tap.restype = None
+    L.orc_prep_8tap.argtypes = [vp, vp, pd] + [i32] * 8
+    L.orc_mc_avg.restype = None
+    L.orc_mc_avg.argtypes = [vp, pd, i32, vp, vp, i32, i32, i32]
+    L.orc_get_filter.restype = None
+    L.orc_get_filter.argtypes = [i32, i32, i32, C.POINTER(C.c_int32)]
+    L.orc_mc_blocks.restype = None
+    L.orc_mc_blocks.argtypes = [vp, pd, i32, vp, vp, sz] + [i32] * 8 + [vp, i32]
     L.orc_valid_av1_transform.restype = i32
     L.orc_valid_av1_transform.argtypes = [i32, i32]
     L.orc_tx_width.restype = i32
@@ -181,4 +191,37 @@ def forward_transform_batch(residual, tx_size, tx_type, bd=8, coeff_i32=None, th
     out = np.empty((n, w * h), np.int32 if coeff_i32 else np.int16)
     L.orc_forward_transform_batch(ptr(residual), ptr(out), n, tx_size, tx_type, bd, int(coeff_i32),
                                   threads)
+    return out
+
+
+# ---------------------------------------------------------------- motion compensation
+def put_8tap(src: Plane, x, y, w, h, col_frac, row_frac, mode_x, mode_y, bit_depth):
+    dst = np.zeros((h, w), src.data.dtype)
+    lib().orc_put_8tap(ptr(dst), w, src.at(x, y), src.stride, src.bpp, w, h, col_frac, row_frac,
+                       mode_x, mode_y, bit_depth)
+    return dst
+
+
+def prep_8tap(src: Plane, x, y, w, h, col_frac, row_frac, mode_x, mode_y, bit_depth):
+    tmp = np.zeros((h, w), np.int16)
+    lib().orc_prep_8tap(ptr(tmp), src.at(x, y), src.stride, src.bpp, w, h, col_frac, row_frac,
+                        mode_x, mode_y, bit_depth)
+    return tmp
+
+
+def mc_avg(t1, t2, bit_depth):
+    h, w = t1.shape
+    dst = np.zeros((h, w), np.uint8 if bit_depth == 8 else np.uint16)
+    lib().orc_mc_avg(ptr(dst), w, dst.itemsize, ptr(np.ascontiguousarray(t1)),
+                     ptr(np.ascontiguousarray(t2)), w, h, bit_depth)
+    return dst
+
+
+def mc_blocks(ref: Plane, blocks, mvs, w, h, mode_x, mode_y, bit_depth, xdec=0, ydec=0, kind=0,
+              threads=0):
+    n = len(blocks)
+    out = np.zeros((n, h, w), ref.data.dtype if kind == 0 else np.int16)
+    mvs = np.ascontiguousarray(mvs, dtype=np.int16)
+    lib().orc_mc_blocks(ref.origin_ptr(), ref.stride, ref.bpp, ptr(blocks), ptr(mvs), n, w, h,
+                        mode_x, mode_y, bit_depth, xdec, ydec, kind, ptr(out), threads)
     return out

@@ -79,3 +79,41 @@ def test_1080p_frame_sweep_checksum():
     assert int(got.astype(np.int64).sum()) == int(want.astype(np.int64).sum())
     np.testing.assert_array_equal(got[::97], want[::97])
     np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("dtype,bd", [(np.uint8, 8), (np.uint16, 10)])
+def test_fused_residual_transform(dtype, bd):
+    """b200_fwd_txfm_residual_dev == oracle(diff -> forward_transform), and the standalone
+    residual kernel agrees with numpy (encoder.rs:1533-1544)."""
+    import torch
+    c = G.ctx()
+    W, H, PAD = 256, 128, 96
+    cur, ref = G.make_planes(W, H, PAD, dtype, seed=5, bit_depth=bd)
+    ocur, dcur = G.both_planes(cur, PAD)
+    oref, dref = G.both_planes(ref, PAD)
+    blocks = G.grid_blocks(W, H, 16, 16)
+    n = len(blocks)
+    rng = np.random.default_rng(1)
+    best = np.zeros(n, B.ME_RESULT_DTYPE)
+    best["mv_col"] = rng.integers(-20, 21, n) * 8 + rng.integers(-7, 8, n)
+    best["mv_row"] = rng.integers(-20, 21, n) * 8 + rng.integers(-7, 8, n)
+    best["cost"][::7] = np.uint64(2**64 - 1)          # empty results mean zero motion
+    resid = np.zeros((n, 16, 16), np.int16)
+    for i, b in enumerate(blocks):
+        dx = int(np.trunc(best["mv_col"][i] / 8)) if best["cost"][i] != np.uint64(2**64 - 1) else 0
+        dy = int(np.trunc(best["mv_row"][i] / 8)) if best["cost"][i] != np.uint64(2**64 - 1) else 0
+        x, y = int(b["x"]), int(b["y"])
+        p = PAD
+        cb = ocur.data[p + y:p + y + 16, p + x:p + x + 16].astype(np.int32)
+        rb = oref.data[p + y + dy:p + y + dy + 16, p + x + dx:p + x + dx + 16].astype(np.int32)
+        resid[i] = cb - rb
+    d_blocks, d_best = G.to_dev(blocks), G.to_dev(best)
+    d_res = torch.empty((n, 16, 16), dtype=torch.int16, device="cuda")
+    c.block_residual_dev(dcur, dref, d_blocks, n, d_best, 16, 16, d_res)
+    i32 = bd > 8
+    d_out = torch.empty((n, 256), dtype=torch.int32 if i32 else torch.int16, device="cuda")
+    c.fwd_txfm_residual_dev(dcur, dref, d_blocks, n, d_best, d_out, 2, 1, bd)
+    c.synchronize()
+    np.testing.assert_array_equal(d_res.cpu().numpy(), resid)
+    want = O.forward_transform_batch(resid, 2, 1, bd, coeff_i32=i32)
+    np.testing.assert_array_equal(d_out.cpu().numpy(), want)
