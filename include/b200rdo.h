@@ -248,6 +248,31 @@ int b200_mc_blocks_dev(b200_ctx *ctx, const b200_plane *ref, const b200_block *d
 int b200_mc_avg_dev(b200_ctx *ctx, const int16_t *d_tmp1, const int16_t *d_tmp2, void *d_dst,
                     size_t nblocks, int w, int h, int bit_depth);
 
+/* ------------------------------------------------------------------ CDEF (cdef.rs)
+ * Per-call forms with the asm signatures rav1e binds (asm/x86/cdef.rs:16-37, :184-191):
+ *   rav1e_cdef_dir_{8,16}bpc(img, stride_bytes, &var[, bitdepth_max]) -> dir
+ *   rav1e_cdef_filter_{4x4,4x8,8x8}(dst, dst_stride, tmp_u16, tmp_stride, pri, sec, dir, damping)
+ * `tmp` addresses the block's top-left inside the caller-built padded u16 tile (2 px border,
+ * CDEF_VERY_LARGE = 0x8000 where pixels are unavailable, cdef.rs:161-194); strides in BYTES. */
+int32_t b200_cdef_dir(const void *img, ptrdiff_t stride, uint32_t *var, int bit_depth);
+void b200_cdef_filter_block(void *dst, ptrdiff_t dst_stride, const uint16_t *tmp,
+                            ptrdiff_t tmp_stride, int pri_strength, int sec_strength, int dir,
+                            int damping, int bit_depth, int xdec, int ydec);
+/* Frame-level batch = cdef_filter_tile (cdef.rs:597-625) with the tile rect equal to the frame.
+ * b200_cdef_find_dir_dev: cdef_analyze_superblock for every 8x8 luma block (d_skip8: one byte
+ * per 8x8 block = AND of its four 4x4 `skip` flags, row-major, may be NULL); writes dir/var
+ * (0 where skipped).  b200_cdef_filter_plane_dev: cdef_filter_superblock for one plane; `in`
+ * and `out` are distinct planes of the same geometry; d_strength_sb holds the 6-bit strength
+ * (pri*4+sec; fi.cdef_y_strengths / cdef_uv_strengths[cdef_index]) per 64x64 superblock,
+ * row-major with ceil(luma_width/64) entries per row; damping = fi.cdef_damping. */
+int b200_cdef_find_dir_dev(b200_ctx *ctx, const b200_plane *luma, int bit_depth,
+                           const uint8_t *d_skip8, uint8_t *d_dir, int32_t *d_var);
+int b200_cdef_filter_plane_dev(b200_ctx *ctx, const b200_plane *in, const b200_plane *out,
+                               int plane, int xdec, int ydec, int luma_width, int luma_height,
+                               int bit_depth, int damping, const uint8_t *d_skip8,
+                               const uint8_t *d_dir, const int32_t *d_var,
+                               const uint8_t *d_strength_sb);
+
 #ifdef __cplusplus
 }
 #endif

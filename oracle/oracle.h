@@ -129,11 +129,23 @@ void orc_pred_cfl_ac(int16_t *ac, const void *luma, ptrdiff_t luma_stride, int b
                      int w_pad, int h_pad, int xdec, int ydec);
 
 /* ----------------------------------------------------------------- cdef.rs */
+int orc_first_max_element(const int32_t *elems, int n, int32_t *max_out);
 int orc_cdef_find_dir(const void *img, ptrdiff_t stride, int bpp, uint32_t *var, int coeff_shift);
+/* asm-facing form: `in` is the padded u16 tile (asm/x86/cdef.rs:16-37) */
 void orc_cdef_filter_block(void *dst, ptrdiff_t dst_stride, int dst_bpp, const uint16_t *in,
                            ptrdiff_t in_stride, int pri_strength, int sec_strength, int dir,
                            int damping, int bit_depth, int xdec, int ydec, int edges);
-int orc_first_max_element(const int32_t *elems, int n, int32_t *max_out);
+/* pixel-facing form (cdef.rs:198-231): pads into tmp16 according to `edges` first */
+void orc_cdef_filter_block_px(void *dst, ptrdiff_t dst_stride, const void *in, ptrdiff_t istride,
+                              int bpp, int pri_strength, int sec_strength, int dir, int damping,
+                              int bit_depth, int xdec, int ydec, int edges);
+int orc_cdef_adjust_strength(int strength, int var);
+void orc_cdef_analyze_frame(const void *luma, ptrdiff_t stride, int bpp, int width, int height,
+                            int bit_depth, const uint8_t *skip8, uint8_t *dir, int32_t *var);
+void orc_cdef_filter_plane(const void *in, ptrdiff_t in_stride, void *out, ptrdiff_t out_stride,
+                           int bpp, int plane, int xdec, int ydec, int width, int height,
+                           int bit_depth, int damping, const uint8_t *skip8, const uint8_t *dir,
+                           const int32_t *var, const uint8_t *strength_sb);
 
 int orc_num_threads(void);
 

@@ -118,6 +118,12 @@ def lib():
     L.b200_mc_avg.restype = None
     L.b200_mc_blocks_dev.argtypes = [vp, pp, vp, vp, sz] + [i32] * 8 + [vp]
     L.b200_mc_avg_dev.argtypes = [vp, vp, vp, vp, sz, i32, i32, i32]
+    L.b200_cdef_dir.argtypes = [vp, C.c_ssize_t, C.POINTER(u32), i32]
+    L.b200_cdef_dir.restype = i32
+    L.b200_cdef_filter_block.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t] + [i32] * 7
+    L.b200_cdef_filter_block.restype = None
+    L.b200_cdef_find_dir_dev.argtypes = [vp, pp, i32, vp, vp, vp]
+    L.b200_cdef_filter_plane_dev.argtypes = [vp, pp, pp] + [i32] * 7 + [vp, vp, vp, vp]
     _LIB = L
     return L
 
@@ -204,6 +210,17 @@ class Context:
     def mc_avg_dev(self, d_t1, d_t2, d_dst, n, w, h, bit_depth):
         self.check(self.L.b200_mc_avg_dev(self.h, _dev_ptr(d_t1), _dev_ptr(d_t2), _dev_ptr(d_dst),
                                           n, w, h, bit_depth))
+
+    # ---- CDEF
+    def cdef_find_dir_dev(self, luma, bit_depth, d_skip8, d_dir, d_var):
+        self.check(self.L.b200_cdef_find_dir_dev(self.h, C.byref(luma), bit_depth, _dev_ptr(d_skip8),
+                                                 _dev_ptr(d_dir), _dev_ptr(d_var)))
+
+    def cdef_filter_plane_dev(self, inp, out, plane, xdec, ydec, luma_w, luma_h, bit_depth, damping,
+                              d_skip8, d_dir, d_var, d_strength_sb):
+        self.check(self.L.b200_cdef_filter_plane_dev(
+            self.h, C.byref(inp), C.byref(out), plane, xdec, ydec, luma_w, luma_h, bit_depth,
+            damping, _dev_ptr(d_skip8), _dev_ptr(d_dir), _dev_ptr(d_var), _dev_ptr(d_strength_sb)))
 
     # ---- forward transform
     def fwd_txfm_dev(self, d_in, in_block_stride, in_row_stride, d_out, n, tx_size, tx_type, bd,

@@ -1,0 +1,366 @@
+// cdef.cu — CDEF direction search and constrained directional filter (rav1e src/cdef.rs) for
+// sm_100a, batched over every 8x8 block of a frame plane.
+//
+//   cdef_find_dir_kernel   one thread per 8x8 luma block: the 8 directional partial-sum costs
+//                          (cdef.rs:84-143) held in registers, first-max direction, variance.
+//   cdef_filter_kernel     one thread per output pixel.  Instead of materialising the
+//                          reference's padded 12x12 u16 scratch with CDEF_VERY_LARGE sentinels
+//                          (cdef.rs:161-231) the tap loader decides availability from the block's
+//                          edge flags and returns the sentinel itself, so taps read the input
+//                          plane directly (L1/L2 resident) and nothing is staged.
+// The frame-level driver reproduces cdef_filter_superblock (cdef.rs:401-570): edge flags from
+// the block's position in the frame, skip -> copy, strength split, adjust_strength on luma,
+// chroma damping - 1 and the 4:2:2 direction remap.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kVeryLarge = 0x8000;  // CDEF_VERY_LARGE, cdef.rs:30
+enum { HAVE_LEFT = 1, HAVE_RIGHT = 2, HAVE_TOP = 4, HAVE_BOTTOM = 8 };
+
+__constant__ int kDivTable[9] = {0, 840, 420, 280, 210, 168, 140, 120, 105};  // cdef.rs:54
+
+template <typename T>
+__device__ int find_dir_8x8(const T *img, int stride, int coeff_shift, unsigned *var_out) {
+  int partial[8][15];
+#pragma unroll
+  for (int d = 0; d < 8; d++)
+#pragma unroll
+    for (int k = 0; k < 15; k++) partial[d][k] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int x = ((int)img[(long long)i * stride + j] >> coeff_shift) - 128;
+      partial[0][i + j] += x;
+      partial[1][i + j / 2] += x;
+      partial[2][i] += x;
+      partial[3][3 + i - j / 2] += x;
+      partial[4][7 + i - j] += x;
+      partial[5][3 - i / 2 + j] += x;
+      partial[6][j] += x;
+      partial[7][i / 2 + j] += x;
+    }
+  }
+  int cost[8];
+#pragma unroll
+  for (int d = 0; d < 8; d++) cost[d] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    cost[2] += partial[2][i] * partial[2][i];
+    cost[6] += partial[6][i] * partial[6][i];
+  }
+  cost[2] *= 105;
+  cost[6] *= 105;
+#pragma unroll
+  for (int i = 0; i < 7; i++) {
+    cost[0] += (partial[0][i] * partial[0][i] + partial[0][14 - i] * partial[0][14 - i]) * kDivTable[i + 1];
+    cost[4] += (partial[4][i] * partial[4][i] + partial[4][14 - i] * partial[4][14 - i]) * kDivTable[i + 1];
+  }
+  cost[0] += partial[0][7] * partial[0][7] * 105;
+  cost[4] += partial[4][7] * partial[4][7] * 105;
+#pragma unroll
+  for (int i = 1; i < 8; i += 2) {
+#pragma unroll
+    for (int j = 0; j < 5; j++) cost[i] += partial[i][3 + j] * partial[i][3 + j];
+    cost[i] *= 105;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      cost[i] += (partial[i][j] * partial[i][j] + partial[i][10 - j] * partial[i][10 - j]) * kDivTable[2 * j + 2];
+  }
+  int best = 0, best_cost = cost[0];
+#pragma unroll
+  for (int d = 1; d < 8; d++)
+    if (cost[d] > best_cost) {  // strict: first maximum wins (cdef.rs:66-76)
+      best = d;
+      best_cost = cost[d];
+    }
+  int ortho = 0;
+#pragma unroll
+  for (int d = 0; d < 8; d++)
+    if (d == ((best + 4) & 7)) ortho = cost[d];
+  *var_out = (unsigned)((best_cost - ortho) >> 10);
+  return best;
+}
+
+template <typename T>
+__global__ void cdef_find_dir_kernel(const T *luma, int stride, int w8, int h8, int coeff_shift,
+                                     const uint8_t *skip8, uint8_t *dir, int *var) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < w8 * h8; b += gridDim.x * blockDim.x) {
+    const int by = b / w8, bx = b - by * w8;
+    unsigned v = 0;
+    int d = 0;
+    if (!(skip8 && skip8[b]))
+      d = find_dir_8x8<T>(luma + (long long)(8 * by) * stride + 8 * bx, stride, coeff_shift, &v);
+    dir[b] = (uint8_t)d;
+    var[b] = (int)v;
+  }
+}
+
+// cdef.rs:146-159
+__device__ __forceinline__ int constrain(int diff, int threshold, int damping) {
+  if (threshold == 0) return 0;
+  const int shift = max(0, damping - (31 - __clz(threshold)));
+  const int ad = abs(diff);
+  const int mag = min(max(threshold - (ad >> shift), 0), ad);
+  return diff < 0 ? -mag : mag;
+}
+
+// cdef.rs:315-322
+__device__ __forceinline__ int adjust_strength(int strength, int var) {
+  const int i = (var >> 6) != 0 ? min(31 - __clz(var >> 6), 12) : 0;
+  return var != 0 ? (strength * (4 + i) + 8) >> 4 : 0;
+}
+
+// direction offsets (dy, dx) for k = 0, 1  (cdef.rs:242-251)
+__constant__ signed char kDirs[8][2][2] = {{{-1, 1}, {-2, 2}}, {{0, 1}, {-1, 2}}, {{0, 1}, {0, 2}},
+                                           {{0, 1}, {1, 2}},   {{1, 1}, {2, 2}},  {{1, 0}, {2, 1}},
+                                           {{1, 0}, {2, 0}},   {{1, 0}, {2, -1}}};
+
+// One output pixel of cdef_filter_block (cdef.rs:253-296).  `load(dy, dx)` returns the input at
+// (i+dy, j+dx) relative to the block, or CDEF_VERY_LARGE where the reference's padded scratch
+// would hold the sentinel.
+template <typename Load>
+__device__ __forceinline__ int cdef_pixel(Load load, int pri_strength, int sec_strength, int dir,
+                                          int damping, int coeff_shift) {
+  const int x = load(0, 0);
+  const int sel = (pri_strength >> coeff_shift) & 1;
+  const int pri_taps[2] = {sel ? 3 : 4, sel ? 3 : 2};
+  const int sec_taps[2] = {2, 1};
+  int sum = 0, mx = x, mn = x;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int d0y = kDirs[dir][k][0], d0x = kDirs[dir][k][1];
+    const int d1y = kDirs[(dir + 2) & 7][k][0], d1x = kDirs[(dir + 2) & 7][k][1];
+    const int d2y = kDirs[(dir + 6) & 7][k][0], d2x = kDirs[(dir + 6) & 7][k][1];
+    const int p[2] = {load(d0y, d0x), load(-d0y, -d0x)};
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      sum += pri_taps[k] * constrain(p[t] - x, pri_strength, damping);
+      if (p[t] != kVeryLarge) mx = max(p[t], mx);
+      mn = min(p[t], mn);
+    }
+    const int s[4] = {load(d1y, d1x), load(-d1y, -d1x), load(d2y, d2x), load(-d2y, -d2x)};
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      if (s[t] != kVeryLarge) mx = max(s[t], mx);
+      mn = min(s[t], mn);
+      sum += sec_taps[k] * constrain(s[t] - x, sec_strength, damping);
+    }
+  }
+  const int v = x + ((8 + sum - (sum < 0)) >> 4);
+  return min(max(v, mn), mx);
+}
+
+struct CdefPlaneArgs {
+  const void *in;
+  void *out;
+  int in_stride, out_stride;  // elements
+  int plane, xdec, ydec;
+  int w8, h8, sbw;            // luma 8x8 grid and superblocks per row
+  int bit_depth, damping;
+  const uint8_t *skip8;
+  const uint8_t *dir;
+  const int *var;
+  const uint8_t *strength_sb;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) cdef_filter_kernel(CdefPlaneArgs a) {
+  const int xsize = 8 >> a.xdec, ysize = 8 >> a.ydec;
+  const int pw = a.w8 * xsize, ph = a.h8 * ysize;
+  const int coeff_shift = a.bit_depth - 8;
+  const T *in = (const T *)a.in;
+  T *out = (T *)a.out;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < (long long)pw * ph;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(idx / pw), x = (int)(idx - (long long)y * pw);
+    const int gy = y / ysize, gx = x / xsize, i = y - gy * ysize, j = x - gx * xsize;
+    const int b = gy * a.w8 + gx;
+    const T *blk = in + (long long)(gy * ysize) * a.in_stride + gx * xsize;
+    int v;
+    if (a.skip8 && a.skip8[b]) {
+      v = (int)blk[(long long)i * a.in_stride + j];  // cdef.rs:557-564
+    } else {
+      int edges = 0;  // cdef.rs:446-466 flattened: frame position decides the padding we have
+      if (gy > 0) edges |= HAVE_TOP;
+      if (gx > 0) edges |= HAVE_LEFT;
+      if (gy + 1 < a.h8) edges |= HAVE_BOTTOM;
+      if (gx + 1 < a.w8) edges |= HAVE_RIGHT;
+      const int strength = a.strength_sb[(gy >> 3) * a.sbw + (gx >> 3)];
+      const int pri = strength >> 2;
+      int sec = strength & 3;
+      if (sec == 3) sec = 4;  // cdef.rs:421-426
+      const int d = a.dir[b];
+      int local_pri, local_dir, local_damping = a.damping + coeff_shift;
+      const int local_sec = sec << coeff_shift;
+      if (a.plane == 0) {
+        local_pri = adjust_strength(pri << coeff_shift, a.var[b]);
+        local_dir = pri != 0 ? d : 0;
+      } else {
+        local_pri = pri << coeff_shift;
+        local_damping -= 1;
+        const int remap = (0x66654207 >> (4 * d)) & 7;  // [7,0,2,4,5,6,6,6], cdef.rs:505-509
+        local_dir = pri != 0 ? (a.xdec != a.ydec ? remap : d) : 0;
+      }
+      const int stride = a.in_stride;
+      auto load = [&](int dy, int dx) -> int {
+        const int yy = i + dy, xx = j + dx;
+        if ((xx < 0 && !(edges & HAVE_LEFT)) || (xx >= xsize && !(edges & HAVE_RIGHT)) ||
+            (yy < 0 && !(edges & HAVE_TOP)) || (yy >= ysize && !(edges & HAVE_BOTTOM)))
+          return kVeryLarge;
+        return (int)blk[(long long)yy * stride + xx];
+      };
+      v = cdef_pixel(load, local_pri, local_sec, local_dir, local_damping, coeff_shift);
+    }
+    out[(long long)y * a.out_stride + x] = (T)v;
+  }
+}
+
+// Asm-facing single block: padded u16 tile in, pixels out (asm/x86/cdef.rs:16-37).
+template <typename T>
+__global__ void cdef_filter_tmp16_kernel(T *dst, int dst_stride, const uint16_t *tmp, int tmp_stride,
+                                         int pri, int sec, int dir, int damping, int bit_depth,
+                                         int xsize, int ysize) {
+  const int t = threadIdx.x;
+  if (t >= xsize * ysize) return;
+  const int i = t / xsize, j = t - i * xsize;
+  auto load = [&](int dy, int dx) -> int { return (int)tmp[(i + dy) * tmp_stride + (j + dx)]; };
+  dst[i * dst_stride + j] = (T)cdef_pixel(load, pri, sec, dir, damping, bit_depth - 8);
+}
+
+}  // namespace
+
+extern "C" int b200_cdef_find_dir_dev(b200_ctx *ctx, const b200_plane *luma, int bit_depth,
+                                      const uint8_t *d_skip8, uint8_t *d_dir, int32_t *d_var) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  B200_REQUIRE(ctx, luma && luma->data && d_dir && d_var, "NULL argument");
+  B200_REQUIRE(ctx, (luma->width & 7) == 0 && (luma->height & 7) == 0,
+               "luma %dx%d must be a multiple of 8 (rav1e pads frames to 8)", luma->width, luma->height);
+  B200_REQUIRE(ctx, (luma->bpp == 1) == (bit_depth == 8), "bpp %d vs bit depth %d", luma->bpp, bit_depth);
+  B200_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int w8 = luma->width >> 3, h8 = luma->height >> 3;
+  const int grid = std::min((w8 * h8 + 127) / 128, ctx->num_sms * 16);
+  if (luma->bpp == 1)
+    cdef_find_dir_kernel<uint8_t><<<grid, 128, 0, ctx->stream>>>((const uint8_t *)luma->data, luma->stride, w8, h8,
+                                                                  bit_depth - 8, d_skip8, d_dir, d_var);
+  else
+    cdef_find_dir_kernel<uint16_t><<<grid, 128, 0, ctx->stream>>>((const uint16_t *)luma->data, luma->stride, w8,
+                                                                   h8, bit_depth - 8, d_skip8, d_dir, d_var);
+  B200_LAUNCH_CHECK(ctx);
+  return B200_OK;
+}
+
+extern "C" int b200_cdef_filter_plane_dev(b200_ctx *ctx, const b200_plane *in, const b200_plane *out,
+                                          int plane, int xdec, int ydec, int luma_width,
+                                          int luma_height, int bit_depth, int damping,
+                                          const uint8_t *d_skip8, const uint8_t *d_dir,
+                                          const int32_t *d_var, const uint8_t *d_strength_sb) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  B200_REQUIRE(ctx, in && out && in->data && out->data && in->bpp == out->bpp, "bad planes");
+  B200_REQUIRE(ctx, in->data != out->data, "CDEF cannot run in place (taps read unfiltered neighbours)");
+  B200_REQUIRE(ctx, (luma_width & 7) == 0 && (luma_height & 7) == 0, "luma size must be a multiple of 8");
+  B200_REQUIRE(ctx, (xdec == 0 || xdec == 1) && (ydec == 0 || ydec == 1) && plane >= 0 && plane < 3, "bad plane");
+  B200_REQUIRE(ctx, (in->bpp == 1) == (bit_depth == 8), "bpp %d vs bit depth %d", in->bpp, bit_depth);
+  B200_REQUIRE(ctx, d_dir && d_var && d_strength_sb, "NULL dir/var/strength");
+  B200_CUDA(ctx, cudaSetDevice(ctx->device));
+  CdefPlaneArgs a;
+  a.in = in->data;
+  a.out = out->data;
+  a.in_stride = in->stride;
+  a.out_stride = out->stride;
+  a.plane = plane;
+  a.xdec = xdec;
+  a.ydec = ydec;
+  a.w8 = luma_width >> 3;
+  a.h8 = luma_height >> 3;
+  a.sbw = (luma_width + 63) >> 6;
+  a.bit_depth = bit_depth;
+  a.damping = damping;
+  a.skip8 = d_skip8;
+  a.dir = d_dir;
+  a.var = d_var;
+  a.strength_sb = d_strength_sb;
+  const long long total = (long long)(luma_width >> xdec) * (luma_height >> ydec);
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 32);
+  if (in->bpp == 1)
+    cdef_filter_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(a);
+  else
+    cdef_filter_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(a);
+  B200_LAUNCH_CHECK(ctx);
+  return B200_OK;
+}
+
+// ---- per-call forms with the reference's asm signatures (asm/x86/cdef.rs:16-37, :184-191)
+extern "C" int32_t b200_cdef_dir(const void *img, ptrdiff_t stride, uint32_t *var, int bit_depth) {
+  b200_ctx *ctx = b200_default_ctx();
+  const int bpp = bit_depth == 8 ? 1 : 2;
+  void *dbase = nullptr;
+  int st = B200_OK;
+  if (cudaSetDevice(ctx->device) != cudaSuccess ||
+      cudaMallocAsync(&dbase, 64 * bpp + 256 + 64, ctx->stream) != cudaSuccess)
+    st = b200_fail(ctx, B200_ERR_CUDA, "alloc failed");
+  uint8_t *d_dir = (uint8_t *)dbase + 256;
+  int32_t *d_var = (int32_t *)((uint8_t *)dbase + 256 + 16);
+  if (!st && cudaMemcpy2DAsync(dbase, 8 * bpp, img, (size_t)stride, 8 * bpp, 8, cudaMemcpyHostToDevice,
+                               ctx->stream) != cudaSuccess)
+    st = b200_fail(ctx, B200_ERR_CUDA, "H2D copy failed");
+  if (!st) {
+    b200_plane p{dbase, 8, 8, 8, 0, bpp, nullptr};
+    st = b200_cdef_find_dir_dev(ctx, &p, bit_depth, nullptr, d_dir, d_var);
+  }
+  uint8_t dir = 0;
+  int32_t v = 0;
+  if (!st && (cudaMemcpyAsync(&dir, d_dir, 1, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+              cudaMemcpyAsync(&v, d_var, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess))
+    st = b200_fail(ctx, B200_ERR_CUDA, "D2H copy failed");
+  if (dbase) cudaFreeAsync(dbase, ctx->stream);
+  if (!st && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = b200_fail(ctx, B200_ERR_CUDA, "sync failed");
+  if (st) {
+    fprintf(stderr, "b200rdo: FATAL: cdef_dir failed: %s\n", b200_last_error(ctx));
+    abort();
+  }
+  *var = (uint32_t)v;
+  return dir;
+}
+
+extern "C" void b200_cdef_filter_block(void *dst, ptrdiff_t dst_stride, const uint16_t *tmp,
+                                       ptrdiff_t tmp_stride, int pri_strength, int sec_strength,
+                                       int dir, int damping, int bit_depth, int xdec, int ydec) {
+  b200_ctx *ctx = b200_default_ctx();
+  const int bpp = bit_depth == 8 ? 1 : 2;
+  const int xsize = 8 >> xdec, ysize = 8 >> ydec;
+  const int tw = xsize + 4, th = ysize + 4;
+  void *dbase = nullptr;
+  int st = B200_OK;
+  if (cudaSetDevice(ctx->device) != cudaSuccess ||
+      cudaMallocAsync(&dbase, 512 + 64 * bpp, ctx->stream) != cudaSuccess)
+    st = b200_fail(ctx, B200_ERR_CUDA, "alloc failed");
+  // the caller's pointer addresses the block's top-left inside the padded tile (2 px border);
+  // tmp_stride is in BYTES like every asm-ABI stride
+  const uint8_t *h0 = (const uint8_t *)tmp - 2 * tmp_stride - 2 * 2;
+  if (!st && cudaMemcpy2DAsync(dbase, tw * 2, h0, (size_t)tmp_stride, tw * 2, th, cudaMemcpyHostToDevice,
+                               ctx->stream) != cudaSuccess)
+    st = b200_fail(ctx, B200_ERR_CUDA, "H2D copy failed");
+  void *d_dst = (uint8_t *)dbase + 512;
+  if (!st) {
+    const uint16_t *d_tmp = (const uint16_t *)dbase + 2 * tw + 2;
+    if (bpp == 1)
+      cdef_filter_tmp16_kernel<uint8_t><<<1, 64, 0, ctx->stream>>>((uint8_t *)d_dst, xsize, d_tmp, tw, pri_strength,
+                                                                   sec_strength, dir, damping, bit_depth, xsize, ysize);
+    else
+      cdef_filter_tmp16_kernel<uint16_t><<<1, 64, 0, ctx->stream>>>((uint16_t *)d_dst, xsize, d_tmp, tw, pri_strength,
+                                                                    sec_strength, dir, damping, bit_depth, xsize, ysize);
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) st = b200_fail(ctx, B200_ERR_CUDA, "launch failed");
+  }
+  if (!st && cudaMemcpy2DAsync(dst, (size_t)dst_stride, d_dst, xsize * bpp, xsize * bpp, ysize,
+                               cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+    st = b200_fail(ctx, B200_ERR_CUDA, "D2H copy failed");
+  if (dbase) cudaFreeAsync(dbase, ctx->stream);
+  if (!st && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = b200_fail(ctx, B200_ERR_CUDA, "sync failed");
+  if (st) {
+    fprintf(stderr, "b200rdo: FATAL: cdef_filter_block failed: %s\n", b200_last_error(ctx));
+    abort();
+  }
+}

@@ -73,6 +73,20 @@ def lib():
     L.orc_get_filter.argtypes = [i32, i32, i32, C.POINTER(C.c_int32)]
     L.orc_mc_blocks.restype = None
     L.orc_mc_blocks.argtypes = [vp, pd, i32, vp, vp, sz] + [i32] * 8 + [vp, i32]
+    L.orc_first_max_element.restype = i32
+    L.orc_first_max_element.argtypes = [vp, i32, C.POINTER(C.c_int32)]
+    L.orc_cdef_find_dir.restype = i32
+    L.orc_cdef_find_dir.argtypes = [vp, pd, i32, C.POINTER(u32), i32]
+    L.orc_cdef_filter_block.restype = None
+    L.orc_cdef_filter_block.argtypes = [vp, pd, i32, vp, pd] + [i32] * 8
+    L.orc_cdef_filter_block_px.restype = None
+    L.orc_cdef_filter_block_px.argtypes = [vp, pd, vp, pd] + [i32] * 9
+    L.orc_cdef_adjust_strength.restype = i32
+    L.orc_cdef_adjust_strength.argtypes = [i32, i32]
+    L.orc_cdef_analyze_frame.restype = None
+    L.orc_cdef_analyze_frame.argtypes = [vp, pd, i32, i32, i32, i32, vp, vp, vp]
+    L.orc_cdef_filter_plane.restype = None
+    L.orc_cdef_filter_plane.argtypes = [vp, pd, vp, pd] + [i32] * 8 + [vp, vp, vp, vp]
     L.orc_valid_av1_transform.restype = i32
     L.orc_valid_av1_transform.argtypes = [i32, i32]
     L.orc_tx_width.restype = i32
@@ -224,4 +238,33 @@ def mc_blocks(ref: Plane, blocks, mvs, w, h, mode_x, mode_y, bit_depth, xdec=0, 
     mvs = np.ascontiguousarray(mvs, dtype=np.int16)
     lib().orc_mc_blocks(ref.origin_ptr(), ref.stride, ref.bpp, ptr(blocks), ptr(mvs), n, w, h,
                         mode_x, mode_y, bit_depth, xdec, ydec, kind, ptr(out), threads)
+    return out
+
+
+# ---------------------------------------------------------------- CDEF
+def cdef_find_dir(img8x8, bit_depth=8):
+    img = np.ascontiguousarray(img8x8)
+    v = C.c_uint32()
+    d = lib().orc_cdef_find_dir(ptr(img), img.shape[1], img.itemsize, C.byref(v), bit_depth - 8)
+    return d, v.value
+
+
+def cdef_analyze_frame(luma, bit_depth, skip8=None):
+    luma = np.ascontiguousarray(luma)
+    h, w = luma.shape
+    dirs = np.zeros((h // 8, w // 8), np.uint8)
+    var = np.zeros((h // 8, w // 8), np.int32)
+    lib().orc_cdef_analyze_frame(ptr(luma), w, luma.itemsize, w, h, bit_depth,
+                                 ptr(skip8) if skip8 is not None else None, ptr(dirs), ptr(var))
+    return dirs, var
+
+
+def cdef_filter_plane(img, plane, xdec, ydec, luma_w, luma_h, bit_depth, damping, skip8, dirs, var,
+                      strength_sb):
+    img = np.ascontiguousarray(img)
+    out = np.zeros_like(img)
+    lib().orc_cdef_filter_plane(ptr(img), img.shape[1], ptr(out), img.shape[1], img.itemsize, plane,
+                                xdec, ydec, luma_w, luma_h, bit_depth, damping,
+                                ptr(skip8) if skip8 is not None else None, ptr(dirs), ptr(var),
+                                ptr(strength_sb))
     return out
