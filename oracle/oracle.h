@@ -117,14 +117,17 @@ void orc_mc_blocks(const void *ref0, ptrdiff_t ref_stride, int bpp, const orc_bl
                    int xdec, int ydec, int kind, void *out, int threads);
 
 /* -------------------------------------------------------------- predict.rs */
-/* dispatch_predict_intra predict.rs:705-784.  edge points at the top-left element of an
- * IntraEdge-style buffer: left[k] = edge[-1-k] (k=0 nearest the top), above[k] = edge[1+k].
- * mode: PredictionMode discriminant (predict.rs:58-100); variant: 0 NONE,1 LEFT,2 TOP,3 BOTH;
- * angle: full prediction angle in degrees for directional modes / alpha for CfL;
- * ief_params: <0 none, else (enable<<1)|smooth... see orc_predict_intra in predict.c. */
+/* dispatch_predict_intra predict.rs:705-784.  `edge` is the reference's IntraEdge buffer
+ * (partition.rs:600-637): 4*64+1 pixels, top-left at index 128, left[k] (bottom -> top) in
+ * [128-left_len, 128), above in [129, 129+above_len).  mode: PredictionMode discriminant
+ * (predict.rs:73-87, 0..13); variant: 0 NONE, 1 LEFT, 2 TOP, 3 BOTH; angle: the prediction angle
+ * in degrees for directional modes, alpha for UV_CFL_PRED; ief: -1 = None, 0/1 =
+ * Some(params) with use_smooth_filter() false/true; plane_w/h and dst_x/y: plane_cfg and
+ * rect() of the destination (only read by the edge filter's num_px clipping). */
 void orc_predict_intra(int mode, int variant, void *dst, ptrdiff_t dst_stride, int bpp, int w,
-                       int h, int bit_depth, const int16_t *ac, int angle, int ief_params,
-                       const void *edge_tl, int left_len, int above_len);
+                       int h, int bit_depth, const int16_t *ac, int angle, int ief,
+                       const void *edge, int left_len, int above_len, int plane_w, int plane_h,
+                       int dst_x, int dst_y);
 void orc_pred_cfl_ac(int16_t *ac, const void *luma, ptrdiff_t luma_stride, int bpp, int bw, int bh,
                      int w_pad, int h_pad, int xdec, int ydec);
 

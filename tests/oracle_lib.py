@@ -87,6 +87,11 @@ def lib():
     L.orc_cdef_analyze_frame.argtypes = [vp, pd, i32, i32, i32, i32, vp, vp, vp]
     L.orc_cdef_filter_plane.restype = None
     L.orc_cdef_filter_plane.argtypes = [vp, pd, vp, pd] + [i32] * 8 + [vp, vp, vp, vp]
+    L.orc_predict_intra.restype = None
+    L.orc_predict_intra.argtypes = [i32, i32, vp, pd, i32, i32, i32, i32, vp, i32, i32, vp, i32, i32,
+                                    i32, i32, i32, i32]
+    L.orc_pred_cfl_ac.restype = None
+    L.orc_pred_cfl_ac.argtypes = [vp, vp, pd] + [i32] * 7
     L.orc_valid_av1_transform.restype = i32
     L.orc_valid_av1_transform.argtypes = [i32, i32]
     L.orc_tx_width.restype = i32
@@ -268,3 +273,34 @@ def cdef_filter_plane(img, plane, xdec, ydec, luma_w, luma_h, bit_depth, damping
                                 ptr(skip8) if skip8 is not None else None, ptr(dirs), ptr(var),
                                 ptr(strength_sb))
     return out
+
+
+# ---------------------------------------------------------------- intra prediction
+MODES = ["DC_PRED", "V_PRED", "H_PRED", "D45_PRED", "D135_PRED", "D113_PRED", "D157_PRED",
+         "D203_PRED", "D67_PRED", "SMOOTH_PRED", "SMOOTH_V_PRED", "SMOOTH_H_PRED", "PAETH_PRED",
+         "UV_CFL_PRED"]                       # predict.rs:73-87
+MODE_ANGLE = {"V_PRED": 90, "H_PRED": 180, "D45_PRED": 45, "D135_PRED": 135, "D113_PRED": 113,
+              "D157_PRED": 157, "D203_PRED": 203, "D67_PRED": 67}   # intra_mode_to_angle
+EDGE_LEN = 4 * 64 + 1
+
+
+def predict_intra(mode, variant, edge, w, h, bit_depth, angle=0, ief=-1, ac=None, left_len=128,
+                  above_len=128, plane_w=4096, plane_h=4096, dst_x=64, dst_y=64):
+    """edge: the 257-element IntraEdge buffer (top-left at [128]).  Returns the h x w block."""
+    edge = np.ascontiguousarray(edge)
+    assert edge.shape == (EDGE_LEN,)
+    dst = np.zeros((h, w), edge.dtype)
+    if ac is not None:
+        ac = np.ascontiguousarray(ac, dtype=np.int16)
+    lib().orc_predict_intra(mode, variant, ptr(dst), w, edge.itemsize, w, h, bit_depth,
+                            ptr(ac) if ac is not None else None, angle, ief, ptr(edge), left_len,
+                            above_len, plane_w, plane_h, dst_x, dst_y)
+    return dst
+
+
+def pred_cfl_ac(luma, bw, bh, w_pad, h_pad, xdec, ydec):
+    luma = np.ascontiguousarray(luma)
+    ac = np.zeros(bw * bh, np.int16)
+    lib().orc_pred_cfl_ac(ptr(ac), ptr(luma), luma.shape[1], luma.itemsize, bw, bh, w_pad, h_pad,
+                          xdec, ydec)
+    return ac
