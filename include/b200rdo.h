@@ -273,6 +273,43 @@ int b200_cdef_filter_plane_dev(b200_ctx *ctx, const b200_plane *in, const b200_p
                                const uint8_t *d_dir, const int32_t *d_var,
                                const uint8_t *d_strength_sb);
 
+/* ------------------------------------------------------- intra prediction (predict.rs)
+ * Boundary = rust::dispatch_predict_intra(mode, variant, dst, tx_size, bit_depth, ac, angle,
+ * ief_params, edge_buf, cpu) (predict.rs:705-784; the asm wrappers, asm/x86/predict.rs:239-873,
+ * have the same Rust signature).  `edge` is the reference's IntraEdge buffer (partition.rs:
+ * 600-637): 4*64+1 pixels, top-left at index 128, left pixels bottom->top in [128-left_len, 128),
+ * above pixels in [129, 129+above_len).  mode = PredictionMode discriminant 0..13
+ * (predict.rs:73-87); variant 0 NONE, 1 LEFT, 2 TOP, 3 BOTH (:112-118); angle = prediction angle
+ * in degrees (intra_mode_to_angle + 3*angle_delta) or the CfL alpha; ief = -1 for None, else
+ * IntraEdgeFilterParameters::use_smooth_filter() as 0/1 (:574-596); plane_w/plane_h/dst_x/dst_y =
+ * dst.plane_cfg.{width,height} and dst.rect().{x,y} (edge-filter clipping, :1357-1364). */
+void b200_predict_intra(int mode, int variant, void *dst, ptrdiff_t dst_stride, int w, int h,
+                        int bit_depth, const int16_t *ac, int angle, int ief, const void *edge,
+                        int left_len, int above_len, int plane_w, int plane_h, int dst_x, int dst_y);
+
+typedef struct {
+  uint32_t edge;    /* index of the IntraEdge buffer inside d_edges (257 pixels each) */
+  uint32_t ac;      /* index of the w*h int16 CfL ac block inside d_ac (UV_CFL_PRED only) */
+  int16_t x, y;     /* dst.rect().x / .y */
+  int16_t angle;    /* degrees, or CfL alpha */
+  uint8_t mode;     /* PredictionMode 0..13 */
+  uint8_t variant;  /* PredictionVariant */
+  int8_t ief;       /* -1 none, 0/1 = Some(use_smooth_filter) */
+  uint8_t left_len, above_len;
+  uint8_t pad_;
+} b200_intra_item;
+
+/* Batched: one prediction per item (typically blocks x candidate modes sharing edge buffers);
+ * d_out receives nitems packed w x h blocks (pixels). */
+int b200_predict_intra_dev(b200_ctx *ctx, const void *d_edges, const b200_intra_item *d_items,
+                           size_t nitems, const int16_t *d_ac, int w, int h, int bit_depth,
+                           int plane_w, int plane_h, void *d_out);
+/* pred_cfl_ac (predict.rs:1020-1063; asm cfl_ac_{420,422,444}, asm/x86/predict.rs:142-186):
+ * bw x bh = chroma block size; d_blocks[i] = LUMA position of block i. */
+int b200_pred_cfl_ac_dev(b200_ctx *ctx, const b200_plane *luma, const b200_block *d_blocks,
+                         size_t nblocks, int bw, int bh, int w_pad, int h_pad, int xdec, int ydec,
+                         int16_t *d_ac);
+
 #ifdef __cplusplus
 }
 #endif

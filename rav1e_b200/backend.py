@@ -41,6 +41,9 @@ class MeParams(C.Structure):
 
 BLOCK_DTYPE = np.dtype([("x", "<i2"), ("y", "<i2")])
 CAND_DTYPE = np.dtype([("block", "<u4"), ("mv_row", "<i2"), ("mv_col", "<i2")])
+INTRA_ITEM_DTYPE = np.dtype([("edge", "<u4"), ("ac", "<u4"), ("x", "<i2"), ("y", "<i2"),
+                             ("angle", "<i2"), ("mode", "u1"), ("variant", "u1"), ("ief", "i1"),
+                             ("left_len", "u1"), ("above_len", "u1"), ("pad_", "u1")])
 ME_RESULT_DTYPE = np.dtype(
     {"names": ["cost", "sad", "mv_row", "mv_col"],
      "formats": ["<u8", "<u4", "<i2", "<i2"], "offsets": [0, 8, 12, 14], "itemsize": 16})
@@ -124,6 +127,10 @@ def lib():
     L.b200_cdef_filter_block.restype = None
     L.b200_cdef_find_dir_dev.argtypes = [vp, pp, i32, vp, vp, vp]
     L.b200_cdef_filter_plane_dev.argtypes = [vp, pp, pp] + [i32] * 7 + [vp, vp, vp, vp]
+    L.b200_predict_intra.argtypes = [i32, i32, vp, C.c_ssize_t, i32, i32, i32, vp, i32, i32, vp] + [i32] * 6
+    L.b200_predict_intra.restype = None
+    L.b200_predict_intra_dev.argtypes = [vp, vp, vp, sz, vp, i32, i32, i32, i32, i32, vp]
+    L.b200_pred_cfl_ac_dev.argtypes = [vp, pp, vp, sz] + [i32] * 6 + [vp]
     _LIB = L
     return L
 
@@ -221,6 +228,16 @@ class Context:
         self.check(self.L.b200_cdef_filter_plane_dev(
             self.h, C.byref(inp), C.byref(out), plane, xdec, ydec, luma_w, luma_h, bit_depth,
             damping, _dev_ptr(d_skip8), _dev_ptr(d_dir), _dev_ptr(d_var), _dev_ptr(d_strength_sb)))
+
+    # ---- intra prediction
+    def predict_intra_dev(self, d_edges, d_items, n, d_ac, w, h, bit_depth, plane_w, plane_h, d_out):
+        self.check(self.L.b200_predict_intra_dev(self.h, _dev_ptr(d_edges), _dev_ptr(d_items), n,
+                                                 _dev_ptr(d_ac), w, h, bit_depth, plane_w, plane_h,
+                                                 _dev_ptr(d_out)))
+
+    def pred_cfl_ac_dev(self, luma, d_blocks, n, bw, bh, w_pad, h_pad, xdec, ydec, d_ac):
+        self.check(self.L.b200_pred_cfl_ac_dev(self.h, C.byref(luma), _dev_ptr(d_blocks), n, bw, bh,
+                                               w_pad, h_pad, xdec, ydec, _dev_ptr(d_ac)))
 
     # ---- forward transform
     def fwd_txfm_dev(self, d_in, in_block_stride, in_row_stride, d_out, n, tx_size, tx_type, bd,
