@@ -59,10 +59,12 @@ def test_batched_blocks_match_oracle(dtype, bd, w, h):
     n = len(blocks)
     rng = np.random.default_rng(5)
     mvs = rng.integers(-60 * 8, 60 * 8 + 1, (n, 2)).astype(np.int16)
-    mvs[0] = (0, 0)
-    mvs[1] = (8, -16)          # full-pel
-    mvs[2] = (0, 3)            # H only
-    mvs[3] = (-5, 0)           # V only
+    special = [(0, 0), (8, -16), (0, 3), (-5, 0)]      # copy, full-pel, H only, V only
+    if n < 8:                  # 128x128 yields only two blocks on this plane: repeat them
+        blocks = np.ascontiguousarray(np.tile(blocks, 4))
+        n = len(blocks)
+        mvs = rng.integers(-60 * 8, 60 * 8 + 1, (n, 2)).astype(np.int16)
+    mvs[:4] = special
     tdt = torch.uint8 if dtype == np.uint8 else torch.int16
     for mode_x, mode_y, xdec, ydec in ((0, 0, 0, 0), (1, 2, 0, 0), (3, 3, 0, 0), (0, 0, 1, 1)):
         for kind in (0, 1):
