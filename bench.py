@@ -136,21 +136,21 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from tests import oracle_lib as O
-    threads = O.lib().orc_num_threads()
+    threads = O.host_threads()
     blocks = grid_blocks()
     cur_img, ref_img = synth_frame_pair(0)
     ocur, oref = O.Plane(W, H, PAD), O.Plane(W, H, PAD)
     ocur.data[:], oref.data[:] = cur_img, ref_img
     # bounded sample: one frame pair, 1/4 of its candidate lists per step
-    sad_c, _ = cand_list(len(blocks), CAND_SAD // 4, 100)
-    satd_c, _ = cand_list(len(blocks), CAND_SATD // 4, 200)
-    resid = np.random.default_rng(5).integers(-255, 256, (len(blocks) // 4, BH, BW)).astype(np.int16)
+    sad_c, _ = cand_list(len(blocks), CAND_SAD, 100)
+    satd_c, _ = cand_list(len(blocks), CAND_SATD, 200)
+    resid = np.random.default_rng(5).integers(-255, 256, (len(blocks), BH, BW)).astype(np.int16)
     units = len(sad_c) + len(satd_c) + len(resid)
 
     def step():
-        O.fullpel_candidates(ocur, oref, blocks, sad_c, BW, BH, False, LAMBDA, want_cost=True)
-        O.fullpel_candidates(ocur, oref, blocks, satd_c, BW, BH, True, LAMBDA, want_cost=True)
-        O.forward_transform_batch(resid, 2, 0, 8)
+        O.fullpel_candidates(ocur, oref, blocks, sad_c, BW, BH, False, LAMBDA, want_cost=True, threads=threads)
+        O.fullpel_candidates(ocur, oref, blocks, satd_c, BW, BH, True, LAMBDA, want_cost=True, threads=threads)
+        O.forward_transform_batch(resid, 2, 0, 8, threads=threads)
 
     for _ in range(args.warmup):
         step()
@@ -159,8 +159,9 @@ def run_reference(args, rank, world):
         step()
     dt = time.perf_counter() - t0
     v = units * args.steps / dt
-    sample = (f"1 of {FRAMES_PER_GPU} frame pairs, {CAND_SAD // 4} SAD + {CAND_SATD // 4} SATD "
-              f"candidates per 16x16 block + 1/4 of the 16x16 DCT_DCT transforms ({units} blocks/step)")
+    sample = (f"1 of {FRAMES_PER_GPU} frame pairs per step: {CAND_SAD} SAD + {CAND_SATD} SATD candidates and "
+              f"one 16x16 DCT_DCT per 16x16 block ({units} blocks/step), {threads} threads "
+              f"(affinity capped by the cgroup CPU quota)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "blocks/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -346,34 +347,52 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def run_e2e(ctx, blocks, args):
-    """Host buffers in, host results out, per frame, through b200_me_candidates_batch."""
+def run_e2e(ctx0, blocks, args):
+    """The same metric through the host-buffer C ABI, per frame: pinned host planes uploaded
+    (b200_plane_upload), candidate descriptors host->device, winners device->host
+    (b200_me_candidates_resident x2: SAD and SATD lists), fused residual + 16x16 DCT with the
+    coefficients device->host (b200_fwd_txfm_residual_resident).  Frames are pipelined over three
+    contexts (streams) in asynchronous mode so PCIe copies overlap kernels; everything is
+    synchronised before the clock stops."""
+    import ctypes as C
     import torch
     from rav1e_b200 import backend as B
     nb = len(blocks)
-    Fe = 8
-    pinned = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    Fe, NCTX = 12, 3
+    pinned = lambda n, dt=np.uint8: torch.empty(n, dtype=torch.uint8).pin_memory().numpy().view(dt)
+    ctxs = [B.Context(ctx0.device) for _ in range(NCTX)]
+    slots = []
+    for c in ctxs:
+        c.set_async(True)
+        pl = []
+        for _ in range(2):
+            p = B.Plane()
+            c.check(c.L.b200_plane_alloc(c.h, W + 2 * PAD, H + 2 * PAD, 0, 1, C.byref(p)))
+            q = B.Plane()
+            q.data = p.data + PAD * p.stride + PAD
+            q.stride, q.width, q.height, q.pad, q.bpp, q.alloc = p.stride, W, H, PAD, 1, None
+            pl.append((p, q))
+        slots.append(pl)
+    hblocks = pinned(blocks.nbytes).view(B.BLOCK_DTYPE)
+    hblocks[:] = blocks
     frames = []
     for f in range(Fe):
         cur_img, ref_img = synth_frame_pair(5000 + (f % 2))
-        hc = pinned(cur_img.shape, torch.uint8)
-        hr = pinned(ref_img.shape, torch.uint8)
+        hc = pinned(cur_img.size).reshape(cur_img.shape)
+        hr = pinned(ref_img.size).reshape(ref_img.shape)
         hc[:], hr[:] = cur_img, ref_img
         c, offs = cand_list(nb, CAND_SAD, 900 + f)
         c2, offs2 = cand_list(nb, CAND_SATD, 1900 + f)
-        hcand = pinned(c.nbytes, torch.uint8)
-        hcand[:] = c.view(np.uint8)
-        hcand2 = pinned(c2.nbytes, torch.uint8)
-        hcand2[:] = c2.view(np.uint8)
-        outs = (pinned(len(c) * 4, torch.uint8).view(np.uint32), None,
-                pinned(nb * 16, torch.uint8).view(B.ME_RESULT_DTYPE))
-        outs2 = (pinned(len(c2) * 4, torch.uint8).view(np.uint32), None,
-                 pinned(nb * 16, torch.uint8).view(B.ME_RESULT_DTYPE))
-        hres = pinned(nb * BW * BH * 2, torch.uint8).view(np.int16).reshape(nb, BH, BW)
-        hres[:] = np.random.default_rng(f).integers(-255, 256, hres.shape)
-        hcoef = pinned(nb * BW * BH * 2, torch.uint8).view(np.int16).reshape(nb, BW * BH)
-        frames.append((B.host_plane(hc, PAD), B.host_plane(hr, PAD), hcand.view(B.CAND_DTYPE),
-                       hcand2.view(B.CAND_DTYPE), outs, outs2, hres, hcoef))
+        hcand = pinned(c.nbytes).view(B.CAND_DTYPE)
+        hcand[:] = c
+        hcand2 = pinned(c2.nbytes).view(B.CAND_DTYPE)
+        hcand2[:] = c2
+        hoffs, hoffs2 = pinned(offs.nbytes).view(np.uint32), pinned(offs2.nbytes).view(np.uint32)
+        hoffs[:], hoffs2[:] = offs, offs2
+        best = pinned(nb * 16).view(B.ME_RESULT_DTYPE)
+        best2 = pinned(nb * 16).view(B.ME_RESULT_DTYPE)
+        coef = pinned(nb * BW * BH * 2).view(np.int16).reshape(nb, BW * BH)
+        frames.append((hc, hr, hcand, hcand2, hoffs, hoffs2, best, best2, coef))
     p_sad = B.me_params(BW, BH, W, H, LAMBDA, window_hint_px=MV_RANGE_PX)
     p_satd = B.me_params(BW, BH, W, H, LAMBDA, use_satd=True, window_hint_px=MV_RANGE_PX)
     h2d = d2h = 0
@@ -381,32 +400,42 @@ def run_e2e(ctx, blocks, args):
     def step():
         nonlocal h2d, d2h
         h2d = d2h = 0
-        for hc, hr, c, c2, outs, outs2, hres, hcoef in frames:
-            sad, _, best = ctx.me_candidates_batch(hc, hr, blocks, c, p_sad, offs, None, out=outs)
-            sad2, _, best2 = ctx.me_candidates_batch(hc, hr, blocks, c2, p_satd, offs2, None, out=outs2)
-            ctx.fwd_txfm_batch(hres, 2, 0, 8, False, out=hcoef)
-            h2d += hres.nbytes
-            d2h += hcoef.nbytes
-            plane_bytes = 2 * (W + 2 * PAD) * (H + 2 * PAD)
-            h2d += 2 * plane_bytes + c.nbytes + c2.nbytes + 2 * blocks.nbytes + offs.nbytes + offs2.nbytes
-            d2h += sad.nbytes + sad2.nbytes + best.nbytes + best2.nbytes
+        for f, (hc, hr, c, c2, o, o2, best, best2, coef) in enumerate(frames):
+            cx = ctxs[f % NCTX]
+            (pc, qc), (pr, qr) = slots[f % NCTX]
+            cx.plane_upload(pc, hc)
+            cx.plane_upload(pr, hr)
+            cx.me_candidates_resident(qc, qr, hblocks, c, p_sad, o, (None, None, best))
+            cx.me_candidates_resident(qc, qr, hblocks, c2, p_satd, o2, (None, None, best2))
+            cx.fwd_txfm_residual_resident(qc, qr, hblocks, best, coef, 2, 0, 8)
+            h2d += hc.nbytes + hr.nbytes + c.nbytes + c2.nbytes + 3 * hblocks.nbytes + o.nbytes + o2.nbytes + best.nbytes
+            d2h += best.nbytes + best2.nbytes + coef.nbytes
+        for cx in ctxs:
+            cx.synchronize()
     for _ in range(2):
         step()
+    l0 = sum(cx.launches for cx in ctxs)
     t0 = time.perf_counter()
-    reps = max(2, min(args.steps, 5))
+    reps = max(3, min(args.steps, 10))
     for _ in range(reps):
         step()
-    ctx.synchronize()
     dt = time.perf_counter() - t0
+    launches = sum(cx.launches for cx in ctxs) - l0
     units = Fe * nb * (CAND_SAD + CAND_SATD + 1)
-    return {"value": units * reps / dt, "unit": "blocks/s", "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h), "frames_per_step": Fe,
-            "api": "b200_me_candidates_batch x2 + b200_fwd_txfm_batch per frame (host buffers in/out)"}
+    res = {"value": units * reps / dt, "unit": "blocks/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "frames_per_step": Fe, "kernel_launches_per_step": launches // reps,
+           "api": "per frame: b200_plane_upload x2 + b200_me_candidates_resident x2 (winners out) + "
+                  "b200_fwd_txfm_residual_resident (coefficients out); 3 contexts, async mode"}
+    for c, pl in zip(ctxs, slots):
+        for p, q in pl:
+            c.check(c.L.b200_plane_free(c.h, C.byref(p)))
+        c.close()
+    return res
 
 
 def run_cpu_baseline(blocks):
     from tests import oracle_lib as O
-    threads = O.lib().orc_num_threads()
+    threads = O.host_threads()
     cur_img, ref_img = synth_frame_pair(0)
     ocur, oref = O.Plane(W, H, PAD), O.Plane(W, H, PAD)
     ocur.data[:], oref.data[:] = cur_img, ref_img
@@ -417,9 +446,9 @@ def run_cpu_baseline(blocks):
     t0 = time.perf_counter()
     reps = 0
     while time.perf_counter() - t0 < 3.0:
-        O.fullpel_candidates(ocur, oref, blocks, sad_c, BW, BH, False, LAMBDA)
-        O.fullpel_candidates(ocur, oref, blocks, satd_c, BW, BH, True, LAMBDA)
-        O.forward_transform_batch(resid, 2, 0, 8)
+        O.fullpel_candidates(ocur, oref, blocks, sad_c, BW, BH, False, LAMBDA, threads=threads)
+        O.fullpel_candidates(ocur, oref, blocks, satd_c, BW, BH, True, LAMBDA, threads=threads)
+        O.forward_transform_batch(resid, 2, 0, 8, threads=threads)
         reps += 1
     dt = time.perf_counter() - t0
     units = (len(sad_c) + len(satd_c) + len(resid)) * reps

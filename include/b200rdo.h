@@ -56,6 +56,11 @@ int b200_ctx_set_stream(b200_ctx *ctx, void *cuda_stream);
 int b200_ctx_reset_stream(b200_ctx *ctx);
 void *b200_ctx_get_stream(b200_ctx *ctx);
 int b200_ctx_synchronize(b200_ctx *ctx);
+/* Asynchronous host-buffer mode: when enabled, the `*_batch` / `*_resident` entry points enqueue
+ * their copies and kernels and return without waiting; output buffers are valid after
+ * b200_ctx_synchronize().  Host input/output buffers must stay alive (and should be pinned) until
+ * then.  Lets a caller pipeline frames over several contexts so PCIe copies overlap kernels. */
+int b200_ctx_set_async(b200_ctx *ctx, int enable);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 uint64_t b200_ctx_launch_count(const b200_ctx *ctx);
 
@@ -189,6 +194,14 @@ int b200_me_candidates_batch(b200_ctx *ctx, const b200_host_plane *cur,
                              const uint32_t *cand_offsets, const int16_t *pmv,
                              const b200_me_params *params, uint32_t *sad, uint64_t *cost,
                              b200_me_result *best);
+/* Same as b200_me_candidates_batch but with the planes already resident on the device
+ * (b200_plane_alloc + b200_plane_upload once per frame, reused by every call of the frame): only
+ * descriptors travel host->device and results device->host. */
+int b200_me_candidates_resident(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                                const b200_block *blocks, size_t nblocks, const b200_cand *cands,
+                                size_t ncands, const uint32_t *cand_offsets, const int16_t *pmv,
+                                const b200_me_params *params, uint32_t *sad, uint64_t *cost,
+                                b200_me_result *best);
 int b200_me_full_search_batch(b200_ctx *ctx, const b200_host_plane *cur,
                               const b200_host_plane *ref, const b200_block *blocks,
                               size_t nblocks, const b200_me_params *params, int range_x,
@@ -220,6 +233,11 @@ int b200_fwd_txfm_residual_dev(b200_ctx *ctx, const b200_plane *cur, const b200_
                                const b200_block *d_blocks, size_t nblocks,
                                const b200_me_result *d_mv_src, void *d_output, int tx_size,
                                int tx_type, int bd);
+/* Fused residual + transform with resident planes and HOST descriptors / outputs. */
+int b200_fwd_txfm_residual_resident(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                                    const b200_block *blocks, size_t nblocks,
+                                    const b200_me_result *mv_src, void *output, int tx_size,
+                                    int tx_type, int bd);
 int b200_fwd_txfm_batch(b200_ctx *ctx, const int16_t *input, size_t in_block_stride,
                         size_t in_row_stride, void *output, size_t nblocks, int tx_size,
                         int tx_type, int bd, int coeff_is_i32);

@@ -76,6 +76,7 @@ def lib():
     L.b200_last_error.restype = C.c_char_p
     L.b200_ctx_set_stream.argtypes = [vp, vp]
     L.b200_ctx_reset_stream.argtypes = [vp]
+    L.b200_ctx_set_async.argtypes = [vp, i32]
     L.b200_ctx_get_stream.argtypes = [vp]
     L.b200_ctx_get_stream.restype = vp
     L.b200_ctx_synchronize.argtypes = [vp]
@@ -104,6 +105,8 @@ def lib():
     L.b200_me_full_search_dev.argtypes = [vp, pp, pp, vp, sz, pmp, i32, i32, i32, vp]
     L.b200_block_residual_dev.argtypes = [vp, pp, pp, vp, sz, vp, i32, i32, vp]
     L.b200_me_candidates_batch.argtypes = [vp, php, php, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
+    L.b200_me_candidates_resident.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
+    L.b200_fwd_txfm_residual_resident.argtypes = [vp, pp, pp, vp, sz, vp, vp, i32, i32, i32]
     L.b200_me_full_search_batch.argtypes = [vp, php, php, vp, sz, pmp, i32, i32, i32, vp]
     L.b200_valid_av1_transform.argtypes = [i32, i32]
     L.b200_tx_width.argtypes = [i32]
@@ -279,6 +282,25 @@ class Context:
             _np_ptr(offsets), _np_ptr(pmv), C.byref(params), _np_ptr(sad), _np_ptr(cost),
             _np_ptr(best)))
         return sad, cost, best
+
+    def set_async(self, enable=True):
+        self.check(self.L.b200_ctx_set_async(self.h, int(enable)))
+
+    def plane_upload(self, plane, img):
+        self.check(self.L.b200_plane_upload(self.h, C.byref(plane), img.ctypes.data, img.strides[0]))
+
+    def me_candidates_resident(self, cur, ref, blocks, cands, params, offsets, out, pmv=None):
+        """Resident planes, host descriptors; `out` = (sad|None, cost|None, best|None) host arrays."""
+        sad, cost, best = out
+        self.check(self.L.b200_me_candidates_resident(
+            self.h, C.byref(cur), C.byref(ref), _np_ptr(blocks), len(blocks), _np_ptr(cands),
+            len(cands), _np_ptr(offsets), _np_ptr(pmv), C.byref(params), _np_ptr(sad), _np_ptr(cost),
+            _np_ptr(best)))
+
+    def fwd_txfm_residual_resident(self, cur, ref, blocks, mv_src, out, tx_size, tx_type, bd):
+        self.check(self.L.b200_fwd_txfm_residual_resident(
+            self.h, C.byref(cur), C.byref(ref), _np_ptr(blocks), len(blocks), _np_ptr(mv_src),
+            out.ctypes.data, tx_size, tx_type, bd))
 
     def me_full_search_batch(self, cur_hp, ref_hp, blocks, params, range_x, range_y, step):
         best = np.empty(len(blocks), ME_RESULT_DTYPE)

@@ -76,6 +76,12 @@ extern "C" int b200_ctx_reset_stream(b200_ctx *ctx) {
   return B200_OK;
 }
 
+extern "C" int b200_ctx_set_async(b200_ctx *ctx, int enable) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  ctx->async_batch = enable ? 1 : 0;
+  return B200_OK;
+}
+
 extern "C" void *b200_ctx_get_stream(b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 extern "C" int b200_ctx_synchronize(b200_ctx *ctx) {
@@ -220,7 +226,7 @@ extern "C" int b200_plane_upload(b200_ctx *ctx, const b200_plane *p, const void 
           (uint16_t *)p->data, p->stride, p->width, p->height, p->pad);
     B200_LAUNCH_CHECK(ctx);
   }
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!ctx->async_batch) B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return B200_OK;
 }
 

@@ -25,6 +25,7 @@ struct b200_ctx {
   size_t pinned_bytes = 0;
   void *dwork = nullptr;
   size_t dwork_bytes = 0;
+  int async_batch = 0;  // host-buffer forms skip their final synchronize (b200_ctx_set_async)
   char err[512] = {0};
 };
 

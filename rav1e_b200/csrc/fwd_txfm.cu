@@ -312,7 +312,41 @@ extern "C" int b200_fwd_txfm_batch(b200_ctx *ctx, const int16_t *input, size_t i
     st = b200_fail(ctx, B200_ERR_CUDA, "D2H copy failed");
   cudaFreeAsync(dbase, ctx->stream);
   if (st) return st;
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!ctx->async_batch) B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+extern "C" int b200_fwd_txfm_residual_resident(b200_ctx *ctx, const b200_plane *cur,
+                                               const b200_plane *ref, const b200_block *blocks,
+                                               size_t nblocks, const b200_me_result *mv_src,
+                                               void *output, int tx_size, int tx_type, int bd) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  B200_REQUIRE(ctx, valid_transform(tx_size, tx_type), "invalid transform: tx_size %d tx_type %d",
+               tx_size, tx_type);
+  if (nblocks == 0) return B200_OK;
+  B200_REQUIRE(ctx, cur && ref && blocks && output, "NULL argument");
+  const size_t area = (size_t)kTxW[tx_size] * kTxH[tx_size];
+  const size_t out_bytes = nblocks * area * (cur->bpp == 2 ? 4 : 2);
+  const size_t blk_bytes = b200_align_up(nblocks * sizeof(b200_block), 256);
+  const size_t mv_bytes = mv_src ? b200_align_up(nblocks * sizeof(b200_me_result), 256) : 0;
+  B200_CUDA(ctx, cudaSetDevice(ctx->device));
+  void *dbase = nullptr;
+  B200_CUDA(ctx, cudaMallocAsync(&dbase, blk_bytes + mv_bytes + out_bytes, ctx->stream));
+  uint8_t *d_blk = (uint8_t *)dbase, *d_mv = d_blk + blk_bytes, *d_out = d_mv + mv_bytes;
+  int st = B200_OK;
+  if (cudaMemcpyAsync(d_blk, blocks, nblocks * sizeof(b200_block), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+      (mv_src && cudaMemcpyAsync(d_mv, mv_src, nblocks * sizeof(b200_me_result), cudaMemcpyHostToDevice,
+                                 ctx->stream) != cudaSuccess))
+    st = b200_fail(ctx, B200_ERR_CUDA, "H2D copy failed");
+  if (!st)
+    st = b200_fwd_txfm_residual_dev(ctx, cur, ref, (const b200_block *)d_blk, nblocks,
+                                    mv_src ? (const b200_me_result *)d_mv : nullptr, d_out, tx_size,
+                                    tx_type, bd);
+  if (!st && cudaMemcpyAsync(output, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+    st = b200_fail(ctx, B200_ERR_CUDA, "D2H copy failed");
+  cudaFreeAsync(dbase, ctx->stream);
+  if (st) return st;
+  if (!ctx->async_batch) B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return B200_OK;
 }
 

@@ -61,22 +61,28 @@ struct Carver {
 
 }  // namespace
 
-extern "C" int b200_me_candidates_batch(b200_ctx *ctx, const b200_host_plane *cur,
-                                        const b200_host_plane *ref, const b200_block *blocks,
-                                        size_t nblocks, const b200_cand *cands, size_t ncands,
-                                        const uint32_t *cand_offsets, const int16_t *pmv,
-                                        const b200_me_params *params, uint32_t *sad,
-                                        uint64_t *cost, b200_me_result *best) {
+// Host descriptors in / host results out; planes either host (copied) or device-resident.
+static int me_candidates_host_impl(b200_ctx *ctx, const b200_host_plane *cur,
+                                   const b200_host_plane *ref, const b200_plane *rcur,
+                                   const b200_plane *rref, const b200_block *blocks,
+                                   size_t nblocks, const b200_cand *cands, size_t ncands,
+                                   const uint32_t *cand_offsets, const int16_t *pmv,
+                                   const b200_me_params *params, uint32_t *sad,
+                                   uint64_t *cost, b200_me_result *best) {
   B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
-  if (int st = check_host_plane(ctx, cur)) return st;
-  if (int st = check_host_plane(ctx, ref)) return st;
+  if (!rcur) {
+    if (int st = check_host_plane(ctx, cur)) return st;
+    if (int st = check_host_plane(ctx, ref)) return st;
+  } else {
+    B200_REQUIRE(ctx, rcur->data && rref && rref->data, "bad resident planes");
+  }
   B200_REQUIRE(ctx, params && blocks && (cands || !ncands), "NULL params/blocks/cands");
   B200_REQUIRE(ctx, best == nullptr || cand_offsets != nullptr, "best needs cand_offsets");
   B200_CUDA(ctx, cudaSetDevice(ctx->device));
 
   size_t rb, rows;
-  const size_t cur_bytes = staged_pitch(cur) * (host_plane_span(cur, &rb, &rows), rows) + 512;
-  const size_t ref_bytes = staged_pitch(ref) * (host_plane_span(ref, &rb, &rows), rows) + 512;
+  const size_t cur_bytes = rcur ? 0 : staged_pitch(cur) * (host_plane_span(cur, &rb, &rows), rows) + 512;
+  const size_t ref_bytes = rcur ? 0 : staged_pitch(ref) * (host_plane_span(ref, &rb, &rows), rows) + 512;
   size_t total = cur_bytes + ref_bytes + nblocks * sizeof(b200_block) + ncands * sizeof(b200_cand) +
                  (cand_offsets ? (nblocks + 1) * 4 : 0) + (pmv ? nblocks * 8 : 0) +
                  (sad ? ncands * 4 : 0) + (cost ? ncands * 8 : 0) +
@@ -87,8 +93,14 @@ extern "C" int b200_me_candidates_batch(b200_ctx *ctx, const b200_host_plane *cu
   B200_CUDA(ctx, cudaMallocAsync(&dbase, total, ctx->stream));
   Carver c(dbase);
   b200_plane dcur, dref;
-  int st = upload_host_plane(ctx, cur, c.take(cur_bytes), &dcur);
-  if (!st) st = upload_host_plane(ctx, ref, c.take(ref_bytes), &dref);
+  int st = B200_OK;
+  if (rcur) {
+    dcur = *rcur;
+    dref = *rref;
+  } else {
+    st = upload_host_plane(ctx, cur, c.take(cur_bytes), &dcur);
+    if (!st) st = upload_host_plane(ctx, ref, c.take(ref_bytes), &dref);
+  }
   b200_block *d_blocks = (b200_block *)c.take(nblocks * sizeof(b200_block));
   b200_cand *d_cands = (b200_cand *)c.take(ncands * sizeof(b200_cand));
   uint32_t *d_offs = cand_offsets ? (uint32_t *)c.take((nblocks + 1) * 4) : nullptr;
@@ -124,8 +136,30 @@ extern "C" int b200_me_candidates_batch(b200_ctx *ctx, const b200_host_plane *cu
   if (best) D2H(best, d_best, nblocks * sizeof(b200_me_result));
 #undef D2H
   cudaFreeAsync(dbase, ctx->stream);
-  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!ctx->async_batch) B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return B200_OK;
+}
+
+extern "C" int b200_me_candidates_batch(b200_ctx *ctx, const b200_host_plane *cur,
+                                        const b200_host_plane *ref, const b200_block *blocks,
+                                        size_t nblocks, const b200_cand *cands, size_t ncands,
+                                        const uint32_t *cand_offsets, const int16_t *pmv,
+                                        const b200_me_params *params, uint32_t *sad,
+                                        uint64_t *cost, b200_me_result *best) {
+  return me_candidates_host_impl(ctx, cur, ref, nullptr, nullptr, blocks, nblocks, cands, ncands,
+                                 cand_offsets, pmv, params, sad, cost, best);
+}
+
+extern "C" int b200_me_candidates_resident(b200_ctx *ctx, const b200_plane *cur,
+                                           const b200_plane *ref, const b200_block *blocks,
+                                           size_t nblocks, const b200_cand *cands, size_t ncands,
+                                           const uint32_t *cand_offsets, const int16_t *pmv,
+                                           const b200_me_params *params, uint32_t *sad,
+                                           uint64_t *cost, b200_me_result *best) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  B200_REQUIRE(ctx, cur && ref, "NULL planes");
+  return me_candidates_host_impl(ctx, nullptr, nullptr, cur, ref, blocks, nblocks, cands, ncands,
+                                 cand_offsets, pmv, params, sad, cost, best);
 }
 
 extern "C" int b200_me_full_search_batch(b200_ctx *ctx, const b200_host_plane *cur,

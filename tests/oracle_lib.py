@@ -32,6 +32,20 @@ def build():
     subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
 
 
+def host_threads():
+    """CPU threads this process may actually use: the affinity mask capped by the cgroup CPU
+    quota (the GPU boxes expose 128 logical CPUs under a 16-CPU CFS quota; running more runnable
+    threads than the quota only gets the whole process throttled)."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, -(-int(quota) // int(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def lib():
     global _LIB
     if _LIB is not None:
@@ -41,6 +55,8 @@ def lib():
             if f.endswith((".c", ".h"))]
     if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
         build()
+    # idle OpenMP workers must sleep, not spin: spinning burns the cgroup's CPU quota
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
     L = C.CDLL(path)
     vp, pd, i32, u32, u64, sz = C.c_void_p, C.c_ssize_t, C.c_int, C.c_uint32, C.c_uint64, C.c_size_t
     for name in ("orc_get_sad_u8", "orc_get_sad_u16", "orc_get_satd_u8", "orc_get_satd_u16"):

@@ -260,3 +260,45 @@ def test_1080p_properties():
     np.testing.assert_array_equal(got_sad, want_all)
     c.check(L.b200_plane_free(c.h, C.byref(pc)))
     c.check(L.b200_plane_free(c.h, C.byref(pr)))
+
+
+def test_resident_planes_async_pipeline():
+    """b200_me_candidates_resident + b200_fwd_txfm_residual_resident in asynchronous mode over two
+    contexts: results are valid after b200_ctx_synchronize and equal the oracle."""
+    import torch
+    W, H, PAD, w, h = 320, 192, 96, 16, 16
+    cur, ref = G.make_planes(W, H, PAD, np.uint8, seed=8)
+    ocur = O.Plane(W, H, PAD)
+    ocur.fill_from(cur)
+    oref = O.Plane(W, H, PAD)
+    oref.fill_from(ref)
+    blocks = G.grid_blocks(W, H, w, h)
+    pin = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).pin_memory().numpy().view(a.dtype)
+    ctxs = [B.Context(0), B.Context(0)]
+    outs = []
+    for k, c in enumerate(ctxs):
+        c.set_async(True)
+        dcur, dref = c.plane_from_host(cur, PAD), c.plane_from_host(ref, PAD)
+        cands, offs = G.random_cands(len(blocks), 20, 24, seed=30 + k)
+        hb, hc, ho = pin(blocks), pin(cands), pin(offs)
+        best = pin(np.zeros(len(blocks), B.ME_RESULT_DTYPE))
+        coef = pin(np.zeros((len(blocks), 256), np.int16)).reshape(len(blocks), 256)
+        p = B.me_params(w, h, W, H, 99, window_hint_px=24)
+        c.me_candidates_resident(dcur, dref, hb, hc, p, ho, (None, None, best))
+        c.fwd_txfm_residual_resident(dcur, dref, hb, best, coef, 2, 0, 8)
+        outs.append((c, cands, offs, best, coef, dcur, dref))
+    for c, cands, offs, best, coef, dcur, dref in outs:
+        c.synchronize()
+        _, want_cost = O.fullpel_candidates(ocur, oref, blocks, cands, w, h, False, 99)
+        resid = np.zeros((len(blocks), 16, 16), np.int16)
+        for b in range(len(blocks)):
+            lo, hi = int(offs[b]), int(offs[b + 1])
+            assert best[b]["cost"] == want_cost[lo:hi].min()
+            dx, dy = int(np.trunc(best[b]["mv_col"] / 8)), int(np.trunc(best[b]["mv_row"] / 8))
+            x, y = int(blocks[b]["x"]) + PAD, int(blocks[b]["y"]) + PAD
+            resid[b] = (ocur.data[y:y + 16, x:x + 16].astype(np.int32) -
+                        oref.data[y + dy:y + dy + 16, x + dx:x + dx + 16].astype(np.int32))
+        np.testing.assert_array_equal(coef, O.forward_transform_batch(resid, 2, 0, 8))
+        c.plane_free(dcur)
+        c.plane_free(dref)
+        c.close()
