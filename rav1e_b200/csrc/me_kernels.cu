@@ -291,17 +291,34 @@ __device__ __forceinline__ uint32_t row_sad_u8(const uint32_t *__restrict__ wrow
   return acc;
 }
 
-// Stage `rows` x `row_bytes` (row_bytes multiple of 16, src 16-byte aligned) into smem.
-// Half-warps own rows: 16 lanes x 16 bytes cover a 256-byte row per step, no index division.
+// Stage `rows` x `row_bytes` (row_bytes multiple of 16, src and smem rows 16-byte aligned) into
+// smem.  Half-warps own rows (16 lanes x 16 bytes = one 256-byte row segment per step); each
+// thread walks its (row, vector) column with pointer increments only, three rows in flight.
+// (A per-row cp.async.bulk / UBLKCP version was measured slower: 144 small bulk copies per window
+// serialise in the copy engine and the whole CTA waits on the mbarrier - profiles/NOTES_r1.md.)
 __device__ __forceinline__ void stage_window(uint32_t *smem, int pitch_words, const uint8_t *src,
                                              long long src_stride, int rows, int row_bytes) {
   const int vpr = row_bytes >> 4;
-  const int l16 = threadIdx.x & 15;
-  const int nhw = blockDim.x >> 4;
-  for (int y = threadIdx.x >> 4; y < rows; y += nhw) {
-    const uint4 *s = (const uint4 *)(src + (long long)y * src_stride);
-    uint4 *d = (uint4 *)(smem + y * pitch_words);
-    for (int v = l16; v < vpr; v += 16) d[v] = __ldg(s + v);
+  const int nhw = blockDim.x >> 4;  // rows per sweep
+  for (int v = threadIdx.x & 15; v < vpr; v += 16) {
+    int y = threadIdx.x >> 4;
+    const uint4 *s = (const uint4 *)(src + (long long)y * src_stride) + v;
+    uint4 *d = (uint4 *)(smem + y * pitch_words) + v;
+    const long long sstep = (long long)nhw * src_stride / 16;  // in uint4 units (stride % 16 == 0)
+    const int dstep = nhw * pitch_words / 4;
+    for (; y + 2 * nhw < rows; y += 3 * nhw) {
+      const uint4 q0 = __ldg(s), q1 = __ldg(s + sstep), q2 = __ldg(s + 2 * sstep);
+      d[0] = q0;
+      d[dstep] = q1;
+      d[2 * dstep] = q2;
+      s += 3 * sstep;
+      d += 3 * dstep;
+    }
+    for (; y < rows; y += nhw) {
+      *d = __ldg(s);
+      s += sstep;
+      d += dstep;
+    }
   }
 }
 
