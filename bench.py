@@ -303,6 +303,29 @@ def run_b200(args, rank, world, local_rank):
             txfm_launch(f)
     txfm_only()
     ms_txfm = timed(txfm_only, args.steps) / (args.steps * F)
+    # ---- extra leg (not part of `value`): the exhaustive grid full_pixel_me falls back to at
+    # speed <= 5 (me.rs:822-846): +-192 x +-64 px, step 4 => up to 97 x 33 = 3201 positions/block
+    d_fs = torch.empty(nb * 16, dtype=torch.uint8, device="cuda")
+    p_fs = B.me_params(BW, BH, W, H, LAMBDA)
+    FS_FRAMES = min(F, 4)
+
+    def fs_only():
+        for f in range(FS_FRAMES):
+            cur, ref = planes[f]
+            ctx.me_full_search_dev(cur, ref, d_blocks, nb, p_fs, 192, 64, 4, d_fs)
+    fs_only()
+    ms_fs = timed(fs_only, max(2, args.steps // 2)) / (max(2, args.steps // 2) * FS_FRAMES)
+    w_in_b, h_in_b = 2 * ((W + 7) >> 3), 2 * ((H + 7) >> 3)
+    bx, by = blocks["x"].astype(np.int64), blocks["y"].astype(np.int64)
+    mvx_min = np.maximum(-(bx // 4) * 32 - (128 + BW * 8), -(1 << 14) + 1)
+    mvx_max = np.minimum((w_in_b - bx // 4 - BW // 4) * 32 + 128 + BW * 8, (1 << 14) - 1)
+    mvy_min = np.maximum(-(by // 4) * 32 - (128 + BH * 8), -(1 << 14) + 1)
+    mvy_max = np.minimum((h_in_b - by // 4 - BH // 4) * 32 + 128 + BH * 8, (1 << 14) - 1)
+    tdiv = lambda a, b: np.sign(a) * (np.abs(a) // b)          # Rust `/` truncates toward zero
+    nxp = (np.minimum(192, tdiv(mvx_max, 8)) - np.maximum(-192, tdiv(mvx_min, 8))) // 4 + 1
+    nyp = (np.minimum(64, tdiv(mvy_max, 8)) - np.maximum(-64, tdiv(mvy_min, 8))) // 4 + 1
+    fs_positions = int((nxp * nyp).sum())
+
     alg_bytes = n_sad * (BW * BH + 4) + nb * BW * BH             # 260 B/cand + 256 B/block
     peak, peak_src = peaks()
     achieved = alg_bytes / (ms_sad * 1e-3) / 1e9
@@ -333,7 +356,12 @@ def run_b200(args, rank, world, local_rank):
                        "parallelism": f"frames sharded over {world} GPU(s); all-gather of winners"
                        if world > 1 else "1 GPU",
                        "per_launch_ms": {"sad_cand": ms_sad, "satd_cand": ms_satd,
-                                         "residual+fwd_txfm": ms_txfm}},
+                                         "residual+fwd_txfm": ms_txfm},
+                       "extra_legs": {"full_search_grid": {
+                           "what": "me_full_search (+-192 x +-64 px, step 4) for every 16x16 block of one frame; "
+                                   "not part of `value` (speed 6 disables full search)",
+                           "positions_per_launch": fs_positions, "launch_ms": ms_fs,
+                           "candidates_per_s": fs_positions / (ms_fs * 1e-3)}}},
             "roofline": {"kernel": "me_cand_smem_u8<16,16> (candidate-list SAD + cost + argmin)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -426,7 +426,7 @@ __device__ __forceinline__ unsigned long long pack_key(unsigned long long cost, 
 // shared atomicMin per warp.  Windows that do not fit fall back to one block per pass, and a
 // single block that still does not fit reads the reference plane directly.
 template <int W, int H, bool SATD>
-__global__ void __launch_bounds__(256) me_cand_group_u8(MeArgs a, int G) {
+__global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, int G) {
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ int s_box[4];
   __shared__ unsigned long long s_key[kMaxGroup];
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(256) me_cand_group_u8(MeArgs a, int G) {
   constexpr int NCH = SATD ? (W / S) * (H / S) : 1;           // chunks per candidate
   constexpr int TPC = NCH < 32 ? NCH : 32;                    // threads per candidate
   constexpr int ORGW = H * W / 4;                             // org words per block
-  constexpr int nthr = 256;  // launch_cand_group always uses 256 threads
+  constexpr int nthr = SATD ? 128 : 256;  // must match launch_cand_group
   const int lane = threadIdx.x & 31;
   uint32_t *const s_org = smem;                               // [G][ORGW]
   uint32_t *const win = smem + G * ORGW;
@@ -864,7 +864,7 @@ int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px) {
   constexpr int S = (W < 8 || H < 8) ? 4 : 8;
   constexpr int NCH = SATD ? (W / S) * (H / S) : 1;
   constexpr int TPC = NCH < 32 ? NCH : 32;
-  const int threads = 256;
+  const int threads = SATD ? 128 : 256;  // SATD holds a 64-entry chunk per thread: smaller CTAs, more of them
   int G = (int)std::min<size_t>(kMaxGroup, std::max<size_t>(1, (threads / TPC) / std::max<size_t>(avg, 1)));
   G = std::max(1, std::min(G, 16384 / (W * H)));  // org tiles <= 16 KB
   // Shared window sized from the caller's search-range hint (+ the group's extent along x);
