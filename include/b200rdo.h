@@ -161,6 +161,17 @@ int b200_me_candidates_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plan
                            const b200_me_params *params, uint32_t *d_sad, uint64_t *d_cost,
                            b200_me_result *d_best);
 
+/* get_subpel_mv_rd (me.rs:1411-1442) over a candidate list of SUB-PEL vectors: each candidate is
+ * predicted with the 8-tap filter `filter_mode` (fi.default_filter; predict_inter_single,
+ * predict.rs:304-336) and measured with SAD or SATD against the source block — the unit of work
+ * of subpel_diamond_search (me.rs:1311-1383).  Same outputs and tie-break as the full-pel form. */
+int b200_me_subpel_candidates_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                                  const b200_block *d_blocks, size_t nblocks,
+                                  const b200_cand *d_cands, size_t ncands,
+                                  const uint32_t *d_cand_offsets, const int16_t *d_pmv,
+                                  const b200_me_params *params, int filter_mode, uint32_t *d_sad,
+                                  uint64_t *d_cost, b200_me_result *d_best);
+
 /* full_search (me.rs:1464-1509) as called from full_pixel_me (me.rs:822-846) for every
  * block: window po +- (range_x, range_y) px clamped to get_mv_range, positions every
  * `step` px, pmv = 0, first-minimum winner in row-major scan order. */

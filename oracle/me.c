@@ -168,3 +168,41 @@ void orc_full_search_blocks(const void *cur0, ptrdiff_t cur_stride, const void *
                              allow_hp);
   }
 }
+
+/* get_subpel_mv_rd (me.rs:1411-1442) over a candidate list: range check, predict_inter_single
+ * (predict.rs:304-336 -> put_8tap with fi.default_filter on the luma plane) into a scratch of
+ * mc_w x mc_h = next_power_of_two(w) x ((h+1)&!1) (me.rs:1322-1324), then compute_mv_rd against it. */
+void orc_subpel_candidates(const void *cur0, ptrdiff_t cur_stride, const void *ref0,
+                           ptrdiff_t ref_stride, int bpp, int frame_w_in_b, int frame_h_in_b,
+                           const orc_block *blocks, const orc_cand *cands, size_t n, int w, int h,
+                           int use_satd, uint32_t lambda, const orc_mv *pmv, int allow_hp,
+                           int filter_mode, int bit_depth, uint32_t *out_sad, uint64_t *out_cost,
+                           int threads) {
+  int mc_w = 1;
+  while (mc_w < w) mc_w <<= 1;
+  const int mc_h = (h + 1) & ~1;
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : orc_num_threads())
+  for (ptrdiff_t i = 0; i < (ptrdiff_t)n; i++) {
+    const orc_cand c = cands[i];
+    const orc_block b = blocks[c.block];
+    int mvx_min, mvx_max, mvy_min, mvy_max;
+    orc_get_mv_range(frame_w_in_b, frame_h_in_b, b.x / MI_SIZE, b.y / MI_SIZE, w, h, &mvx_min,
+                     &mvx_max, &mvy_min, &mvy_max);
+    uint32_t sad = UINT32_MAX;
+    uint64_t cost = UINT64_MAX;
+    if (!(c.mv_col < mvx_min || c.mv_col > mvx_max || c.mv_row < mvy_min || c.mv_row > mvy_max)) {
+      uint16_t tmp[128 * 128];
+      int ro, co, rf, cf;
+      orc_get_mv_params(c.mv_row, c.mv_col, 0, 0, &ro, &co, &rf, &cf);
+      orc_put_8tap(tmp, mc_w, px_at(ref0, ref_stride, bpp, b.x + co, b.y + ro), ref_stride, bpp, mc_w,
+                   mc_h, cf, rf, filter_mode, filter_mode, bit_depth);
+      sad = dist_any(px_at(cur0, cur_stride, bpp, b.x, b.y), cur_stride, tmp, mc_w, bpp, w, h, use_satd);
+      orc_mv z = {0, 0};
+      orc_mv cm = {c.mv_row, c.mv_col};
+      cost = orc_mv_cost(sad, cm, pmv ? pmv[2 * c.block] : z, pmv ? pmv[2 * c.block + 1] : z, lambda,
+                         allow_hp);
+    }
+    if (out_sad) out_sad[i] = sad;
+    if (out_cost) out_cost[i] = cost;
+  }
+}

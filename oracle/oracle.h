@@ -83,6 +83,14 @@ void orc_fullpel_candidates(const void *cur0, ptrdiff_t cur_stride, const void *
                             int h, int use_satd, uint32_t lambda, const orc_mv *pmv /*2 per block or NULL*/,
                             int allow_hp, uint32_t *out_sad, uint64_t *out_cost, int threads);
 
+/* get_subpel_mv_rd (me.rs:1411-1442) over a candidate list (sub-pel mvs): 8-tap MC + SAD/SATD. */
+void orc_subpel_candidates(const void *cur0, ptrdiff_t cur_stride, const void *ref0,
+                           ptrdiff_t ref_stride, int bpp, int frame_w_in_b, int frame_h_in_b,
+                           const orc_block *blocks, const orc_cand *cands, size_t n, int w, int h,
+                           int use_satd, uint32_t lambda, const orc_mv *pmv, int allow_hp,
+                           int filter_mode, int bit_depth, uint32_t *out_sad, uint64_t *out_cost,
+                           int threads);
+
 /* full_pixel_me's final stage (me.rs:822-846) for every block: window +-range, step. */
 void orc_full_search_blocks(const void *cur0, ptrdiff_t cur_stride, const void *ref0,
                             ptrdiff_t ref_stride, int bpp, int frame_w_in_b, int frame_h_in_b,

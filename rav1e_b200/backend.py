@@ -102,6 +102,7 @@ def lib():
             f.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t] + extra
             f.restype = u32
     L.b200_me_candidates_dev.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
+    L.b200_me_subpel_candidates_dev.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, i32, vp, vp, vp]
     L.b200_me_full_search_dev.argtypes = [vp, pp, pp, vp, sz, pmp, i32, i32, i32, vp]
     L.b200_block_residual_dev.argtypes = [vp, pp, pp, vp, sz, vp, i32, i32, vp]
     L.b200_me_candidates_batch.argtypes = [vp, php, php, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
@@ -198,6 +199,13 @@ class Context:
         self.check(self.L.b200_me_candidates_dev(
             self.h, C.byref(cur), C.byref(ref), _dev_ptr(d_blocks), nblocks, _dev_ptr(d_cands),
             ncands, _dev_ptr(d_offsets), _dev_ptr(d_pmv), C.byref(params), _dev_ptr(d_sad),
+            _dev_ptr(d_cost), _dev_ptr(d_best)))
+
+    def me_subpel_candidates_dev(self, cur, ref, d_blocks, nblocks, d_cands, ncands, params, filter_mode=0,
+                                 d_offsets=None, d_pmv=None, d_sad=None, d_cost=None, d_best=None):
+        self.check(self.L.b200_me_subpel_candidates_dev(
+            self.h, C.byref(cur), C.byref(ref), _dev_ptr(d_blocks), nblocks, _dev_ptr(d_cands), ncands,
+            _dev_ptr(d_offsets), _dev_ptr(d_pmv), C.byref(params), filter_mode, _dev_ptr(d_sad),
             _dev_ptr(d_cost), _dev_ptr(d_best)))
 
     def me_full_search_dev(self, cur, ref, d_blocks, nblocks, params, range_x, range_y, step, d_best):

@@ -62,6 +62,7 @@ struct McArgs {
   int ref_stride;     // elements
   const b200_block *blocks;
   const short *mvs;   // row, col per block (1/8 pel); null = zero motion
+  const b200_cand *cands;  // optional: item i = (blocks[cands[i].block], cands[i].mv)
   size_t n;
   int w, h;
   int mode_x, mode_y;
@@ -89,8 +90,18 @@ __global__ void __launch_bounds__(256) mc_kernel(McArgs a) {
   for (size_t blk = blockIdx.x; blk < a.n; blk += gridDim.x) {
     int x0 = 0, y0 = 0, col_frac = a.col_frac, row_frac = a.row_frac;
     if (!a.explicit_frac) {
-      const b200_block b = a.blocks[blk];
-      const int mvr = a.mvs ? a.mvs[2 * blk] : 0, mvc = a.mvs ? a.mvs[2 * blk + 1] : 0;
+      b200_block b;
+      int mvr, mvc;
+      if (a.cands) {
+        const b200_cand c = a.cands[blk];
+        b = a.blocks[c.block];
+        mvr = c.mv_row;
+        mvc = c.mv_col;
+      } else {
+        b = a.blocks[blk];
+        mvr = a.mvs ? a.mvs[2 * blk] : 0;
+        mvc = a.mvs ? a.mvs[2 * blk + 1] : 0;
+      }
       // predict.rs:284-297 get_mv_params
       y0 = b.y + (mvr >> (3 + a.ydec));
       x0 = b.x + (mvc >> (3 + a.xdec));
@@ -228,6 +239,27 @@ extern "C" int b200_mc_blocks_dev(b200_ctx *ctx, const b200_plane *ref, const b2
   a.xdec = xdec;
   a.ydec = ydec;
   a.kind = kind;
+  a.out = d_out;
+  return launch_mc(ctx, a, ref->bpp);
+}
+
+// Internal (me_kernels.cu): one `put` prediction per candidate, luma plane, packed w x h outputs.
+int b200_mc_cands_internal(b200_ctx *ctx, const b200_plane *ref, const b200_block *d_blocks,
+                           const b200_cand *d_cands, size_t ncands, int w, int h, int mode,
+                           int bit_depth, void *d_out) {
+  if (int st = check_mc(ctx, w, h, mode, mode, bit_depth)) return st;
+  McArgs a{};
+  a.ref = ref->data;
+  a.ref_stride = ref->stride;
+  a.blocks = d_blocks;
+  a.cands = d_cands;
+  a.n = ncands;
+  a.w = w;
+  a.h = h;
+  a.mode_x = mode;
+  a.mode_y = mode;
+  a.bit_depth = bit_depth;
+  a.kind = 0;
   a.out = d_out;
   return launch_mc(ctx, a, ref->bpp);
 }

@@ -1063,6 +1063,109 @@ extern "C" int b200_block_residual_dev(b200_ctx *ctx, const b200_plane *cur, con
   return B200_OK;
 }
 
+// Distortion of each candidate's PACKED prediction (mc output, stride = pw) against the source
+// block: the compute_mv_rd half of get_subpel_mv_rd (me.rs:1434-1441).  One warp per candidate.
+template <typename T>
+__global__ void __launch_bounds__(256) me_dist_packed_kernel(MeArgs a, const T *pred, int pw, int ph) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+  for (size_t i = warp0; i < a.ncands; i += nwarps) {
+    const b200_cand c = a.cands[i];
+    const b200_block b = a.blocks[c.block];
+    const MvRange r = b200_mv_range(a.w_in_b, a.h_in_b, b.x / MI_SIZE, b.y / MI_SIZE, a.w, a.h);
+    uint32_t sad = kEmptySad;
+    unsigned long long cost = kEmptyCost;
+    if (!(c.mv_col < r.x_min || c.mv_col > r.x_max || c.mv_row < r.y_min || c.mv_row > r.y_max)) {
+      sad = warp_block_dist<T>(px<T>(a.cur, b.x, b.y), a.cur.stride, pred + i * (size_t)pw * ph, pw,
+                               a.w, a.h, a.use_satd, lane);
+      int p0r = 0, p0c = 0, p1r = 0, p1c = 0;
+      if (a.pmv) {
+        const short *p = a.pmv + 4 * (size_t)c.block;
+        p0r = p[0], p0c = p[1], p1r = p[2], p1c = p[3];
+      }
+      cost = b200_mv_cost(sad, c.mv_row, c.mv_col, p0r, p0c, p1r, p1c, a.lambda, a.allow_hp);
+    }
+    if (lane == 0) {
+      if (a.out_sad) a.out_sad[i] = sad;
+      if (a.out_cost) a.out_cost[i] = cost;
+    }
+  }
+}
+
+// get_subpel_mv_rd (me.rs:1411-1442) over a candidate list: predict_inter_single (8-tap put with
+// `filter_mode`, the frame's default_filter) into a scratch of next_power_of_two(w) x ((h+1)&~1)
+// per candidate (me.rs:1322-1324), distortion against the source block, cost, per-block
+// first-minimum.  Out-of-range vectors give the empty result, exactly like the full-pel form.
+extern "C" int b200_me_subpel_candidates_dev(b200_ctx *ctx, const b200_plane *cur,
+                                             const b200_plane *ref, const b200_block *d_blocks,
+                                             size_t nblocks, const b200_cand *d_cands, size_t ncands,
+                                             const uint32_t *d_cand_offsets, const int16_t *d_pmv,
+                                             const b200_me_params *p, int filter_mode,
+                                             uint32_t *d_sad, uint64_t *d_cost,
+                                             b200_me_result *d_best) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  if (int st = check_planes(ctx, cur, ref, p)) return st;
+  B200_REQUIRE(ctx, d_best == nullptr || d_cand_offsets != nullptr, "d_best needs CSR d_cand_offsets");
+  B200_REQUIRE(ctx, filter_mode >= 0 && filter_mode <= 3, "bad FilterMode %d", filter_mode);
+  B200_REQUIRE(ctx, (cur->bpp == 1) == (p->bit_depth == 8), "bpp %d vs bit depth %d", cur->bpp, p->bit_depth);
+  if (ncands == 0 && (nblocks == 0 || !d_best)) return B200_OK;
+  B200_REQUIRE(ctx, d_blocks && (d_cands || ncands == 0), "NULL blocks/cands");
+  B200_CUDA(ctx, cudaSetDevice(ctx->device));
+  int mc_w = 1;
+  while (mc_w < p->w) mc_w <<= 1;
+  const int mc_h = (p->h + 1) & ~1;
+  const size_t pred_bytes = b200_align_up(ncands * (size_t)mc_w * mc_h * cur->bpp, 256);
+  const size_t need = pred_bytes + (d_cost ? 0 : ncands * 8) + (d_sad ? 0 : ncands * 4) + 512;
+  if (int st = b200_reserve_dwork(ctx, need)) return st;
+  uint8_t *wsp = (uint8_t *)ctx->dwork;
+  void *d_pred = wsp;
+  wsp += pred_bytes;
+  unsigned long long *cost_buf = (unsigned long long *)d_cost;
+  uint32_t *sad_buf = d_sad;
+  if (!cost_buf) {
+    cost_buf = (unsigned long long *)wsp;
+    wsp += b200_align_up(ncands * 8, 256);
+  }
+  if (!sad_buf) sad_buf = (uint32_t *)wsp;
+  if (ncands) {
+    if (int st = b200_mc_cands_internal(ctx, ref, d_blocks, d_cands, ncands, mc_w, mc_h, filter_mode,
+                                        p->bit_depth, d_pred))
+      return st;
+    MeArgs a{};
+    a.cur = {cur->data, cur->stride};
+    a.ref = {ref->data, ref->stride};
+    a.blocks = d_blocks;
+    a.cands = d_cands;
+    a.pmv = d_pmv;
+    a.out_sad = sad_buf;
+    a.out_cost = cost_buf;
+    a.ncands = ncands;
+    a.nblocks = nblocks;
+    a.w = p->w;
+    a.h = p->h;
+    a.w_in_b = p->frame_w_in_b;
+    a.h_in_b = p->frame_h_in_b;
+    a.lambda = p->lambda;
+    a.allow_hp = p->allow_high_precision_mv;
+    a.use_satd = p->use_satd;
+    const int wpc = 8;
+    const int grid = (int)std::min<size_t>((ncands + wpc - 1) / wpc, (size_t)ctx->num_sms * 16);
+    if (cur->bpp == 1)
+      me_dist_packed_kernel<uint8_t><<<grid, wpc * 32, 0, ctx->stream>>>(a, (const uint8_t *)d_pred, mc_w, mc_h);
+    else
+      me_dist_packed_kernel<uint16_t><<<grid, wpc * 32, 0, ctx->stream>>>(a, (const uint16_t *)d_pred, mc_w, mc_h);
+    B200_LAUNCH_CHECK(ctx);
+  }
+  if (d_best && nblocks) {
+    const int wpc = 8;
+    me_best_from_cost<<<(int)((nblocks + wpc - 1) / wpc), wpc * 32, 0, ctx->stream>>>(
+        cost_buf, sad_buf, d_cands, d_cand_offsets, nblocks, d_best);
+    B200_LAUNCH_CHECK(ctx);
+  }
+  return B200_OK;
+}
+
 extern "C" int b200_me_full_search_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
                                        const b200_block *d_blocks, size_t nblocks,
                                        const b200_me_params *p, int range_x, int range_y, int step,

@@ -75,6 +75,9 @@ def lib():
     L.orc_fullpel_candidates.restype = None
     L.orc_fullpel_candidates.argtypes = [vp, pd, vp, pd, i32, i32, i32, vp, vp, sz, i32, i32, i32,
                                          u32, vp, i32, vp, vp, i32]
+    L.orc_subpel_candidates.restype = None
+    L.orc_subpel_candidates.argtypes = [vp, pd, vp, pd, i32, i32, i32, vp, vp, sz, i32, i32, i32,
+                                        u32, vp, i32, i32, i32, vp, vp, i32]
     L.orc_full_search_blocks.restype = None
     L.orc_full_search_blocks.argtypes = [vp, pd, vp, pd, i32, i32, i32, vp, sz, i32, i32, i32, i32,
                                          i32, u32, i32, vp, i32]
@@ -180,6 +183,21 @@ def fullpel_candidates(cur: Plane, ref: Plane, blocks, cands, w, h, use_satd=Fal
                              w_in_b, h_in_b, ptr(blocks), ptr(cands), n, w, h, int(use_satd),
                              int(lambda_), ptr(pmv) if pmv is not None else None, int(allow_hp),
                              ptr(sad), ptr(cost) if want_cost else None, threads)
+    return sad, cost
+
+
+def subpel_candidates(cur: Plane, ref: Plane, blocks, cands, w, h, use_satd=True, lambda_=0, pmv=None,
+                      allow_hp=False, filter_mode=0, bit_depth=8, threads=0):
+    L = lib()
+    n = len(cands)
+    sad = np.empty(n, np.uint32)
+    cost = np.empty(n, np.uint64)
+    w_in_b = 2 * ((cur.width + 7) >> 3)
+    h_in_b = 2 * ((cur.height + 7) >> 3)
+    L.orc_subpel_candidates(cur.origin_ptr(), cur.stride, ref.origin_ptr(), ref.stride, cur.bpp,
+                            w_in_b, h_in_b, ptr(blocks), ptr(cands), n, w, h, int(use_satd),
+                            int(lambda_), ptr(pmv) if pmv is not None else None, int(allow_hp),
+                            filter_mode, bit_depth, ptr(sad), ptr(cost), threads)
     return sad, cost
 
 

@@ -302,3 +302,46 @@ def test_resident_planes_async_pipeline():
         c.plane_free(dcur)
         c.plane_free(dref)
         c.close()
+
+
+@pytest.mark.parametrize("dtype,bd,w,h,use_satd", [(np.uint8, 8, 16, 16, True), (np.uint8, 8, 8, 8, False),
+                                                  (np.uint16, 10, 16, 16, True), (np.uint16, 10, 32, 16, True),
+                                                  (np.uint16, 12, 8, 16, False), (np.uint8, 8, 64, 64, True)])
+def test_subpel_candidates_match_oracle(dtype, bd, w, h, use_satd):
+    """get_subpel_mv_rd (me.rs:1411-1442): 8-tap MC + SATD/SAD + cost + first-min winner, for the
+    diamond pattern of subpel_diamond_search around random full-pel vectors (BASELINE config 4)."""
+    W, H, PAD = 320, 192, 160
+    cur, ref = G.make_planes(W, H, PAD, dtype, seed=bd + w, bit_depth=bd)
+    ocur, dcur = G.both_planes(cur, PAD)
+    oref, dref = G.both_planes(ref, PAD)
+    blocks = G.grid_blocks(W, H, w, h)
+    nb = len(blocks)
+    rng = np.random.default_rng(4)
+    centre = rng.integers(-20, 21, (nb, 2)) * 8
+    pattern = np.array([(0, 0)] + [(r * s, c * s) for s in (4, 2, 1) for r, c in ((1, 0), (0, 1), (-1, 0), (0, -1))])
+    cands = np.zeros(nb * len(pattern), B.CAND_DTYPE)
+    cands["block"] = np.repeat(np.arange(nb, dtype=np.uint32), len(pattern))
+    mv = centre[:, None, :] + pattern[None, :, :]
+    cands["mv_row"], cands["mv_col"] = mv[:, :, 0].reshape(-1), mv[:, :, 1].reshape(-1)
+    offs = (np.arange(nb + 1) * len(pattern)).astype(np.uint32)
+    pmv = (rng.integers(-64, 65, (nb, 4)) * 2).astype(np.int16)
+    lam = 777
+    want_sad, want_cost = O.subpel_candidates(ocur, oref, blocks, cands, w, h, use_satd, lam, pmv,
+                                              allow_hp=True, filter_mode=0, bit_depth=bd)
+    c = G.ctx()
+    p = B.me_params(w, h, W, H, lam, allow_hp=True, use_satd=use_satd, bit_depth=bd)
+    d_sad, d_cost = G.dev_empty(4 * len(cands)), G.dev_empty(8 * len(cands))
+    d_best = G.dev_empty(16 * nb)
+    c.me_subpel_candidates_dev(dcur, dref, G.to_dev(blocks), nb, G.to_dev(cands), len(cands), p, 0,
+                               G.to_dev(offs), G.to_dev(pmv), d_sad, d_cost, d_best)
+    c.synchronize()
+    np.testing.assert_array_equal(G.from_dev(d_sad, np.uint32)[:len(cands)], want_sad)
+    np.testing.assert_array_equal(G.from_dev(d_cost, np.uint64)[:len(cands)], want_cost)
+    best = G.from_dev(d_best, B.ME_RESULT_DTYPE)[:nb]
+    for b in range(nb):
+        lo, hi = int(offs[b]), int(offs[b + 1])
+        k = lo + int(np.argmin(want_cost[lo:hi]))
+        assert best[b]["cost"] == want_cost[k] and best[b]["sad"] == want_sad[k]
+        assert (best[b]["mv_row"], best[b]["mv_col"]) == (cands[k]["mv_row"], cands[k]["mv_col"])
+    for pl in (dcur, dref):
+        c.plane_free(pl)
