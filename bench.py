@@ -394,21 +394,20 @@ def run_e2e(ctx0, blocks, args):
         c.set_async(True)
         pl = []
         for _ in range(2):
+            # visible W x H area travels; the PAD-pixel border is replicated on the device
+            # (b200_plane_upload = v_frame Plane::pad semantics, like rav1e's own frames)
             p = B.Plane()
-            c.check(c.L.b200_plane_alloc(c.h, W + 2 * PAD, H + 2 * PAD, 0, 1, C.byref(p)))
-            q = B.Plane()
-            q.data = p.data + PAD * p.stride + PAD
-            q.stride, q.width, q.height, q.pad, q.bpp, q.alloc = p.stride, W, H, PAD, 1, None
-            pl.append((p, q))
+            c.check(c.L.b200_plane_alloc(c.h, W, H, PAD, 1, C.byref(p)))
+            pl.append((p, p))
         slots.append(pl)
     hblocks = pinned(blocks.nbytes).view(B.BLOCK_DTYPE)
     hblocks[:] = blocks
     frames = []
     for f in range(Fe):
         cur_img, ref_img = synth_frame_pair(5000 + (f % 2))
-        hc = pinned(cur_img.size).reshape(cur_img.shape)
-        hr = pinned(ref_img.size).reshape(ref_img.shape)
-        hc[:], hr[:] = cur_img, ref_img
+        hc = pinned(W * H).reshape(H, W)
+        hr = pinned(W * H).reshape(H, W)
+        hc[:], hr[:] = cur_img[PAD:PAD + H, PAD:PAD + W], ref_img[PAD:PAD + H, PAD:PAD + W]
         c, offs = cand_list(nb, CAND_SAD, 900 + f)
         c2, offs2 = cand_list(nb, CAND_SATD, 1900 + f)
         hcand = pinned(c.nbytes).view(B.CAND_DTYPE)
@@ -425,21 +424,31 @@ def run_e2e(ctx0, blocks, args):
     p_satd = B.me_params(BW, BH, W, H, LAMBDA, use_satd=True, window_hint_px=MV_RANGE_PX)
     h2d = d2h = 0
 
-    def step():
-        nonlocal h2d, d2h
-        h2d = d2h = 0
-        for f, (hc, hr, c, c2, o, o2, best, best2, coef) in enumerate(frames):
-            cx = ctxs[f % NCTX]
-            (pc, qc), (pr, qr) = slots[f % NCTX]
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(NCTX)
+
+    def drive(k):
+        """One host thread per context (like one rayon worker per tile, encoder.rs:3253): ctypes
+        releases the GIL inside the C ABI, so the CUDA API work of the contexts overlaps too."""
+        cx = ctxs[k]
+        (pc, qc), (pr, qr) = slots[k]
+        nb_h2d = nb_d2h = 0
+        for f in range(k, Fe, NCTX):
+            hc, hr, c, c2, o, o2, best, best2, coef = frames[f]
             cx.plane_upload(pc, hc)
             cx.plane_upload(pr, hr)
             cx.me_candidates_resident(qc, qr, hblocks, c, p_sad, o, (None, None, best))
             cx.me_candidates_resident(qc, qr, hblocks, c2, p_satd, o2, (None, None, best2))
             cx.fwd_txfm_residual_resident(qc, qr, hblocks, best, coef, 2, 0, 8)
-            h2d += hc.nbytes + hr.nbytes + c.nbytes + c2.nbytes + 3 * hblocks.nbytes + o.nbytes + o2.nbytes + best.nbytes
-            d2h += best.nbytes + best2.nbytes + coef.nbytes
-        for cx in ctxs:
-            cx.synchronize()
+            nb_h2d += hc.nbytes + hr.nbytes + c.nbytes + c2.nbytes + 3 * hblocks.nbytes + o.nbytes + o2.nbytes + best.nbytes
+            nb_d2h += best.nbytes + best2.nbytes + coef.nbytes
+        cx.synchronize()
+        return nb_h2d, nb_d2h
+
+    def step():
+        nonlocal h2d, d2h
+        res = list(pool.map(drive, range(NCTX)))
+        h2d, d2h = sum(r[0] for r in res), sum(r[1] for r in res)
     for _ in range(2):
         step()
     l0 = sum(cx.launches for cx in ctxs)
@@ -453,7 +462,9 @@ def run_e2e(ctx0, blocks, args):
     res = {"value": units * reps / dt, "unit": "blocks/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "frames_per_step": Fe, "kernel_launches_per_step": launches // reps,
            "api": "per frame: b200_plane_upload x2 + b200_me_candidates_resident x2 (winners out) + "
-                  "b200_fwd_txfm_residual_resident (coefficients out); 3 contexts, async mode"}
+                  "b200_fwd_txfm_residual_resident (coefficients out); 3 contexts in async mode, one host "
+                  "thread each"}
+    pool.shutdown()
     for c, pl in zip(ctxs, slots):
         for p, q in pl:
             c.check(c.L.b200_plane_free(c.h, C.byref(p)))

@@ -249,6 +249,12 @@ int b200_fwd_txfm_residual_resident(b200_ctx *ctx, const b200_plane *cur, const 
                                     const b200_block *blocks, size_t nblocks,
                                     const b200_me_result *mv_src, void *output, int tx_size,
                                     int tx_type, int bd);
+/* Residual against PACKED predictions (nblocks x h x w pixels, the output of b200_mc_blocks_dev or
+ * b200_predict_intra_dev) + forward transform: predict -> diff -> forward_transform of
+ * encode_tx_block (encoder.rs:1492-1544) without the residual touching HBM. */
+int b200_fwd_txfm_pred_dev(b200_ctx *ctx, const b200_plane *cur, const void *d_pred,
+                           const b200_block *d_blocks, size_t nblocks, void *d_output, int tx_size,
+                           int tx_type, int bd);
 int b200_fwd_txfm_batch(b200_ctx *ctx, const int16_t *input, size_t in_block_stride,
                         size_t in_row_stride, void *output, size_t nblocks, int tx_size,
                         int tx_type, int bd, int coeff_is_i32);

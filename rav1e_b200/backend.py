@@ -116,6 +116,7 @@ def lib():
     L.b200_forward_transform.restype = None
     L.b200_fwd_txfm_dev.argtypes = [vp, vp, sz, sz, vp, sz, i32, i32, i32, i32]
     L.b200_fwd_txfm_residual_dev.argtypes = [vp, pp, pp, vp, sz, vp, vp, i32, i32, i32]
+    L.b200_fwd_txfm_pred_dev.argtypes = [vp, pp, vp, vp, sz, vp, i32, i32, i32]
     L.b200_fwd_txfm_batch.argtypes = [vp, vp, sz, sz, vp, sz, i32, i32, i32, i32]
     L.b200_put_8tap.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t] + [i32] * 7
     L.b200_put_8tap.restype = None
@@ -260,6 +261,10 @@ class Context:
         self.check(self.L.b200_fwd_txfm_residual_dev(self.h, C.byref(cur), C.byref(ref),
                                                      _dev_ptr(d_blocks), nblocks, _dev_ptr(d_mv_src),
                                                      _dev_ptr(d_out), tx_size, tx_type, bd))
+
+    def fwd_txfm_pred_dev(self, cur, d_pred, d_blocks, nblocks, d_out, tx_size, tx_type, bd):
+        self.check(self.L.b200_fwd_txfm_pred_dev(self.h, C.byref(cur), _dev_ptr(d_pred), _dev_ptr(d_blocks),
+                                                 nblocks, _dev_ptr(d_out), tx_size, tx_type, bd))
 
     def fwd_txfm_batch(self, residual, tx_size, tx_type, bd=8, coeff_i32=None, out=None):
         """residual: int16 (n, h, w) numpy -> (n, w*h) coefficients (host buffers, copies inside)."""

@@ -60,6 +60,7 @@ struct TxArgs {
   int cur_stride, ref_stride;
   const b200_block *blocks;
   const b200_me_result *mv_src;
+  const void *pred_packed;  // PLANES variants: prediction given as packed W x H blocks instead of a plane
   const int16_t *in;
   void *out;
   size_t n;
@@ -125,13 +126,19 @@ __global__ void __launch_bounds__(kTxThreads) fwd_txfm_kernel(TxArgs a) {
           dy = a.mv_src[blk].mv_row / 8;
         }
         const Px *pc = (const Px *)a.cur + (long long)b.y * a.cur_stride + b.x + t;
-        const Px *pr = (const Px *)a.ref + (long long)(b.y + dy) * a.ref_stride + b.x + dx + t;
+        const Px *pr;
+        long long rstride;
+        if (a.pred_packed) {
+          pr = (const Px *)a.pred_packed + blk * (size_t)(W * H) + t;
+          rstride = W;
+        } else {
+          pr = (const Px *)a.ref + (long long)(b.y + dy) * a.ref_stride + b.x + dx + t;
+          rstride = a.ref_stride;
+        }
 #pragma unroll
         for (int r = 0; r < H; r++) {
           const int rr = a.ud_flip ? H - 1 - r : r;
-          c[r] = round_shift_bit((int)pc[(long long)rr * a.cur_stride] -
-                                     (int)pr[(long long)rr * a.ref_stride],
-                                 a.bit0);
+          c[r] = round_shift_bit((int)pc[(long long)rr * a.cur_stride] - (int)pr[rr * rstride], a.bit0);
         }
       } else {
         const int16_t *src = a.in + blk * a.in_block_stride + t;
@@ -192,7 +199,8 @@ extern "C" int b200_tx_width(int tx_size) { return tx_size >= 0 && tx_size < 19 
 extern "C" int b200_tx_height(int tx_size) { return tx_size >= 0 && tx_size < 19 ? kTxH[tx_size] : 0; }
 
 static int fwd_txfm_impl(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
-                         const b200_block *d_blocks, const b200_me_result *d_mv_src,
+                         const void *d_pred_packed, const b200_block *d_blocks,
+                         const b200_me_result *d_mv_src,
                          const int16_t *d_input, size_t in_block_stride, size_t in_row_stride,
                          void *d_output, size_t nblocks, int tx_size, int tx_type, int bd,
                          int coeff_is_i32) {
@@ -221,6 +229,7 @@ static int fwd_txfm_impl(b200_ctx *ctx, const b200_plane *cur, const b200_plane 
   a.ref_stride = ref ? ref->stride : 0;
   a.blocks = d_blocks;
   a.mv_src = d_mv_src;
+  a.pred_packed = d_pred_packed;
   a.in = d_input;
   a.out = d_output;
   a.n = nblocks;
@@ -266,7 +275,7 @@ extern "C" int b200_fwd_txfm_dev(b200_ctx *ctx, const int16_t *d_input, size_t i
                                  int tx_type, int bd, int coeff_is_i32) {
   B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
   B200_REQUIRE(ctx, d_input || nblocks == 0, "NULL input");
-  return fwd_txfm_impl(ctx, nullptr, nullptr, nullptr, nullptr, d_input, in_block_stride,
+  return fwd_txfm_impl(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, d_input, in_block_stride,
                        in_row_stride, d_output, nblocks, tx_size, tx_type, bd, coeff_is_i32);
 }
 
@@ -281,7 +290,22 @@ extern "C" int b200_fwd_txfm_residual_dev(b200_ctx *ctx, const b200_plane *cur,
   B200_REQUIRE(ctx, cur && ref && cur->data && ref->data && cur->bpp == ref->bpp, "bad planes");
   B200_REQUIRE(ctx, (cur->bpp == 1) == (bd == 8), "bpp %d does not match bit depth %d", cur->bpp, bd);
   B200_REQUIRE(ctx, d_blocks || nblocks == 0, "NULL blocks");
-  return fwd_txfm_impl(ctx, cur, ref, d_blocks, d_mv_src, nullptr, 0, 0, d_output, nblocks,
+  return fwd_txfm_impl(ctx, cur, ref, nullptr, d_blocks, d_mv_src, nullptr, 0, 0, d_output, nblocks,
+                       tx_size, tx_type, bd, cur->bpp == 2);
+}
+
+// Residual against PACKED predictions (the output layout of b200_mc_blocks_dev /
+// b200_predict_intra_dev): block i = cur(d_blocks[i]) - d_pred[i], then the forward transform.
+// This is encode_tx_block's predict -> diff -> forward_transform chain (encoder.rs:1492-1544)
+// for sub-pel inter or intra predictions.
+extern "C" int b200_fwd_txfm_pred_dev(b200_ctx *ctx, const b200_plane *cur, const void *d_pred,
+                                      const b200_block *d_blocks, size_t nblocks, void *d_output,
+                                      int tx_size, int tx_type, int bd) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  B200_REQUIRE(ctx, cur && cur->data && d_pred, "bad plane / prediction");
+  B200_REQUIRE(ctx, (cur->bpp == 1) == (bd == 8), "bpp %d does not match bit depth %d", cur->bpp, bd);
+  B200_REQUIRE(ctx, d_blocks || nblocks == 0, "NULL blocks");
+  return fwd_txfm_impl(ctx, cur, cur, d_pred, d_blocks, nullptr, nullptr, 0, 0, d_output, nblocks,
                        tx_size, tx_type, bd, cur->bpp == 2);
 }
 

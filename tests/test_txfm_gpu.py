@@ -117,3 +117,31 @@ def test_fused_residual_transform(dtype, bd):
     np.testing.assert_array_equal(d_res.cpu().numpy(), resid)
     want = O.forward_transform_batch(resid, 2, 1, bd, coeff_i32=i32)
     np.testing.assert_array_equal(d_out.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("dtype,bd", [(np.uint8, 8), (np.uint16, 10)])
+def test_subpel_predict_diff_transform_chain(dtype, bd):
+    """BASELINE config 4 chain on the device: put_8tap at sub-pel vectors -> residual against the
+    packed prediction -> 16x16 DCT_DCT, equal to the oracle's mc -> diff -> forward_transform."""
+    import torch
+    c = G.ctx()
+    W, H, PAD = 256, 128, 96
+    cur, ref = G.make_planes(W, H, PAD, dtype, seed=11, bit_depth=bd)
+    ocur, dcur = G.both_planes(cur, PAD)
+    oref, dref = G.both_planes(ref, PAD)
+    blocks = G.grid_blocks(W, H, 16, 16)
+    n = len(blocks)
+    mvs = np.random.default_rng(2).integers(-20 * 8, 20 * 8 + 1, (n, 2)).astype(np.int16)
+    pred = O.mc_blocks(oref, blocks, mvs, 16, 16, 0, 0, bd)
+    resid = np.zeros((n, 16, 16), np.int16)
+    for i, b in enumerate(blocks):
+        x, y = int(b["x"]) + PAD, int(b["y"]) + PAD
+        resid[i] = ocur.data[y:y + 16, x:x + 16].astype(np.int32) - pred[i].astype(np.int32)
+    want = O.forward_transform_batch(resid, 2, 0, bd, coeff_i32=bd > 8)
+    d_blocks = G.to_dev(blocks)
+    d_pred = torch.empty((n, 16, 16), dtype=torch.uint8 if bd == 8 else torch.int16, device="cuda")
+    c.mc_blocks_dev(dref, d_blocks, G.to_dev(mvs), n, 16, 16, 0, 0, bd, 0, 0, 0, d_pred)
+    d_out = torch.empty((n, 256), dtype=torch.int32 if bd > 8 else torch.int16, device="cuda")
+    c.fwd_txfm_pred_dev(dcur, d_pred, d_blocks, n, d_out, 2, 0, bd)
+    c.synchronize()
+    np.testing.assert_array_equal(d_out.cpu().numpy(), want)
