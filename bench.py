@@ -61,7 +61,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -272,12 +272,12 @@ def run_b200(args, rank, world, local_rank):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    clk = ClockSampler(local_rank)
+    if rank == 0:
+        clk.start()          # sampled from the warm-up on: the same kernels at the same load
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
-    clk = ClockSampler(local_rank)
-    if rank == 0:
-        clk.start()
     l0 = ctx.launches
     ms = timed(step, args.steps)
     launches = ctx.launches - l0
@@ -362,7 +362,7 @@ def run_b200(args, rank, world, local_rank):
                                    "not part of `value` (speed 6 disables full search)",
                            "positions_per_launch": fs_positions, "launch_ms": ms_fs,
                            "candidates_per_s": fs_positions / (ms_fs * 1e-3)}}},
-            "roofline": {"kernel": "me_cand_smem_u8<16,16> (candidate-list SAD + cost + argmin)",
+            "roofline": {"kernel": "me_cand_group_u8<16,16,SAD> (candidate-list SAD + cost + argmin)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,

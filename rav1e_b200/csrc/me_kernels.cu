@@ -291,6 +291,8 @@ __device__ __forceinline__ uint32_t row_sad_u8(const uint32_t *__restrict__ wrow
   return acc;
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 // Stage `rows` x `row_bytes` (row_bytes multiple of 16, src and smem rows 16-byte aligned) into
 // smem.  Half-warps own rows (16 lanes x 16 bytes = one 256-byte row segment per step); each
 // thread walks its (row, vector) column with pointer increments only, three rows in flight.
@@ -439,6 +441,13 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
   constexpr int NCH = SATD ? (W / S) * (H / S) : 1;           // chunks per candidate
   constexpr int TPC = NCH < 32 ? NCH : 32;                    // threads per candidate
   constexpr int ORGW = H * W / 4;                             // org words per block
+  // COOP = cooperative SAD evaluation: a warp evaluates its 32 candidates one after the other,
+  // lane = (row % RPP, word), so every LDS touches RPP rows x LPR words on 32 distinct banks
+  // (pitch == LPR mod 32) instead of 32 randomly placed rows (3.4-way conflicts).
+  constexpr int LPR = W / 4;
+  constexpr bool COOP = !SATD && W >= 16 && W <= 64 && (LPR * H) >= 32 && (LPR * H) % 32 == 0;
+  constexpr int RPP = COOP ? 32 / LPR : 1;
+  constexpr int P = COOP ? H / RPP : 1;
   constexpr int nthr = SATD ? 128 : 256;  // must match launch_cand_group
   const int lane = threadIdx.x & 31;
   uint32_t *const s_org = smem;                               // [G][ORGW]
@@ -506,7 +515,13 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
       // +4 bytes: the funnel shift reads one word past the last pixel
       const int row_bytes = have ? (int)b200_align_up((size_t)(s_box[1] + W + 4 - wx0), 16) : 0;
       const int rows = have ? s_box[3] - wy0 + H : 0;
-      const int pitch_words = (row_bytes >> 2) | 4;  // 16-byte aligned rows, odd multiple of 4 words
+      int pitch_words;
+      if (COOP) {  // == LPR (mod 32): conflict-free cooperative loads, rows stay 16-byte aligned
+        pitch_words = ((row_bytes >> 2) & ~31) + LPR;
+        if (pitch_words < (row_bytes >> 2)) pitch_words += 32;
+      } else {     // 16-byte aligned rows, odd multiple of 4 words
+        pitch_words = (row_bytes >> 2) | 4;
+      }
       const bool fits = (long long)rows * pitch_words * 4 <= (long long)win_bytes;
       if (!fits && nb > 1) {  // uniform: derived from shared state
         whole = false;
@@ -530,6 +545,99 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
       }
       __syncthreads();
 
+      if (COOP && staged) {
+        // Pass 1 (thread per candidate): range check and addresses -> one uint4 per candidate:
+        //   {shared address of the candidate's first footprint word, shared address of its
+        //    block's org words, funnel shift, 0}.  Out-of-range candidates point at the window
+        //   origin: they are evaluated like the others (no divergence) and discarded afterwards.
+        // Pass 2 (warp per 32 candidates, fully unrolled): one broadcast LDS.128 fetches the
+        //   parameters, each lane loads its (row, word) of the footprint and of org with plain
+        //   32-bit shared addresses, REDUX.SUM hands the SAD to the owner lane.
+        __shared__ uint4 s_par[nthr];
+        const int warp = threadIdx.x >> 5;
+        const int lrow = lane / LPR, lword = lane - lrow * LPR;
+        const uint32_t win_s = smem_u32(win), org_s = smem_u32(s_org);
+        const uint32_t lane_win = (uint32_t)(lrow * pitch_words + lword) * 4u;
+        const uint32_t lane_org = (uint32_t)(lrow * (W / 4) + lword) * 4u;
+        const uint32_t pstep = (uint32_t)(RPP * pitch_words) * 4u;
+        for (uint32_t base = lo; base < hi; base += nthr) {
+          const uint32_t i = base + threadIdx.x;
+          const bool valid = i < hi;
+          bool inr = false;
+          b200_cand cd;
+          cd.block = 0;
+          cd.mv_row = 0;
+          cd.mv_col = 0;
+          int lb = 0;
+          uint4 par = make_uint4(win_s, org_s, 0u, 0u);
+          if (valid) {
+            cd = a.cands[i];
+            lb = (int)(cd.block - (uint32_t)b0);
+            const MvRange r = s_rng[lb];
+            inr = !(cd.mv_col < r.x_min || cd.mv_col > r.x_max || cd.mv_row < r.y_min ||
+                    cd.mv_row > r.y_max);
+            if (inr) {
+              const int off = s_blk[lb].x + cd.mv_col / 8 - wx0;
+              par.x = win_s + (uint32_t)((s_blk[lb].y + cd.mv_row / 8 - wy0) * pitch_words + (off >> 2)) * 4u;
+              par.y = org_s + (uint32_t)(lb * ORGW) * 4u;
+              par.z = (uint32_t)(off & 3) * 8u;
+            }
+          }
+          __syncthreads();  // previous round's readers of s_par are done
+          s_par[threadIdx.x] = par;
+          __syncthreads();
+          uint32_t sad = 0;
+          const uint32_t par_s = smem_u32(s_par + warp * 32);
+#pragma unroll
+          for (int sidx = 0; sidx < 32; sidx++) {
+            uint32_t qa, qo, qs, qz;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(qa), "=r"(qo), "=r"(qs), "=r"(qz)
+                         : "r"(par_s + (uint32_t)sidx * 16u));
+            uint32_t wa = qa + lane_win;
+            const uint32_t oa = qo + lane_org;
+            uint32_t part = 0;
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+              uint32_t w0, w1, o;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(wa));
+              asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(wa));
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(o) : "r"(oa + (uint32_t)(p * RPP * (W / 4)) * 4u));
+              part = sad4_acc(__funnelshift_r(w0, w1, qs), o, part);
+              wa += pstep;
+            }
+            const uint32_t tot = __reduce_add_sync(0xffffffffu, part);
+            if (lane == sidx) sad = tot;
+          }
+          unsigned long long cost = kEmptyCost, key = ~0ull;
+          if (inr) {
+            cost = b200_mv_cost(sad, cd.mv_row, cd.mv_col, s_pmv[lb][0], s_pmv[lb][1], s_pmv[lb][2],
+                                s_pmv[lb][3], a.lambda, a.allow_hp);
+            key = pack_key(cost, i - s_off[lb]);
+          } else {
+            sad = kEmptySad;
+            lb = -1;
+          }
+          if (valid) {
+            if (a.out_sad) a.out_sad[i] = sad;
+            if (a.out_cost) a.out_cost[i] = cost;
+          }
+          if (a.out_best) {
+            const int lb0 = __shfl_sync(0xffffffffu, lb, 0);
+            if (__all_sync(0xffffffffu, lb == lb0 || key == ~0ull)) {
+              const uint32_t khi = (uint32_t)(key >> 32);
+              const uint32_t mh = __reduce_min_sync(0xffffffffu, khi);
+              const uint32_t klo = khi == mh ? (uint32_t)key : 0xffffffffu;
+              const uint32_t ml = __reduce_min_sync(0xffffffffu, klo);
+              const int owner = __reduce_max_sync(0xffffffffu, key == ~0ull ? -1 : lb);
+              if (lane == 0 && owner >= 0)
+                atomicMin(&s_key[owner], ((unsigned long long)mh << 32) | ml);
+            } else if (key != ~0ull) {
+              atomicMin(&s_key[lb], key);
+            }
+          }
+        }
+      } else {
       // ---- evaluate: each slot of TPC threads takes candidates lo+slot, lo+slot+nslots, ...
       const int nslots = nthr / TPC;
       const int slot = threadIdx.x / TPC, sub = threadIdx.x - slot * TPC;
@@ -634,6 +742,7 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
           }
         }
       }
+      }  // cooperative / generic evaluation
       if (a.out_best) {
         __syncthreads();
         if (threadIdx.x < nb) {
@@ -870,7 +979,17 @@ int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px) {
   // Shared window sized from the caller's search-range hint (+ the group's extent along x);
   // groups/blocks that do not fit degrade inside the kernel, never fail.
   const int hint = window_hint_px > 0 ? window_hint_px : 32;
-  const size_t pitch = (b200_align_up((size_t)(2 * hint + G * W + 4 + 15), 16) >> 2) | 4;
+  // mirror the kernel's pitch choice for the widest window the hint allows
+  const size_t words = b200_align_up((size_t)(2 * hint + G * W + 4 + 15), 16) >> 2;
+  constexpr int LPR = W / 4;
+  constexpr bool COOP = !SATD && W >= 16 && W <= 64 && (LPR * H) >= 32 && (LPR * H) % 32 == 0;
+  size_t pitch;
+  if (COOP) {
+    pitch = (words & ~(size_t)31) + LPR;
+    if (pitch < words) pitch += 32;
+  } else {
+    pitch = words | 4;
+  }
   size_t smem = pitch * 4 * (size_t)(2 * hint + H) + (size_t)G * W * H;
   smem = std::min<size_t>(std::max<size_t>(smem, 16 * 1024), (size_t)kCandSmemBytes);
   if ((int)smem > attr_bytes) {
