@@ -1,0 +1,211 @@
+#!/usr/bin/env python
+"""bench_kernels.py — per-kernel throughput and roofline for every row of SURVEY §8(a), on the
+BASELINE configs that are not the headline one (configs[2..4] shapes).  Not the driver's
+contract (that is bench.py); this fills BASELINE.md §5's per-kernel table.
+
+Each leg: device-resident inputs, >=3 warm-up launches, CUDA events on the launching stream,
+algorithmic bytes per unit from SURVEY §8(d).  Prints one JSON line per leg.
+"""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from rav1e_b200 import backend as B  # noqa: E402
+from tests import oracle_lib as O  # noqa: E402  (CPU baseline column only)
+
+PEAK = 6571.6
+if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+TX_SIZES = [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (4, 8), (8, 4), (8, 16), (16, 8), (16, 32),
+            (32, 16), (32, 64), (64, 32), (4, 16), (16, 4), (8, 32), (32, 8), (16, 64), (64, 16)]
+
+
+def timed(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def cpu_rate(fn, units):
+    """units/s of the oracle (all usable host threads) on the same inputs: ~0.5 s of work."""
+    import time
+    fn()
+    t0, reps = time.perf_counter(), 0
+    while time.perf_counter() - t0 < 0.5:
+        fn()
+        reps += 1
+    return units * reps / (time.perf_counter() - t0)
+
+
+def emit(name, units, unit_name, ms, bytes_per_unit, note="", cpu=None):
+    gbs = units * bytes_per_unit / (ms * 1e-3) / 1e9
+    d = {"kernel": name, "units_per_launch": units, "unit": unit_name, "launch_ms": ms,
+         "units_per_s": units / (ms * 1e-3), "algorithmic_bytes_per_unit": bytes_per_unit,
+         "algorithmic_GBps": gbs, "frac_of_measured_hbm": gbs / PEAK, "note": note}
+    if cpu is not None:
+        d["cpu_port_units_per_s"] = cpu
+        d["cpu_threads"] = O.host_threads()
+        d["gpu_over_cpu"] = d["units_per_s"] / cpu
+    print(json.dumps(d))
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).cuda()
+
+
+def grid_blocks(w, h, bw, bh):
+    xs, ys = np.arange(0, w - bw + 1, bw), np.arange(0, h - bh + 1, bh)
+    b = np.zeros(len(xs) * len(ys), B.BLOCK_DTYPE)
+    b["x"], b["y"] = np.tile(xs, len(ys)), np.repeat(ys, len(xs))
+    return b
+
+
+def main():
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = B.Context(0, use_torch_stream=True)
+    rng = np.random.default_rng(0)
+    W, H, PAD = 1920, 1080, 96
+
+    # ---- config 3: forward-transform sweep over a 1080p residual frame, all 160 pairs, 8 bit
+    resid = torch.from_numpy(rng.integers(-255, 256, (H * W,)).astype(np.int16)).cuda()
+    out = torch.empty(H * W, dtype=torch.int32, device="cuda")
+    sweep_ms = 0.0
+    for ts, (w, h) in enumerate(TX_SIZES):
+        n = (W // w) * (H // h)
+        for tt in range(17):
+            if not ctx.L.b200_valid_av1_transform(ts, tt):
+                continue
+            ms = timed(lambda: ctx.fwd_txfm_dev(resid, w * h, w, out, n, ts, tt, 8, False), reps=5)
+            sweep_ms += ms
+            if tt == 0:
+                cpu = None
+                if (w, h) in ((16, 16), (4, 4), (64, 64)):
+                    hres = resid.cpu().numpy()[:n * w * h].reshape(n, h, w)
+                    cpu = cpu_rate(lambda: O.forward_transform_batch(hres, ts, 0, 8, threads=O.host_threads()), n)
+                emit(f"fwd_txfm {w}x{h} DCT_DCT 8-bit", n, "blocks", ms, w * h * 4,
+                     "1080p residual frame tiled by this size; i16 in + i16 out", cpu)
+    print(json.dumps({"kernel": "fwd_txfm sweep (160 size/type pairs x whole 1080p frame)",
+                      "total_ms": sweep_ms, "pixels_per_s": 160 * W * H / (sweep_ms * 1e-3)}))
+
+    # ---- planes
+    oplanes = {}
+
+    def mk(key, dtype, bd):
+        img = rng.integers(0, 1 << bd, (H, W)).astype(dtype)
+        op = O.Plane(W, H, PAD, dtype=dtype)
+        op.fill_from(img)
+        oplanes[key] = op
+        return ctx.plane_from_host(img, PAD)
+    cur8, ref8 = mk("cur8", np.uint8, 8), mk("ref8", np.uint8, 8)
+    cur10, ref10 = mk("cur10", np.uint16, 10), mk("ref10", np.uint16, 10)
+    TH = O.host_threads()
+    blocks = grid_blocks(W, H, 16, 16)
+    nb = len(blocks)
+    d_blocks = dev(blocks)
+
+    # ---- mc: put_8tap HV, 16x16, REGULAR, 8 sub-pel vectors per block (config 4 shape)
+    pattern = np.array([(r * s, c * s) for s in (4, 2) for r, c in ((1, 0), (0, 1), (-1, 0), (0, -1))])
+    centre = rng.integers(-16, 17, (nb, 2)) * 8 + 3
+    mvs = (centre[:, None, :] + pattern[None]).reshape(-1, 2).astype(np.int16)
+    mblocks = np.repeat(blocks, len(pattern))
+    n = len(mblocks)
+    d_mb, d_mv = dev(mblocks), dev(mvs)
+    for name, ref, oref, bd, bpp in (("8-bit", ref8, "ref8", 8, 1), ("10-bit", ref10, "ref10", 10, 2)):
+        d_pred = torch.empty(n * 256 * bpp, dtype=torch.uint8, device="cuda")
+        ms = timed(lambda: ctx.mc_blocks_dev(ref, d_mb, d_mv, n, 16, 16, 0, 0, bd, 0, 0, 0, d_pred), reps=10)
+        cpu = cpu_rate(lambda: O.mc_blocks(oplanes[oref], mblocks, mvs, 16, 16, 0, 0, bd, threads=TH), n)
+        emit(f"put_8tap HV 16x16 {name}", n, "blocks", ms, (23 * 23 + 256) * bpp, cpu=cpu)
+
+    # ---- config 4: sub-pel candidates (MC + SATD + cost + argmin), 10-bit, 8 per block
+    cands = np.zeros(n, B.CAND_DTYPE)
+    cands["block"] = np.repeat(np.arange(nb, dtype=np.uint32), len(pattern))
+    cands["mv_row"], cands["mv_col"] = mvs[:, 0], mvs[:, 1]
+    offs = (np.arange(nb + 1) * len(pattern)).astype(np.uint32)
+    d_c, d_o = dev(cands), dev(offs)
+    d_best = torch.empty(nb * 16, dtype=torch.uint8, device="cuda")
+    for name, cur, ref, ocur, oref, bd, bpp in (("8-bit", cur8, ref8, "cur8", "ref8", 8, 1),
+                                                ("10-bit", cur10, ref10, "cur10", "ref10", 10, 2)):
+        p = B.me_params(16, 16, W, H, 6400, allow_hp=True, use_satd=True, bit_depth=bd)
+        ms = timed(lambda: ctx.me_subpel_candidates_dev(cur, ref, d_blocks, nb, d_c, n, p, 0, d_o, None,
+                                                        None, None, d_best), reps=10)
+        cpu = cpu_rate(lambda: O.subpel_candidates(oplanes[ocur], oplanes[oref], blocks, cands, 16, 16, True,
+                                                   6400, None, True, 0, bd, threads=TH), n)
+        emit(f"subpel candidates (put_8tap + SATD + cost + argmin) 16x16 {name}", n, "candidates", ms,
+             23 * 23 * bpp + 256 * bpp + 4, "two launches + argmin; prediction round-trips through HBM", cpu)
+    # chain tail: winners' prediction -> residual -> 16x16 DCT (10-bit)
+    d_pred = torch.empty(nb * 256 * 2, dtype=torch.uint8, device="cuda")
+    d_coef = torch.empty(nb * 256, dtype=torch.int32, device="cuda")
+    d_wmv = dev(mvs[::len(pattern)].copy())
+
+    def chain():
+        ctx.mc_blocks_dev(ref10, d_blocks, d_wmv, nb, 16, 16, 0, 0, 10, 0, 0, 0, d_pred)
+        ctx.fwd_txfm_pred_dev(cur10, d_pred, d_blocks, nb, d_coef, 2, 0, 10)
+    ms = timed(chain, reps=10)
+    emit("winner put_8tap + residual + fwd_txfm 16x16 10-bit", nb, "blocks", ms, 2598,
+         "SURVEY §8d fused MC->SATD->txfm figure (2598 B/block)")
+
+    # ---- intra: 13 modes per 16x16 block
+    edges = rng.integers(0, 256, (nb, 257)).astype(np.uint8)
+    modes = [(0, 3, 0), (2, 3, 180), (1, 3, 90), (9, 3, 0), (11, 3, 0), (10, 3, 0), (12, 3, 0), (3, 3, 45),
+             (4, 3, 135), (5, 3, 113), (6, 3, 157), (7, 3, 203), (8, 3, 67)]        # RAV1E_INTRA_MODES
+    items = np.zeros(nb * len(modes), B.INTRA_ITEM_DTYPE)
+    items["edge"] = np.repeat(np.arange(nb, dtype=np.uint32), len(modes))
+    items["mode"] = np.tile([m[0] for m in modes], nb)
+    items["variant"] = 3
+    items["angle"] = np.tile([m[2] for m in modes], nb)
+    items["ief"] = 0
+    items["left_len"] = items["above_len"] = 32
+    items["x"] = np.repeat(blocks["x"], len(modes))
+    items["y"] = np.repeat(blocks["y"], len(modes))
+    d_e, d_i = dev(edges), dev(items)
+    d_p = torch.empty(len(items) * 256, dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: ctx.predict_intra_dev(d_e, d_i, len(items), None, 16, 16, 8, W, H, d_p), reps=10)
+    hout = np.zeros((len(items), 256), np.uint8)
+    OL = O.lib()
+    OL.orc_predict_intra_batch.restype = None
+    OL.orc_predict_intra_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
+    cpu = cpu_rate(lambda: OL.orc_predict_intra_batch(edges.ctypes.data, 1, items.ctypes.data, len(items), None,
+                                                      16, 16, 8, W, H, hout.ctypes.data), len(items))
+    emit("predict_intra 16x16 x 13 modes 8-bit", len(items), "predictions", ms, 257 + 256, cpu=cpu)
+
+    # ---- config 5: CDEF on a 4K frame (luma + one 4:2:0 chroma plane)
+    W4, H4 = 3840, 2160
+    luma = rng.integers(0, 256, (H4, W4)).astype(np.uint8)
+    chroma = rng.integers(0, 256, (H4 // 2, W4 // 2)).astype(np.uint8)
+    pl, plo = ctx.plane_from_host(luma, 0), ctx.plane_from_host(np.zeros_like(luma), 0)
+    pc, pco = ctx.plane_from_host(chroma, 0), ctx.plane_from_host(np.zeros_like(chroma), 0)
+    n8 = (W4 // 8) * (H4 // 8)
+    d_dir = torch.empty(n8, dtype=torch.uint8, device="cuda")
+    d_var = torch.empty(n8, dtype=torch.int32, device="cuda")
+    d_str = dev(np.full(((H4 + 63) // 64) * ((W4 + 63) // 64), 4 * 7 + 2, np.uint8))
+    ms = timed(lambda: ctx.cdef_find_dir_dev(pl, 8, None, d_dir, d_var), reps=10)
+    cpu = cpu_rate(lambda: O.cdef_analyze_frame(luma, 8), n8)
+    emit("cdef_find_dir 4K luma", n8, "8x8 blocks", ms, 64 + 8, cpu=cpu)
+    hdirs, hvar = O.cdef_analyze_frame(luma, 8)
+    hstr = np.full(((H4 + 63) // 64, (W4 + 63) // 64), 4 * 7 + 2, np.uint8)
+    ms = timed(lambda: ctx.cdef_filter_plane_dev(pl, plo, 0, 0, 0, W4, H4, 8, 5, None, d_dir, d_var, d_str), reps=10)
+    cpu = cpu_rate(lambda: O.cdef_filter_plane(luma, 0, 0, 0, W4, H4, 8, 5, None, hdirs, hvar, hstr), n8)
+    emit("cdef_filter 4K luma", n8, "8x8 blocks", ms, 208, cpu=cpu)
+    ms = timed(lambda: ctx.cdef_filter_plane_dev(pc, pco, 1, 1, 1, W4, H4, 8, 5, None, d_dir, d_var, d_str), reps=10)
+    emit("cdef_filter 4K chroma 4:2:0", n8, "4x4 blocks", ms, 8 * 8 + 16)
+
+
+if __name__ == "__main__":
+    main()

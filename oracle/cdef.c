@@ -184,6 +184,7 @@ int orc_cdef_adjust_strength(int strength, int var) {
 void orc_cdef_analyze_frame(const void *luma, ptrdiff_t stride, int bpp, int width, int height,
                             int bit_depth, const uint8_t *skip8, uint8_t *dir, int32_t *var) {
   const int w8 = width >> 3, h8 = height >> 3;
+#pragma omp parallel for schedule(static)
   for (int by = 0; by < h8; by++)
     for (int bx = 0; bx < w8; bx++) {
       dir[by * w8 + bx] = 0;
@@ -208,6 +209,7 @@ void orc_cdef_filter_plane(const void *in, ptrdiff_t in_stride, void *out, ptrdi
   const int coeff_shift = bit_depth - 8;
   const int xsize = 8 >> xdec, ysize = 8 >> ydec;
   static const uint8_t uv_dir_422[8] = {7, 0, 2, 4, 5, 6, 6, 6}; /* :505-509 */
+#pragma omp parallel for schedule(static)
   for (int gy = 0; gy < h8; gy++)
     for (int gx = 0; gx < w8; gx++) {
       int edges = 0;

@@ -136,3 +136,25 @@ void orc_pred_cfl_ac(int16_t *ac, const void *luma, ptrdiff_t luma_stride, int b
   else
     pred_cfl_ac_u16(ac, (const uint16_t *)luma, luma_stride, bw, bh, w_pad, h_pad, xdec, ydec);
 }
+
+/* Batched form for the CPU baseline: items mirror b200_intra_item (include/b200rdo.h). */
+typedef struct {
+  uint32_t edge, ac;
+  int16_t x, y, angle;
+  uint8_t mode, variant;
+  int8_t ief;
+  uint8_t left_len, above_len, pad_;
+} orc_intra_item;
+
+void orc_predict_intra_batch(const void *edges, int bpp, const orc_intra_item *items, size_t n,
+                             const int16_t *ac, int w, int h, int bit_depth, int plane_w, int plane_h,
+                             void *out) {
+#pragma omp parallel for schedule(static)
+  for (ptrdiff_t i = 0; i < (ptrdiff_t)n; i++) {
+    const orc_intra_item it = items[i];
+    orc_predict_intra(it.mode, it.variant, (uint8_t *)out + (size_t)i * w * h * bpp, w, bpp, w, h,
+                      bit_depth, ac ? ac + (size_t)it.ac * w * h : 0, it.angle, it.ief,
+                      (const uint8_t *)edges + (size_t)it.edge * 257 * bpp, it.left_len, it.above_len,
+                      plane_w, plane_h, it.x, it.y);
+  }
+}

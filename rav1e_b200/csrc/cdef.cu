@@ -97,12 +97,14 @@ __global__ void cdef_find_dir_kernel(const T *luma, int stride, int w8, int h8, 
   }
 }
 
-// cdef.rs:146-159
-__device__ __forceinline__ int constrain(int diff, int threshold, int damping) {
-  if (threshold == 0) return 0;
-  const int shift = max(0, damping - (31 - __clz(threshold)));
+// cdef.rs:146-159, with `shift = max(0, damping - msb(threshold))` hoisted out of the tap loop
+// (it only depends on the block's strength).  threshold == 0 gives 0 for any shift.
+__device__ __forceinline__ int constrain_shift(int threshold, int damping) {
+  return threshold ? max(0, damping - (31 - __clz(threshold))) : 0;
+}
+__device__ __forceinline__ int constrain(int diff, int threshold, int shift) {
   const int ad = abs(diff);
-  const int mag = min(max(threshold - (ad >> shift), 0), ad);
+  const int mag = min(max(threshold - (ad >> shift), 0), ad);  // threshold == 0 -> 0
   return diff < 0 ? -mag : mag;
 }
 
@@ -124,6 +126,8 @@ template <typename Load>
 __device__ __forceinline__ int cdef_pixel(Load load, int pri_strength, int sec_strength, int dir,
                                           int damping, int coeff_shift) {
   const int x = load(0, 0);
+  const int pri_shift = constrain_shift(pri_strength, damping);
+  const int sec_shift = constrain_shift(sec_strength, damping);
   const int sel = (pri_strength >> coeff_shift) & 1;
   const int pri_taps[2] = {sel ? 3 : 4, sel ? 3 : 2};
   const int sec_taps[2] = {2, 1};
@@ -136,7 +140,7 @@ __device__ __forceinline__ int cdef_pixel(Load load, int pri_strength, int sec_s
     const int p[2] = {load(d0y, d0x), load(-d0y, -d0x)};
 #pragma unroll
     for (int t = 0; t < 2; t++) {
-      sum += pri_taps[k] * constrain(p[t] - x, pri_strength, damping);
+      sum += pri_taps[k] * constrain(p[t] - x, pri_strength, pri_shift);
       if (p[t] != kVeryLarge) mx = max(p[t], mx);
       mn = min(p[t], mn);
     }
@@ -145,7 +149,7 @@ __device__ __forceinline__ int cdef_pixel(Load load, int pri_strength, int sec_s
     for (int t = 0; t < 4; t++) {
       if (s[t] != kVeryLarge) mx = max(s[t], mx);
       mn = min(s[t], mn);
-      sum += sec_taps[k] * constrain(s[t] - x, sec_strength, damping);
+      sum += sec_taps[k] * constrain(s[t] - x, sec_strength, sec_shift);
     }
   }
   const int v = x + ((8 + sum - (sum < 0)) >> 4);
@@ -172,10 +176,12 @@ __global__ void __launch_bounds__(256) cdef_filter_kernel(CdefPlaneArgs a) {
   const int coeff_shift = a.bit_depth - 8;
   const T *in = (const T *)a.in;
   T *out = (T *)a.out;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < (long long)pw * ph;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int y = (int)(idx / pw), x = (int)(idx - (long long)y * pw);
-    const int gy = y / ysize, gx = x / xsize, i = y - gy * ysize, j = x - gx * xsize;
+  // 2-D launch: 64 x 4 pixels per CTA, one pixel per thread; block sizes are powers of two
+  const int xs_log2 = 3 - a.xdec, ys_log2 = 3 - a.ydec;
+  {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= pw || y >= ph) return;
+    const int gy = y >> ys_log2, gx = x >> xs_log2, i = y - (gy << ys_log2), j = x - (gx << xs_log2);
     const int b = gy * a.w8 + gx;
     const T *blk = in + (long long)(gy * ysize) * a.in_stride + gx * xsize;
     int v;
@@ -281,8 +287,7 @@ extern "C" int b200_cdef_filter_plane_dev(b200_ctx *ctx, const b200_plane *in, c
   a.dir = d_dir;
   a.var = d_var;
   a.strength_sb = d_strength_sb;
-  const long long total = (long long)(luma_width >> xdec) * (luma_height >> ydec);
-  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 32);
+  const dim3 grid(((luma_width >> xdec) + 63) / 64, ((luma_height >> ydec) + 3) / 4);
   if (in->bpp == 1)
     cdef_filter_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(a);
   else

@@ -1,7 +1,7 @@
 // mc.cu — batched 8-tap sub-pel motion compensation (rav1e src/mc.rs:250-479) for sm_100a.
 //
-// One CTA per predicted block.  The (w+7) x (h+7) source footprint is staged once in shared
-// memory; the separable filter then runs as the reference's four cases (copy / V only /
+// One warp per predicted block (up to 8 blocks per CTA).  The (w+7) x (h+7) source footprint is
+// staged once in shared memory; the separable filter then runs as the reference's four cases (copy / V only /
 // H only with its double rounding / H into an i16 intermediate then V), all in exact integer
 // arithmetic, with the 6 x 16 x 8 coefficient table in constant memory.  `put` writes pixels,
 // `prep` writes the biased i16 intermediate used by compound prediction, `avg` blends two of
@@ -75,19 +75,24 @@ struct McArgs {
   int col_frac, row_frac;
 };
 
+// One WARP per predicted block; a CTA carries `blockDim.x / 32` blocks, each with its own slice
+// of shared memory (source tile + i16 intermediate).  Warp-level staging and passes need no
+// block-wide barriers; filter taps sit in registers.
 template <typename T>
-__global__ void __launch_bounds__(256) mc_kernel(McArgs a) {
+__global__ void __launch_bounds__(256) mc_kernel(McArgs a, int smem_per_warp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = a.w, h = a.h;
   const int tw = w + 7, th = h + 7;
-  T *tile = (T *)smem_raw;                                  // [th][tw]
-  short *inter = (short *)(tile + (size_t)th * tw + (((size_t)th * tw) & 1));  // [th][w]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  T *tile = (T *)(smem_raw + (size_t)wid * smem_per_warp);                       // [th][tw]
+  short *inter = (short *)(tile + (size_t)th * tw + (((size_t)th * tw) & 1));     // [th][w]
   const int ib = 4 - (a.bit_depth == 12 ? 2 : 0);
   const int maxv = (1 << a.bit_depth) - 1;
   const int prep_bias = a.bit_depth == 8 ? 0 : 8192;
   const int xb = filter_bank(a.mode_x, w), yb = filter_bank(a.mode_y, h);
+  const int wlog2 = 31 - __clz(w);
 
-  for (size_t blk = blockIdx.x; blk < a.n; blk += gridDim.x) {
+  for (size_t blk = (size_t)blockIdx.x * nw + wid; blk < a.n; blk += (size_t)gridDim.x * nw) {
     int x0 = 0, y0 = 0, col_frac = a.col_frac, row_frac = a.row_frac;
     if (!a.explicit_frac) {
       b200_block b;
@@ -109,63 +114,70 @@ __global__ void __launch_bounds__(256) mc_kernel(McArgs a) {
       col_frac = (int)(((unsigned)mvc << (1 - a.xdec)) & 0xf);
     }
     const T *src = (const T *)a.ref + (long long)y0 * a.ref_stride + x0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < th * tw; i += blockDim.x) {
-      const int r = i / tw, c = i - r * tw;
-      tile[i] = src[(long long)(r - 3) * a.ref_stride + (c - 3)];
+    int xf[8], yf[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      xf[k] = kSubpel[xb][col_frac][k];
+      yf[k] = kSubpel[yb][row_frac][k];
     }
-    __syncthreads();
-    const short *xf = kSubpel[xb][col_frac], *yf = kSubpel[yb][row_frac];
+    __syncwarp();
+    for (int r = 0; r < th; r++) {
+      const T *srow = src + (long long)(r - 3) * a.ref_stride - 3;
+      for (int c = lane; c < tw; c += 32) tile[r * tw + c] = srow[c];
+    }
+    __syncwarp();
     T *outp = (T *)a.out + blk * (size_t)w * h;
     short *outs = (short *)a.out + blk * (size_t)w * h;
     if (col_frac != 0 && row_frac != 0) {
       // H pass into the i16 intermediate over h+7 rows (mc.rs:312-327): `as i16` truncates
-      for (int i = threadIdx.x; i < th * w; i += blockDim.x) {
-        const int r = i / w, c = i - r * w;
+      // flattened (row, col) index: w is a power of two, so all 32 lanes stay busy for any w
+      for (int i = lane; i < th * w; i += 32) {
+        const int r = i >> wlog2, c = i & (w - 1);
         int s = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) s += xf[k] * (int)tile[r * tw + c + k];
         inter[i] = (short)rshift_round(s, 7 - ib);
       }
-      __syncthreads();
-      for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
-        const int r = i / w, c = i - r * w;
+      __syncwarp();
+      for (int i = lane; i < h * w; i += 32) {
         int s = 0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) s += yf[k] * (int)inter[(r + k) * w + c];
+        for (int k = 0; k < 8; k++) s += yf[k] * (int)inter[i + k * w];
         if (a.kind == 0)
           outp[i] = (T)min(max(rshift_round(s, 7 + ib), 0), maxv);
         else
           outs[i] = (short)(rshift_round(s, 7) - prep_bias);
       }
     } else {
-      for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
-        const int r = i / w, c = i - r * w;
-        if (col_frac == 0 && row_frac == 0) {
-          const int p = (int)tile[(r + 3) * tw + c + 3];
-          if (a.kind == 0)
-            outp[i] = (T)p;
-          else
-            outs[i] = (short)((short)((short)p << ib) - (short)prep_bias);
-        } else if (col_frac == 0) {  // V only (mc.rs:277-296 / :387-403)
-          int s = 0;
+      for (int i = lane; i < h * w; i += 32) {
+        {
+          const int r = i >> wlog2, c = i & (w - 1);
+          if (col_frac == 0 && row_frac == 0) {
+            const int p = (int)tile[(r + 3) * tw + c + 3];
+            if (a.kind == 0)
+              outp[i] = (T)p;
+            else
+              outs[i] = (short)((short)((short)p << ib) - (short)prep_bias);
+          } else if (col_frac == 0) {  // V only (mc.rs:277-296 / :387-403)
+            int s = 0;
 #pragma unroll
-          for (int k = 0; k < 8; k++) s += yf[k] * (int)tile[(r + k) * tw + c + 3];
-          if (a.kind == 0)
-            outp[i] = (T)min(max(rshift_round(s, 7), 0), maxv);
-          else
-            outs[i] = (short)(rshift_round(s, 7 - ib) - prep_bias);
-        } else {  // H only, double rounding in `put` (mc.rs:297-311)
-          int s = 0;
+            for (int k = 0; k < 8; k++) s += yf[k] * (int)tile[(r + k) * tw + c + 3];
+            if (a.kind == 0)
+              outp[i] = (T)min(max(rshift_round(s, 7), 0), maxv);
+            else
+              outs[i] = (short)(rshift_round(s, 7 - ib) - prep_bias);
+          } else {  // H only, double rounding in `put` (mc.rs:297-311)
+            int s = 0;
 #pragma unroll
-          for (int k = 0; k < 8; k++) s += xf[k] * (int)tile[(r + 3) * tw + c + k];
-          if (a.kind == 0)
-            outp[i] = (T)min(max(rshift_round(rshift_round(s, 7 - ib), ib), 0), maxv);
-          else
-            outs[i] = (short)(rshift_round(s, 7 - ib) - prep_bias);
+            for (int k = 0; k < 8; k++) s += xf[k] * (int)tile[(r + 3) * tw + c + k];
+            if (a.kind == 0)
+              outp[i] = (T)min(max(rshift_round(rshift_round(s, 7 - ib), ib), 0), maxv);
+            else
+              outs[i] = (short)(rshift_round(s, 7 - ib) - prep_bias);
+          }
         }
-      }
     }
+    __syncwarp();
   }
 }
 
@@ -190,7 +202,10 @@ int check_mc(b200_ctx *ctx, int w, int h, int mode_x, int mode_y, int bit_depth)
 
 int launch_mc(b200_ctx *ctx, const McArgs &a, int bpp) {
   const size_t tile_elems = (size_t)(a.w + 7) * (a.h + 7);
-  const size_t smem = (tile_elems + (tile_elems & 1)) * bpp + (size_t)(a.h + 7) * a.w * 2 + 16;
+  const size_t per_warp = b200_align_up((tile_elems + (tile_elems & 1)) * bpp + (size_t)(a.h + 7) * a.w * 2, 16);
+  // warps (= blocks in flight) per CTA: as many as fit ~96 KB, at most 8
+  int wpc = (int)std::min<size_t>(8, std::max<size_t>(1, (96 * 1024) / per_warp));
+  const size_t smem = per_warp * wpc;
   static size_t attr8 = 0, attr16 = 0;
   size_t &attr = bpp == 1 ? attr8 : attr16;
   if (smem > 48 * 1024 && smem > attr) {
@@ -200,12 +215,12 @@ int launch_mc(b200_ctx *ctx, const McArgs &a, int bpp) {
       B200_CUDA(ctx, cudaFuncSetAttribute(mc_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  const int threads = a.w * a.h >= 256 ? 256 : (a.w * a.h >= 64 ? 64 : 32);
-  const int grid = (int)std::min<size_t>(a.n, (size_t)ctx->num_sms * 16);
+  const size_t ctas = (a.n + wpc - 1) / wpc;
+  const int grid = (int)std::min<size_t>(ctas, (size_t)ctx->num_sms * 16);
   if (bpp == 1)
-    mc_kernel<uint8_t><<<grid, threads, smem, ctx->stream>>>(a);
+    mc_kernel<uint8_t><<<grid, wpc * 32, smem, ctx->stream>>>(a, (int)per_warp);
   else
-    mc_kernel<uint16_t><<<grid, threads, smem, ctx->stream>>>(a);
+    mc_kernel<uint16_t><<<grid, wpc * 32, smem, ctx->stream>>>(a, (int)per_warp);
   B200_LAUNCH_CHECK(ctx);
   return B200_OK;
 }
