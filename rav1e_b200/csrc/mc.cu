@@ -150,7 +150,6 @@ __global__ void __launch_bounds__(256) mc_kernel(McArgs a, int smem_per_warp) {
       }
     } else {
       for (int i = lane; i < h * w; i += 32) {
-        {
           const int r = i >> wlog2, c = i & (w - 1);
           if (col_frac == 0 && row_frac == 0) {
             const int p = (int)tile[(r + 3) * tw + c + 3];
