@@ -528,7 +528,11 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
         b1 = b0 + 1;
         continue;
       }
-      const bool staged = have && fits;
+      // Sparse candidate sets (few candidates per block, e.g. the sub-pel / mode-pruning SATD
+      // lists) read fewer bytes straight from L1/L2 than staging the whole bounding window would
+      // move: stage only when the candidates' own footprints exceed half the window.
+      const bool dense = (long long)(hi - lo) * (W * H) * 2 >= (long long)rows * row_bytes;
+      const bool staged = have && fits && dense;
       if (staged)
         stage_window(win, pitch_words, px<uint8_t>(a.ref, wx0, wy0), a.ref.stride, rows, row_bytes);
       // org blocks -> packed words
@@ -680,29 +684,24 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
                                         org + cy * (W / 4) + cx / 4, W / 4);
               }
             }
-          } else {  // window too large for shared memory: bytes straight from L1/L2
+          } else {
+            // not staged (sparse set, or a window too large for shared memory): the same word /
+            // funnel-shift arithmetic straight from the plane through L1/L2.  Rows are word
+            // addressed from a 4-byte aligned base (the row pitch is a multiple of 16 bytes).
             const uint8_t *rp = px<uint8_t>(a.ref, rx, ry);
+            const int gsh = (int)((uintptr_t)rp & 3);
+            const uint32_t *gw = (const uint32_t *)(rp - gsh);
+            const int gpitch = a.ref.stride >> 2;
             if (!SATD) {
-              for (int y = 0; y < H; y++) {
-                const uint8_t *q = rp + (long long)y * a.ref.stride;
-                const uint8_t *o = (const uint8_t *)(org + y * (W / 4));
-#pragma unroll
-                for (int x = 0; x < W; x++) acc += (uint32_t)abs((int)q[x] - (int)o[x]);
-              }
+#pragma unroll 4
+              for (int y = 0; y < H; y++)
+                acc = row_sad_u8<W>(gw + (long long)y * gpitch, 0, gsh * 8, org + y * (W / 4), acc);
             } else {
               for (int ch = sub; ch < NCH; ch += TPC) {
                 const int cy = (ch / (W / S)) * S, cx = (ch % (W / S)) * S;
-                int d[S * S];
-#pragma unroll
-                for (int y = 0; y < S; y++)
-#pragma unroll
-                  for (int x = 0; x < S; x++)
-                    d[y * S + x] = (int)((const uint8_t *)(org + (cy + y) * (W / 4)))[cx + x] -
-                                   (int)rp[(long long)(cy + y) * a.ref.stride + cx + x];
-                if (S == 4)
-                  acc += hadamard4x4_abs_sum(*(int(*)[16])d);
-                else
-                  acc += hadamard8x8_abs_sum(*(int(*)[64])d);
+                const int o2 = gsh + cx;
+                acc += chunk_satd_u8<S>(gw + (long long)cy * gpitch, gpitch, o2 >> 2, (o2 & 3) * 8,
+                                        org + cy * (W / 4) + cx / 4, W / 4);
               }
             }
           }
@@ -773,6 +772,136 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
       if (whole) break;
       b0 = b1;
       b1 = b0 + 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- sparse candidate lists
+// Few candidates per block (sub-pel refinement, mode pruning: ~4-16): staging a window per group
+// costs more than the candidates read, and a CTA-wide pipeline has nothing to amortise.  One WARP
+// per block instead: TPC lanes per candidate (SATD: one Hadamard chunk each; SAD: TPC = 1), the
+// reference and org words come straight from the planes through L1 (all lanes of a warp share the
+// block, so org reads are broadcasts), cost + first-min argmin by REDUX over the packed key.  No
+// shared memory, no barriers.
+template <int W, int H, bool SATD>
+__global__ void __launch_bounds__(256) me_cand_warp_u8(MeArgs a) {
+  constexpr int S = (W < 8 || H < 8) ? 4 : 8;
+  constexpr int NCH = SATD ? (W / S) * (H / S) : 1;
+  constexpr int TPC = NCH < 32 ? NCH : 32;
+  constexpr int SLOTS = 32 / TPC;
+  const int lane = threadIdx.x & 31;
+  const int slot = lane / TPC, sub = lane - slot * TPC;
+  const size_t warp0 = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+  const int cpitch = a.cur.stride >> 2, rpitch = a.ref.stride >> 2;
+  for (size_t blk = warp0; blk < a.nblocks; blk += nwarps) {
+    const uint32_t lo = a.cand_offsets[blk], hi = a.cand_offsets[blk + 1];
+    const b200_block b = a.blocks[blk];
+    const MvRange r = b200_mv_range(a.w_in_b, a.h_in_b, b.x / MI_SIZE, b.y / MI_SIZE, W, H);
+    int p0r = 0, p0c = 0, p1r = 0, p1c = 0;
+    if (a.pmv) {
+      const short *p = a.pmv + 4 * blk;
+      p0r = p[0], p0c = p[1], p1r = p[2], p1c = p[3];
+    }
+    // org block: word-addressed from a 4-byte aligned base
+    const uint8_t *op = px<uint8_t>(a.cur, b.x, b.y);
+    const int osh = (int)((uintptr_t)op & 3);
+    const uint32_t *ow = (const uint32_t *)(op - osh);
+    unsigned long long best = ~0ull;
+    for (uint32_t base = lo; base < hi; base += SLOTS) {
+      const uint32_t i = base + slot;
+      const bool valid = i < hi;
+      b200_cand c;
+      c.block = 0;
+      c.mv_row = 0;
+      c.mv_col = 0;
+      if (valid) c = a.cands[i];
+      const bool inr = valid && !(c.mv_col < r.x_min || c.mv_col > r.x_max || c.mv_row < r.y_min ||
+                                  c.mv_row > r.y_max);
+      uint32_t acc = 0;
+      if (inr) {
+        const uint8_t *rp = px<uint8_t>(a.ref, b.x + c.mv_col / 8, b.y + c.mv_row / 8);
+        const int gsh = (int)((uintptr_t)rp & 3);
+        const uint32_t *gw = (const uint32_t *)(rp - gsh);
+        if (!SATD) {
+          for (int y = 0; y < H; y++) {
+            uint32_t orow[W / 4];
+            const uint32_t *os = ow + (long long)y * cpitch;
+            uint32_t olo = __ldg(os);
+#pragma unroll
+            for (int k = 0; k < W / 4; k++) {
+              const uint32_t ohi = __ldg(os + k + 1);
+              orow[k] = __funnelshift_r(olo, ohi, osh * 8);
+              olo = ohi;
+            }
+            acc = row_sad_u8<W>(gw + (long long)y * rpitch, 0, gsh * 8, orow, acc);
+          }
+        } else {
+          for (int ch = sub; ch < NCH; ch += TPC) {
+            const int cy = (ch / (W / S)) * S, cx = (ch % (W / S)) * S;
+            uint32_t ochunk[S * (S / 4)];  // this chunk's org rows, realigned to words
+#pragma unroll
+            for (int y = 0; y < S; y++) {
+              const int oo = osh + cx;
+              const uint32_t *os = ow + (long long)(cy + y) * cpitch + (oo >> 2);
+              uint32_t olo = __ldg(os);
+#pragma unroll
+              for (int k = 0; k < S / 4; k++) {
+                const uint32_t ohi = __ldg(os + k + 1);
+                ochunk[y * (S / 4) + k] = __funnelshift_r(olo, ohi, (oo & 3) * 8);
+                olo = ohi;
+              }
+            }
+            const int o2 = gsh + cx;
+            acc += chunk_satd_u8<S>(gw + (long long)cy * rpitch, rpitch, o2 >> 2, (o2 & 3) * 8, ochunk, S / 4);
+          }
+        }
+      }
+      if (SATD) {
+#pragma unroll
+        for (int o = TPC >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        constexpr int ln = S == 4 ? 2 : 3;
+        acc = (acc + ((1u << ln) >> 1)) >> ln;
+      }
+      uint32_t sad = kEmptySad;
+      unsigned long long cost = kEmptyCost, key = ~0ull;
+      if (inr && sub == 0) {
+        sad = acc;
+        cost = b200_mv_cost(sad, c.mv_row, c.mv_col, p0r, p0c, p1r, p1c, a.lambda, a.allow_hp);
+        key = pack_key(cost, i - lo);
+      }
+      if (valid && sub == 0) {
+        if (a.out_sad) a.out_sad[i] = sad;
+        if (a.out_cost) a.out_cost[i] = cost;
+      }
+      best = key < best ? key : best;
+    }
+    if (a.out_best) {
+      const uint32_t khi = (uint32_t)(best >> 32);
+      const uint32_t mh = __reduce_min_sync(0xffffffffu, khi);
+      const uint32_t klo = khi == mh ? (uint32_t)best : 0xffffffffu;
+      const uint32_t ml = __reduce_min_sync(0xffffffffu, klo);
+      if (lane == 0) {
+        const unsigned long long key = ((unsigned long long)mh << 32) | ml;
+        b200_me_result res;
+        res.cost = kEmptyCost;
+        res.sad = kEmptySad;
+        res.mv_row = 0;
+        res.mv_col = 0;
+        if (key != ~0ull) {
+          const uint32_t idx = (uint32_t)(key & ((1u << kKeyIdxBits) - 1));
+          const unsigned long long cost = key >> kKeyIdxBits;
+          const b200_cand c = a.cands[lo + idx];
+          const uint32_t r1 = b200_mv_rate(c.mv_row, c.mv_col, p0r, p0c, a.allow_hp);
+          const uint32_t r2 = b200_mv_rate(c.mv_row, c.mv_col, p1r, p1c, a.allow_hp) + 1;
+          const uint32_t rate = r1 < r2 ? r1 : r2;
+          res.cost = cost;
+          res.sad = (uint32_t)((cost - (unsigned long long)rate * a.lambda) >> 8);
+          res.mv_row = c.mv_row;
+          res.mv_col = c.mv_col;
+        }
+        a.out_best[blk] = res;
+      }
     }
   }
 }
@@ -968,6 +1097,20 @@ __global__ void __launch_bounds__(256) me_full_search_u8(FsArgs a) {
 template <int W, int H, bool SATD>
 int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px) {
   static int attr_bytes = 0;
+  {
+    // Sparse lists: when a block's candidates cover less than a quarter of the window the
+    // grouped kernel would stage for it, take the warp-per-block kernel (no staging at all).
+    const int hint0 = window_hint_px > 0 ? window_hint_px : 32;
+    const double win_bytes = (double)(2 * hint0 + W) * (2 * hint0 + H);
+    const double avg0 = a.nblocks ? (double)a.ncands / (double)a.nblocks : 0.0;
+    if (avg0 * W * H * 4 < win_bytes && (a.cur.stride & 3) == 0) {
+      const int wpc = 8;
+      const int grid = (int)std::min<size_t>((a.nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms * 16);
+      me_cand_warp_u8<W, H, SATD><<<grid, wpc * 32, 0, ctx->stream>>>(a);
+      B200_LAUNCH_CHECK(ctx);
+      return B200_OK;
+    }
+  }
   // Group size: enough candidates to fill a CTA, bounded by the org tile budget.
   const size_t avg = a.nblocks ? a.ncands / a.nblocks : 0;
   constexpr int S = (W < 8 || H < 8) ? 4 : 8;

@@ -68,6 +68,14 @@ CAND_CASES = [
     (16, 16, np.uint16, 10, True, 10, 24),
     (32, 16, np.uint16, 12, True, 7, 24),
     (64, 64, np.uint16, 12, False, 3, 24),
+    # sparse lists (few candidates per block): the warp-per-block kernel without window staging
+    (16, 16, np.uint8, 8, True, 4, 40),
+    (16, 16, np.uint8, 8, False, 3, 40),
+    (8, 8, np.uint8, 8, True, 2, 30),
+    (32, 32, np.uint8, 8, True, 3, 64),
+    (4, 8, np.uint8, 8, True, 3, 20),
+    (64, 64, np.uint8, 8, True, 2, 60),
+    (32, 16, np.uint8, 8, False, 1, 50),
 ]
 
 
