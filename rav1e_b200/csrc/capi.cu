@@ -58,7 +58,6 @@ extern "C" void b200_ctx_destroy(b200_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->dwork) cudaFree(ctx->dwork);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -116,20 +115,6 @@ extern "C" int b200_memcpy_d2h(b200_ctx *ctx, void *host, const void *dptr, size
   B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
   B200_CUDA(ctx, cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return B200_OK;
-}
-
-int b200_reserve_pinned(b200_ctx *ctx, size_t bytes) {
-  if (bytes <= ctx->pinned_bytes) return B200_OK;
-  if (ctx->pinned) {
-    B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    B200_CUDA(ctx, cudaFreeHost(ctx->pinned));
-    ctx->pinned = nullptr;
-    ctx->pinned_bytes = 0;
-  }
-  size_t want = b200_align_up(bytes + bytes / 4, 1 << 20);
-  B200_CUDA(ctx, cudaMallocHost(&ctx->pinned, want));
-  ctx->pinned_bytes = want;
   return B200_OK;
 }
 

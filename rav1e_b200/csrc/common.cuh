@@ -20,9 +20,7 @@ struct b200_ctx {
   cudaStream_t stream = nullptr;  // the stream kernels are enqueued on
   uint64_t launches = 0;
   int num_sms = B200_NUM_SMS;
-  // grow-only staging: pinned host + device workspace for the host-buffer (batch) forms
-  void *pinned = nullptr;
-  size_t pinned_bytes = 0;
+  // grow-only device workspace (generic path scratch, sub-pel predictions)
   void *dwork = nullptr;
   size_t dwork_bytes = 0;
   int async_batch = 0;  // host-buffer forms skip their final synchronize (b200_ctx_set_async)
@@ -61,8 +59,7 @@ inline int b200_fail(b200_ctx *ctx, int status, const char *fmt, ...) {
     B200_CUDA((ctx), cudaGetLastError()); \
   } while (0)
 
-// Grow-only scratch used by the host-buffer entry points.
-int b200_reserve_pinned(b200_ctx *ctx, size_t bytes);
+// Grow-only device scratch.
 int b200_reserve_dwork(b200_ctx *ctx, size_t bytes);
 int b200_mc_cands_internal(b200_ctx *ctx, const b200_plane *ref, const b200_block *d_blocks,
                            const b200_cand *d_cands, size_t ncands, int w, int h, int mode,

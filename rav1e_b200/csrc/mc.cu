@@ -7,6 +7,8 @@
 // `prep` writes the biased i16 intermediate used by compound prediction, `avg` blends two of
 // those (mc.rs:454-479).  Blocks are addressed by (position, motion vector) through
 // get_mv_params (predict.rs:284-297), so one launch predicts thousands of blocks.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace {
@@ -205,15 +207,14 @@ int launch_mc(b200_ctx *ctx, const McArgs &a, int bpp) {
   // warps (= blocks in flight) per CTA: as many as fit ~96 KB, at most 8
   int wpc = (int)std::min<size_t>(8, std::max<size_t>(1, (96 * 1024) / per_warp));
   const size_t smem = per_warp * wpc;
-  static size_t attr8 = 0, attr16 = 0;
-  size_t &attr = bpp == 1 ? attr8 : attr16;
-  if (smem > 48 * 1024 && smem > attr) {
-    if (bpp == 1)
-      B200_CUDA(ctx, cudaFuncSetAttribute(mc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else
-      B200_CUDA(ctx, cudaFuncSetAttribute(mc_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {  // thread safe; 128 KB covers one 128x128 u16 block per warp slot
+    attr_err = cudaFuncSetAttribute(mc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(mc_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+  });
+  B200_CUDA(ctx, attr_err);
   const size_t ctas = (a.n + wpc - 1) / wpc;
   const int grid = (int)std::min<size_t>(ctas, (size_t)ctx->num_sms * 16);
   if (bpp == 1)

@@ -18,6 +18,8 @@
 //                           sharing their loaded words.
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace {
@@ -1096,7 +1098,15 @@ __global__ void __launch_bounds__(256) me_full_search_u8(FsArgs a) {
 // ---------------------------------------------------------------- host-side dispatch
 template <int W, int H, bool SATD>
 int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px) {
-  static int attr_bytes = 0;
+  // opt in to the largest dynamic shared memory this kernel may be launched with, once
+  // (thread safe: contexts on several host threads launch concurrently)
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(me_cand_group_u8<W, H, SATD>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, kCandSmemBytes);
+  });
+  B200_CUDA(ctx, attr_err);
   {
     // Sparse lists: when a block's candidates cover less than a quarter of the window the
     // grouped kernel would stage for it, take the warp-per-block kernel (no staging at all).
@@ -1135,11 +1145,6 @@ int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px) {
   }
   size_t smem = pitch * 4 * (size_t)(2 * hint + H) + (size_t)G * W * H;
   smem = std::min<size_t>(std::max<size_t>(smem, 16 * 1024), (size_t)kCandSmemBytes);
-  if ((int)smem > attr_bytes) {
-    B200_CUDA(ctx, cudaFuncSetAttribute(me_cand_group_u8<W, H, SATD>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_bytes = (int)smem;
-  }
   a.smem_bytes = (int)smem;
   const size_t ngroups = (a.nblocks + G - 1) / G;
   a.ngroups = ngroups;
@@ -1152,13 +1157,13 @@ int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px) {
 template <int W, int H>
 int launch_fs_u8(b200_ctx *ctx, const FsArgs &a, size_t smem_bytes) {
   constexpr int NP = W >= 8 ? 4 : 2;
-  static size_t attr = 0;
-  if (smem_bytes > attr) {
-    B200_CUDA(ctx, cudaFuncSetAttribute(me_full_search_u8<W, H, NP>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem_bytes));
-    attr = smem_bytes;
-  }
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(me_full_search_u8<W, H, NP>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, kFsSmemBytes);
+  });
+  B200_CUDA(ctx, attr_err);
   const int grid = (int)std::min<size_t>(a.nblocks, (size_t)ctx->num_sms * 32);
   me_full_search_u8<W, H, NP><<<grid, 256, smem_bytes, ctx->stream>>>(a);
   B200_LAUNCH_CHECK(ctx);

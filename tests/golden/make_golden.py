@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Extracts the reference's own known-answer vectors for the hot path into
+tests/golden/reference_kats.json (run by hand in the build container; needs /root/reference).
+
+Sources (xiph/rav1e @ 564ae3b):
+  src/dist.rs:418-441     get_sad_same_inner   (w, h, SAD)  on the closed-form planes of :384-413
+  src/dist.rs:477-500     get_satd_same_inner  (w, h, SATD)
+  src/predict.rs:1523-1566  4x4 DC / DC_TOP / DC_LEFT / DC_128 / V / H / Paeth / smooth x3
+  src/predict.rs:1569-1602  27 directional angles and their expected 4x4 outputs
+  src/cdef.rs:304-309     first_max_element
+The Rust test code is parsed textually; nothing is executed (no rustc in this image).
+"""
+import json
+import os
+import re
+
+REF = "/root/reference/src"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_kats.json")
+
+
+def triples(text):
+    return [[int(a), int(b), int(c)] for a, b, c in re.findall(r"\((\d+),\s*(\d+),\s*(\d+)\)", text)]
+
+
+def main():
+    dist = open(os.path.join(REF, "dist.rs")).read()
+    sad_part = dist[dist.index("fn get_sad_same_inner"):dist.index("fn get_sad_same_u8")]
+    satd_part = dist[dist.index("fn get_satd_same_inner"):dist.index("fn get_satd_same_u8")]
+    pred = open(os.path.join(REF, "predict.rs")).read()
+    t = pred[pred.index("fn pred_matches_u8"):pred.index("fn pred_max")]
+    arrays = re.findall(r"\[((?:\s*\d+\s*,?)+)\s*\]", t)
+    nums = [[int(x) for x in re.findall(r"\d+", a)] for a in arrays]
+    lists16 = [a for a in nums if len(a) == 16]
+    angles = next(a for a in nums if len(a) == 27)
+    # order of appearance: V, H, Paeth, smooth, smooth_h, smooth_v, then 27 directional rows
+    names = ["V_PRED", "H_PRED", "PAETH_PRED", "SMOOTH_PRED", "SMOOTH_H_PRED", "SMOOTH_V_PRED"]
+    fixed = dict(zip(names, lists16[:6]))
+    directional = lists16[6:6 + 27]
+    assert len(directional) == 27
+    consts = dict(zip(["DC_PRED", "DC_TOP", "DC_LEFT", "DC_128"],
+                      [int(x) for x in re.findall(r"\[(\d+)u8; 16\]", t)]))
+    cdef = open(os.path.join(REF, "cdef.rs")).read()
+    c = cdef[cdef.index("fn check_max_element"):]
+    fme = [{"input": [int(x) for x in re.findall(r"-?\d+", inp)], "expect": [int(i), int(v)]}
+           for inp, i, v in re.findall(r"first_max_element\(&\[([^\]]+)\]\),\s*\((\d+),\s*(-?\d+)\)", c)]
+    out = {
+        "source": "xiph/rav1e @ 564ae3b, extracted by tests/golden/make_golden.py",
+        "dist_pattern": {"org": "(x + y + 24) & 255", "ref": "(x - y + 8) & 255", "block_at": [32, 40],
+                         "derivation": "src/dist.rs:384-413 (xpad/ypad 136 and 264; alignment terms cancel)"},
+        "sad": triples(sad_part), "satd": triples(satd_part),
+        "intra_4x4_edge": "edge_buf[i] = max(0, i + 32 - 128), i in 0..257 (predict.rs:1516-1517)",
+        "intra_4x4_const": consts, "intra_4x4": fixed,
+        "directional_angles": angles, "directional_4x4": directional,
+        "first_max_element": fme,
+    }
+    assert len(out["sad"]) == 22 and len(out["satd"]) == 22 and len(fme) == 3
+    with open(OUT, "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote", OUT)
+
+
+if __name__ == "__main__":
+    main()
