@@ -212,46 +212,79 @@ def run_b200(args, rank, world, local_rank):
             q.stride, q.width, q.height, q.pad, q.bpp, q.alloc = p.stride, W, H, PAD, 1, None
             pr.append(q)
         planes.append(pr)
-    sad_lists, satd_lists = [], []
+    # Descriptors of all F frame pairs, concatenated pair after pair (b200_me_candidates_multi_dev
+    # layout: global block indices, one CSR over all blocks).  P pairs go into one launch.
+    P = max(1, min(args.pairs_per_launch, F))
+    sad_np, satd_np = [], []
     for f in range(F):
         c, offs = cand_list(nb, CAND_SAD, 7 * f + 1 + 100000 * rank)
-        sad_lists.append(torch.from_numpy(c.view(np.uint8)).cuda())
+        c["block"] += f * nb
+        sad_np.append(c)
         c2, offs2 = cand_list(nb, CAND_SATD, 7 * f + 2 + 100000 * rank)
-        satd_lists.append(torch.from_numpy(c2.view(np.uint8)).cuda())
-    d_offs = torch.from_numpy(offs.view(np.uint8)).cuda()
-    d_offs2 = torch.from_numpy(offs2.view(np.uint8)).cuda()
+        c2["block"] += f * nb
+        satd_np.append(c2)
     n_sad, n_satd = nb * CAND_SAD, nb * CAND_SATD
+    d_sad_c = torch.from_numpy(np.concatenate(sad_np).view(np.uint8)).cuda()
+    d_satd_c = torch.from_numpy(np.concatenate(satd_np).view(np.uint8)).cuda()
+    del sad_np, satd_np
+    d_blocks_all = torch.from_numpy(np.tile(blocks, F).view(np.uint8)).cuda()
+    d_offs = torch.from_numpy((np.arange(F * nb + 1, dtype=np.uint64) * CAND_SAD).astype(np.uint32).view(np.uint8)).cuda()
+    d_offs2 = torch.from_numpy((np.arange(F * nb + 1, dtype=np.uint64) * CAND_SATD).astype(np.uint32).view(np.uint8)).cuda()
     d_sad = torch.empty(F * n_sad * 4, dtype=torch.uint8, device="cuda")
     d_satd = torch.empty(F * n_satd * 4, dtype=torch.uint8, device="cuda")
     d_best = torch.empty(F * nb * 16, dtype=torch.uint8, device="cuda")
     d_best2 = torch.empty(F * nb * 16, dtype=torch.uint8, device="cuda")
+    d_coef = torch.empty(F * nb * BW * BH, dtype=torch.int16, device="cuda")
     gathered = torch.empty(world * F * nb * 16, dtype=torch.uint8, device="cuda") if world > 1 else None
     p_sad = B.me_params(BW, BH, W, H, LAMBDA, window_hint_px=MV_RANGE_PX)
     p_satd = B.me_params(BW, BH, W, H, LAMBDA, use_satd=True, window_hint_px=MV_RANGE_PX)
+    # launch groups: frames [f0, f1) -> one call of each leg.  Offsets/cands keep global block
+    # indices, so a group passes the concatenated arrays from its first block / candidate on with
+    # indices rebased by the library's pair table (block_end / cand_end are relative to the group).
+    groups = []
+    for f0 in range(0, F, P):
+        f1 = min(F, f0 + P)
+        k = f1 - f0
+        pairs_sad = B.PlanePairs([planes[f][0] for f in range(f0, f1)], [planes[f][1] for f in range(f0, f1)],
+                                 [(i + 1) * nb for i in range(k)], [(i + 1) * n_sad for i in range(k)])
+        pairs_satd = B.PlanePairs([planes[f][0] for f in range(f0, f1)], [planes[f][1] for f in range(f0, f1)],
+                                  [(i + 1) * nb for i in range(k)], [(i + 1) * n_satd for i in range(k)])
+        groups.append((f0, k, pairs_sad, pairs_satd))
+    # per-group descriptor views: candidates of group g carry block indices relative to the group
+    if P < F:
+        for f in range(F):
+            base = (f // P) * P * nb
+            if base:
+                v = d_sad_c[f * n_sad * 8:(f + 1) * n_sad * 8].view(torch.int32).view(-1, 2)
+                v[:, 0] -= base
+                v2 = d_satd_c[f * n_satd * 8:(f + 1) * n_satd * 8].view(torch.int32).view(-1, 2)
+                v2[:, 0] -= base
+    d_offs_g = d_offs[:(P * nb + 1) * 4]        # identical for every group (uniform list lengths)
+    d_offs2_g = d_offs2[:(P * nb + 1) * 4]
 
-    def sad_launch(f):
-        cur, ref = planes[f]
-        ctx.me_candidates_dev(cur, ref, d_blocks, nb, sad_lists[f], n_sad, p_sad, d_offs, None,
-                              d_sad[f * n_sad * 4:], None, d_best[f * nb * 16:])
+    def sad_launch(g):
+        f0, k, ps, _ = groups[g]
+        ctx.me_candidates_multi_dev(ps, d_blocks_all, k * nb, d_sad_c[f0 * n_sad * 8:], k * n_sad, p_sad,
+                                    d_offs_g, None, d_sad[f0 * n_sad * 4:], None, d_best[f0 * nb * 16:])
 
-    def satd_launch(f):
-        cur, ref = planes[f]
-        ctx.me_candidates_dev(cur, ref, d_blocks, nb, satd_lists[f], n_satd, p_satd, d_offs2, None,
-                              d_satd[f * n_satd * 4:], None, d_best2[f * nb * 16:])
+    def satd_launch(g):
+        f0, k, _, ps = groups[g]
+        ctx.me_candidates_multi_dev(ps, d_blocks_all, k * nb, d_satd_c[f0 * n_satd * 8:], k * n_satd, p_satd,
+                                    d_offs2_g, None, d_satd[f0 * n_satd * 4:], None, d_best2[f0 * nb * 16:])
 
-    d_coef = torch.empty(F * nb * BW * BH, dtype=torch.int16, device="cuda")
-
-    def txfm_launch(f):
-        cur, ref = planes[f]
+    def txfm_launch(g):
+        f0, k, ps, _ = groups[g]
         # fused diff + TX_16X16 DCT_DCT (8-bit -> i16 coefficients) of the SAD winners
-        ctx.fwd_txfm_residual_dev(cur, ref, d_blocks, nb, d_best[f * nb * 16:],
-                                  d_coef[f * nb * BW * BH:], 2, 0, 8)
+        ctx.fwd_txfm_residual_multi_dev(ps, d_blocks_all, k * nb, d_best[f0 * nb * 16:],
+                                        d_coef[f0 * nb * BW * BH:], 2, 0, 8)
+
+    NG = len(groups)
 
     def step():
-        for f in range(F):
-            sad_launch(f)
-            satd_launch(f)
-            txfm_launch(f)
+        for g in range(NG):
+            sad_launch(g)
+            satd_launch(g)
+            txfm_launch(g)
         if world > 1:   # per-tile/frame winners to every rank (the entropy-coder owner)
             dist.all_gather_into_tensor(gathered, d_best)
 
@@ -287,22 +320,22 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- roofline of the dominant kernel (candidate-list SAD), timed alone on the same stream
     def sad_only():
-        for f in range(F):
-            sad_launch(f)
+        for g in range(NG):
+            sad_launch(g)
 
     def satd_only():
-        for f in range(F):
-            satd_launch(f)
+        for g in range(NG):
+            satd_launch(g)
     sad_only()
-    ms_sad = timed(sad_only, args.steps) / (args.steps * F)      # ms per launch
+    ms_sad = timed(sad_only, args.steps) / (args.steps * NG)      # ms per launch
     satd_only()
-    ms_satd = timed(satd_only, args.steps) / (args.steps * F)
+    ms_satd = timed(satd_only, args.steps) / (args.steps * NG)
 
     def txfm_only():
-        for f in range(F):
-            txfm_launch(f)
+        for g in range(NG):
+            txfm_launch(g)
     txfm_only()
-    ms_txfm = timed(txfm_only, args.steps) / (args.steps * F)
+    ms_txfm = timed(txfm_only, args.steps) / (args.steps * NG)
     # ---- extra leg (not part of `value`): the exhaustive grid full_pixel_me falls back to at
     # speed <= 5 (me.rs:822-846): +-192 x +-64 px, step 4 => up to 97 x 33 = 3201 positions/block
     d_fs = torch.empty(nb * 16, dtype=torch.uint8, device="cuda")
@@ -326,7 +359,9 @@ def run_b200(args, rank, world, local_rank):
     nyp = (np.minimum(64, tdiv(mvy_max, 8)) - np.maximum(-64, tdiv(mvy_min, 8))) // 4 + 1
     fs_positions = int((nxp * nyp).sum())
 
-    alg_bytes = n_sad * (BW * BH + 4) + nb * BW * BH             # 260 B/cand + 256 B/block
+    pairs_per_launch = F / NG
+    # 260 B/cand + 256 B/block, x the frame pairs one launch covers
+    alg_bytes = int((n_sad * (BW * BH + 4) + nb * BW * BH) * pairs_per_launch)
     peak, peak_src = peaks()
     achieved = alg_bytes / (ms_sad * 1e-3) / 1e9
     traffic = None
@@ -351,6 +386,7 @@ def run_b200(args, rank, world, local_rank):
                                 "satd_candidates_per_block": CAND_SATD,
                                 "fwd_txfm_per_block": "1 x TX_16X16 DCT_DCT of the SAD winner's residual"},
                        "mv_range_px": MV_RANGE_PX, "lambda": LAMBDA,
+                       "frame_pairs_per_launch": pairs_per_launch,
                        "l2": "inputs>L2 (planes %.0f MB + descriptors %.0f MB per GPU)" % (
                            F * 2 * (W + 2 * PAD) * (H + 2 * PAD) / 1e6, F * (n_sad + n_satd) * 8 / 1e6),
                        "parallelism": f"frames sharded over {world} GPU(s); all-gather of winners"
@@ -503,6 +539,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU)
+    ap.add_argument("--pairs-per-launch", type=int, default=32,
+                    help="frame pairs served by one launch of each leg (b200_*_multi_dev); 1 = a launch per pair")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

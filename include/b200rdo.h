@@ -161,6 +161,23 @@ int b200_me_candidates_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plan
                            const b200_me_params *params, uint32_t *d_sad, uint64_t *d_cost,
                            b200_me_result *d_best);
 
+/* The same over `npairs` (cur, ref) plane pairs in ONE launch — the reference evaluates every
+ * allowed reference frame of every superblock in turn (estimate_tile_motion, me.rs:178-212) and
+ * runs tiles and frames concurrently; a 30 us launch per pair leaves a B200 mostly ramping up and
+ * draining, so the pairs share a grid.  Blocks, candidates, offsets, pmv and the outputs are the
+ * concatenation pair after pair: pair k owns blocks [pair_block_end[k-1], pair_block_end[k]) and
+ * candidates [pair_cand_end[k-1], pair_cand_end[k]) (HOST arrays, npairs entries; the last entries
+ * equal nblocks / ncands); b200_cand.block and d_cand_offsets index the concatenated arrays.
+ * curs/refs: HOST arrays of npairs plane descriptors sharing bpp and the frame size in `params`.
+ * Results are identical to npairs calls of b200_me_candidates_dev. */
+int b200_me_candidates_multi_dev(b200_ctx *ctx, size_t npairs, const b200_plane *curs,
+                                 const b200_plane *refs, const uint32_t *pair_block_end,
+                                 const uint32_t *pair_cand_end, const b200_block *d_blocks,
+                                 size_t nblocks, const b200_cand *d_cands, size_t ncands,
+                                 const uint32_t *d_cand_offsets, const int16_t *d_pmv,
+                                 const b200_me_params *params, uint32_t *d_sad, uint64_t *d_cost,
+                                 b200_me_result *d_best);
+
 /* get_subpel_mv_rd (me.rs:1411-1442) over a candidate list of SUB-PEL vectors: each candidate is
  * predicted with the 8-tap filter `filter_mode` (fi.default_filter; predict_inter_single,
  * predict.rs:304-336) and measured with SAD or SATD against the source block — the unit of work
@@ -244,6 +261,14 @@ int b200_fwd_txfm_residual_dev(b200_ctx *ctx, const b200_plane *cur, const b200_
                                const b200_block *d_blocks, size_t nblocks,
                                const b200_me_result *d_mv_src, void *d_output, int tx_size,
                                int tx_type, int bd);
+/* The same over `npairs` plane pairs in one launch; pair k owns blocks
+ * [pair_block_end[k-1], pair_block_end[k]) (HOST array) of the concatenated d_blocks / d_mv_src /
+ * d_output, as in b200_me_candidates_multi_dev. */
+int b200_fwd_txfm_residual_multi_dev(b200_ctx *ctx, size_t npairs, const b200_plane *curs,
+                                     const b200_plane *refs, const uint32_t *pair_block_end,
+                                     const b200_block *d_blocks, size_t nblocks,
+                                     const b200_me_result *d_mv_src, void *d_output, int tx_size,
+                                     int tx_type, int bd);
 /* Fused residual + transform with resident planes and HOST descriptors / outputs. */
 int b200_fwd_txfm_residual_resident(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
                                     const b200_block *blocks, size_t nblocks,

@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libb200rdo.so")
+# B200RDO_LIB: load another build of the same ABI (kernel experiments, packaging)
+LIB_PATH = os.environ.get("B200RDO_LIB") or os.path.join(PKG, "libb200rdo.so")
 _LIB = None
 
 OK, ERR_CUDA, ERR_ARG, ERR_NODEV, ERR_OOM = range(5)
@@ -51,6 +52,22 @@ ME_RESULT_DTYPE = np.dtype(
 BLOCK_SIZES = [(4, 4), (4, 8), (4, 16), (8, 4), (8, 8), (8, 16), (8, 32), (16, 4), (16, 8),
                (16, 16), (16, 32), (16, 64), (32, 8), (32, 16), (32, 32), (32, 64), (64, 16),
                (64, 32), (64, 64), (64, 128), (128, 64), (128, 128)]
+
+
+class PlanePairs:
+    """Host-side table for b200_me_candidates_multi_dev: plane descriptors of each (cur, ref) pair
+    and the running ends of each pair's blocks / candidates in the concatenated arrays."""
+
+    def __init__(self, curs, refs, block_end, cand_end):
+        self.n = len(curs)
+        assert len(refs) == self.n and len(block_end) == self.n and len(cand_end) == self.n
+        self.curs = (Plane * self.n)()
+        self.refs = (Plane * self.n)()
+        for k in range(self.n):
+            C.memmove(C.byref(self.curs[k]), C.byref(curs[k]), C.sizeof(Plane))
+            C.memmove(C.byref(self.refs[k]), C.byref(refs[k]), C.sizeof(Plane))
+        self.block_end = np.ascontiguousarray(block_end, np.uint32)
+        self.cand_end = np.ascontiguousarray(cand_end, np.uint32)
 
 
 def lib():
@@ -102,6 +119,7 @@ def lib():
             f.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t] + extra
             f.restype = u32
     L.b200_me_candidates_dev.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
+    L.b200_me_candidates_multi_dev.argtypes = [vp, sz, vp, vp, vp, vp, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
     L.b200_me_subpel_candidates_dev.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, i32, vp, vp, vp]
     L.b200_me_full_search_dev.argtypes = [vp, pp, pp, vp, sz, pmp, i32, i32, i32, vp]
     L.b200_block_residual_dev.argtypes = [vp, pp, pp, vp, sz, vp, i32, i32, vp]
@@ -116,6 +134,7 @@ def lib():
     L.b200_forward_transform.restype = None
     L.b200_fwd_txfm_dev.argtypes = [vp, vp, sz, sz, vp, sz, i32, i32, i32, i32]
     L.b200_fwd_txfm_residual_dev.argtypes = [vp, pp, pp, vp, sz, vp, vp, i32, i32, i32]
+    L.b200_fwd_txfm_residual_multi_dev.argtypes = [vp, sz, vp, vp, vp, vp, sz, vp, vp, i32, i32, i32]
     L.b200_fwd_txfm_pred_dev.argtypes = [vp, pp, vp, vp, sz, vp, i32, i32, i32]
     L.b200_fwd_txfm_batch.argtypes = [vp, vp, sz, sz, vp, sz, i32, i32, i32, i32]
     L.b200_put_8tap.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t] + [i32] * 7
@@ -202,6 +221,15 @@ class Context:
             ncands, _dev_ptr(d_offsets), _dev_ptr(d_pmv), C.byref(params), _dev_ptr(d_sad),
             _dev_ptr(d_cost), _dev_ptr(d_best)))
 
+    def me_candidates_multi_dev(self, pairs, d_blocks, nblocks, d_cands, ncands, params,
+                                d_offsets=None, d_pmv=None, d_sad=None, d_cost=None, d_best=None):
+        """One launch over several (cur, ref) plane pairs (`pairs`: a PlanePairs)."""
+        self.check(self.L.b200_me_candidates_multi_dev(
+            self.h, pairs.n, C.addressof(pairs.curs), C.addressof(pairs.refs),
+            pairs.block_end.ctypes.data, pairs.cand_end.ctypes.data,
+            _dev_ptr(d_blocks), nblocks, _dev_ptr(d_cands), ncands, _dev_ptr(d_offsets),
+            _dev_ptr(d_pmv), C.byref(params), _dev_ptr(d_sad), _dev_ptr(d_cost), _dev_ptr(d_best)))
+
     def me_subpel_candidates_dev(self, cur, ref, d_blocks, nblocks, d_cands, ncands, params, filter_mode=0,
                                  d_offsets=None, d_pmv=None, d_sad=None, d_cost=None, d_best=None):
         self.check(self.L.b200_me_subpel_candidates_dev(
@@ -261,6 +289,12 @@ class Context:
         self.check(self.L.b200_fwd_txfm_residual_dev(self.h, C.byref(cur), C.byref(ref),
                                                      _dev_ptr(d_blocks), nblocks, _dev_ptr(d_mv_src),
                                                      _dev_ptr(d_out), tx_size, tx_type, bd))
+
+    def fwd_txfm_residual_multi_dev(self, pairs, d_blocks, nblocks, d_mv_src, d_out, tx_size, tx_type, bd):
+        self.check(self.L.b200_fwd_txfm_residual_multi_dev(
+            self.h, pairs.n, C.addressof(pairs.curs), C.addressof(pairs.refs),
+            pairs.block_end.ctypes.data, _dev_ptr(d_blocks), nblocks, _dev_ptr(d_mv_src),
+            _dev_ptr(d_out), tx_size, tx_type, bd))
 
     def fwd_txfm_pred_dev(self, cur, d_pred, d_blocks, nblocks, d_out, tx_size, tx_type, bd):
         self.check(self.L.b200_fwd_txfm_pred_dev(self.h, C.byref(cur), _dev_ptr(d_pred), _dev_ptr(d_blocks),

@@ -54,10 +54,21 @@ bool valid_transform(int tx_size, int tx_type) {
   return true;
 }
 
+// Several (cur, ref) plane pairs per launch (see b200_me_candidates_multi_dev): pair k owns
+// blocks [block_end[k-1], block_end[k]) of the launch.
+constexpr int kTxMaxPairs = 32;
+struct TxPairs {
+  int n;  // <= 1: TxArgs::cur / ref
+  uint32_t block_end[kTxMaxPairs];
+  const void *cur[kTxMaxPairs], *ref[kTxMaxPairs];
+  int cur_stride[kTxMaxPairs], ref_stride[kTxMaxPairs];
+};
+
 struct TxArgs {
   // fused residual source (PLANES variants): cur - ref displaced by the full-pel winner mv
   const void *cur, *ref;
   int cur_stride, ref_stride;
+  TxPairs pr;
   const b200_block *blocks;
   const b200_me_result *mv_src;
   const void *pred_packed;  // PLANES variants: prediction given as packed W x H blocks instead of a plane
@@ -100,7 +111,7 @@ __device__ __forceinline__ void run_1d(int type, TXV (&c)[N]) {
 constexpr int kTxThreads = 128;
 
 template <int W, int H, typename CoefT, bool PLANES>
-__global__ void __launch_bounds__(kTxThreads) fwd_txfm_kernel(TxArgs a) {
+__global__ void __launch_bounds__(kTxThreads) fwd_txfm_kernel(const __grid_constant__ TxArgs a) {
   constexpr int T = W > H ? W : H;       // threads per block-transform
   constexpr int PER = kTxThreads / T;    // transforms in flight per CTA
   constexpr int PITCH = W + 1;           // padded row pitch: conflict-free transposition
@@ -125,20 +136,34 @@ __global__ void __launch_bounds__(kTxThreads) fwd_txfm_kernel(TxArgs a) {
           dx = a.mv_src[blk].mv_col / 8;
           dy = a.mv_src[blk].mv_row / 8;
         }
-        const Px *pc = (const Px *)a.cur + (long long)b.y * a.cur_stride + b.x + t;
+        const void *cur_p = a.cur, *ref_p = a.ref;
+        int cur_stride = a.cur_stride, ref_stride = a.ref_stride;
+        if (a.pr.n > 1) {  // first pair whose block range holds blk
+          int lo = 0, hi = a.pr.n - 1;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((uint32_t)blk < a.pr.block_end[mid])
+              hi = mid;
+            else
+              lo = mid + 1;
+          }
+          cur_p = a.pr.cur[lo], ref_p = a.pr.ref[lo];
+          cur_stride = a.pr.cur_stride[lo], ref_stride = a.pr.ref_stride[lo];
+        }
+        const Px *pc = (const Px *)cur_p + (long long)b.y * cur_stride + b.x + t;
         const Px *pr;
         long long rstride;
         if (a.pred_packed) {
           pr = (const Px *)a.pred_packed + blk * (size_t)(W * H) + t;
           rstride = W;
         } else {
-          pr = (const Px *)a.ref + (long long)(b.y + dy) * a.ref_stride + b.x + dx + t;
-          rstride = a.ref_stride;
+          pr = (const Px *)ref_p + (long long)(b.y + dy) * ref_stride + b.x + dx + t;
+          rstride = ref_stride;
         }
 #pragma unroll
         for (int r = 0; r < H; r++) {
           const int rr = a.ud_flip ? H - 1 - r : r;
-          c[r] = round_shift_bit((int)pc[(long long)rr * a.cur_stride] - (int)pr[rr * rstride], a.bit0);
+          c[r] = round_shift_bit((int)pc[(long long)rr * cur_stride] - (int)pr[rr * rstride], a.bit0);
         }
       } else {
         const int16_t *src = a.in + blk * a.in_block_stride + t;
@@ -199,7 +224,7 @@ extern "C" int b200_tx_width(int tx_size) { return tx_size >= 0 && tx_size < 19 
 extern "C" int b200_tx_height(int tx_size) { return tx_size >= 0 && tx_size < 19 ? kTxH[tx_size] : 0; }
 
 static int fwd_txfm_impl(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
-                         const void *d_pred_packed, const b200_block *d_blocks,
+                         const TxPairs *pairs, const void *d_pred_packed, const b200_block *d_blocks,
                          const b200_me_result *d_mv_src,
                          const int16_t *d_input, size_t in_block_stride, size_t in_row_stride,
                          void *d_output, size_t nblocks, int tx_size, int tx_type, int bd,
@@ -227,6 +252,10 @@ static int fwd_txfm_impl(b200_ctx *ctx, const b200_plane *cur, const b200_plane 
   a.ref = ref ? ref->data : nullptr;
   a.cur_stride = cur ? cur->stride : 0;
   a.ref_stride = ref ? ref->stride : 0;
+  if (pairs)
+    a.pr = *pairs;
+  else
+    a.pr.n = 0;
   a.blocks = d_blocks;
   a.mv_src = d_mv_src;
   a.pred_packed = d_pred_packed;
@@ -275,7 +304,7 @@ extern "C" int b200_fwd_txfm_dev(b200_ctx *ctx, const int16_t *d_input, size_t i
                                  int tx_type, int bd, int coeff_is_i32) {
   B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
   B200_REQUIRE(ctx, d_input || nblocks == 0, "NULL input");
-  return fwd_txfm_impl(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, d_input, in_block_stride,
+  return fwd_txfm_impl(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, d_input, in_block_stride,
                        in_row_stride, d_output, nblocks, tx_size, tx_type, bd, coeff_is_i32);
 }
 
@@ -290,8 +319,53 @@ extern "C" int b200_fwd_txfm_residual_dev(b200_ctx *ctx, const b200_plane *cur,
   B200_REQUIRE(ctx, cur && ref && cur->data && ref->data && cur->bpp == ref->bpp, "bad planes");
   B200_REQUIRE(ctx, (cur->bpp == 1) == (bd == 8), "bpp %d does not match bit depth %d", cur->bpp, bd);
   B200_REQUIRE(ctx, d_blocks || nblocks == 0, "NULL blocks");
-  return fwd_txfm_impl(ctx, cur, ref, nullptr, d_blocks, d_mv_src, nullptr, 0, 0, d_output, nblocks,
-                       tx_size, tx_type, bd, cur->bpp == 2);
+  return fwd_txfm_impl(ctx, cur, ref, nullptr, nullptr, d_blocks, d_mv_src, nullptr, 0, 0, d_output,
+                       nblocks, tx_size, tx_type, bd, cur->bpp == 2);
+}
+
+// The fused residual + transform over several plane pairs in one launch (block ranges as in
+// b200_me_candidates_multi_dev; d_mv_src / d_output follow the concatenated block order).
+extern "C" int b200_fwd_txfm_residual_multi_dev(b200_ctx *ctx, size_t npairs, const b200_plane *curs,
+                                                const b200_plane *refs, const uint32_t *pair_block_end,
+                                                const b200_block *d_blocks, size_t nblocks,
+                                                const b200_me_result *d_mv_src, void *d_output,
+                                                int tx_size, int tx_type, int bd) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  B200_REQUIRE(ctx, npairs >= 1 && curs && refs && pair_block_end, "NULL plane pair table");
+  B200_REQUIRE(ctx, valid_transform(tx_size, tx_type), "invalid transform: tx_size %d tx_type %d",
+               tx_size, tx_type);
+  B200_REQUIRE(ctx, d_blocks || nblocks == 0, "NULL blocks");
+  B200_REQUIRE(ctx, pair_block_end[npairs - 1] == nblocks && nblocks < (1ull << 32),
+               "last pair must end at nblocks");
+  for (size_t k = 0; k < npairs; k++) {
+    B200_REQUIRE(ctx, curs[k].data && refs[k].data && curs[k].bpp == refs[k].bpp &&
+                          curs[k].bpp == curs[0].bpp, "pair %zu: bad planes", k);
+    B200_REQUIRE(ctx, pair_block_end[k] >= (k ? pair_block_end[k - 1] : 0),
+                 "pair %zu: block ends must be non-decreasing", k);
+  }
+  B200_REQUIRE(ctx, (curs[0].bpp == 1) == (bd == 8), "bpp %d does not match bit depth %d", curs[0].bpp, bd);
+  const size_t coef_bytes = (size_t)kTxW[tx_size] * kTxH[tx_size] * (curs[0].bpp == 2 ? 4 : 2);
+  for (size_t k0 = 0; k0 < npairs; k0 += kTxMaxPairs) {
+    const int n = (int)std::min<size_t>(kTxMaxPairs, npairs - k0);
+    const uint32_t b0 = k0 ? pair_block_end[k0 - 1] : 0;
+    TxPairs t;
+    t.n = n;
+    for (int k = 0; k < n; k++) {
+      t.block_end[k] = pair_block_end[k0 + k] - b0;
+      t.cur[k] = curs[k0 + k].data;
+      t.ref[k] = refs[k0 + k].data;
+      t.cur_stride[k] = curs[k0 + k].stride;
+      t.ref_stride[k] = refs[k0 + k].stride;
+    }
+    const size_t nb = t.block_end[n - 1];
+    if (nb == 0) continue;
+    if (int st = fwd_txfm_impl(ctx, &curs[k0], &refs[k0], &t, nullptr, d_blocks + b0,
+                               d_mv_src ? d_mv_src + b0 : nullptr, nullptr, 0, 0,
+                               (uint8_t *)d_output + (size_t)b0 * coef_bytes, nb, tx_size, tx_type, bd,
+                               curs[0].bpp == 2))
+      return st;
+  }
+  return B200_OK;
 }
 
 // Residual against PACKED predictions (the output layout of b200_mc_blocks_dev /
@@ -305,7 +379,7 @@ extern "C" int b200_fwd_txfm_pred_dev(b200_ctx *ctx, const b200_plane *cur, cons
   B200_REQUIRE(ctx, cur && cur->data && d_pred, "bad plane / prediction");
   B200_REQUIRE(ctx, (cur->bpp == 1) == (bd == 8), "bpp %d does not match bit depth %d", cur->bpp, bd);
   B200_REQUIRE(ctx, d_blocks || nblocks == 0, "NULL blocks");
-  return fwd_txfm_impl(ctx, cur, cur, d_pred, d_blocks, nullptr, nullptr, 0, 0, d_output, nblocks,
+  return fwd_txfm_impl(ctx, cur, cur, nullptr, d_pred, d_blocks, nullptr, nullptr, 0, 0, d_output, nblocks,
                        tx_size, tx_type, bd, cur->bpp == 2);
 }
 

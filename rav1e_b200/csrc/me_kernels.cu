@@ -22,6 +22,12 @@
 
 #include "common.cuh"
 
+#ifndef B200_SAD16_MINBLOCKS
+// Resident CTAs per SM the 16x16 SAD kernel is register-capped for: 4 (64 registers, no spills)
+// measured 0.850 ms per 32-pair launch against 0.931 ms at 5 (48 registers, 66 B of spills).
+#define B200_SAD16_MINBLOCKS 4
+#endif
+
 namespace {
 
 constexpr unsigned long long kEmptyCost = ~0ull;  // MVCandidateRD::empty(), me.rs:139-146
@@ -37,8 +43,34 @@ __device__ __forceinline__ const T *px(const PlaneView &p, int x, int y) {
   return (const T *)p.data + (long long)y * p.stride + x;
 }
 
+// Several (cur, ref) plane pairs served by one launch (me.rs:178-212 walks every allowed reference
+// frame of every superblock; tiles and frames in flight add more): blocks, candidates and outputs
+// are concatenated pair after pair, the table maps a block / group index back to its planes.
+// Lives in the kernel parameters (constant bank, uniform lookups).
+constexpr int kMaxPairs = 32;
+struct MePairs {
+  int n;
+  uint32_t block_begin;            // first block of pair 0
+  uint32_t block_end[kMaxPairs];   // pair k owns blocks [block_end[k-1], block_end[k])
+  uint32_t group_end[kMaxPairs];   // grouped kernel: likewise for its groups (from 0)
+  PlaneView cur[kMaxPairs], ref[kMaxPairs];
+};
+
+// first k with v < ends[k] (v < ends[n-1] is the caller's invariant)
+__device__ __forceinline__ int pair_lookup(const uint32_t *ends, int n, uint32_t v) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (v < ends[mid])
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  return lo;
+}
+
 struct MeArgs {
-  PlaneView cur, ref;
+  PlaneView cur, ref;  // == pr.cur[0] / pr.ref[0]; the only planes the generic kernels read
   const b200_block *blocks;
   const b200_cand *cands;
   const uint32_t *cand_offsets;  // CSR or null
@@ -55,6 +87,8 @@ struct MeArgs {
   int use_satd;
   int smem_bytes;  // dynamic smem given to the staged kernels
   size_t ngroups;  // ceil(nblocks / G) for the grouped kernel
+  int hint_px;     // caller's bound on |mv|/8 (0 = unknown)
+  MePairs pr;
 };
 
 // ---------------------------------------------------------------- Hadamard (dist.rs:55-149)
@@ -430,7 +464,8 @@ __device__ __forceinline__ unsigned long long pack_key(unsigned long long cost, 
 // shared atomicMin per warp.  Windows that do not fit fall back to one block per pass, and a
 // single block that still does not fit reads the reference plane directly.
 template <int W, int H, bool SATD>
-__global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, int G) {
+__global__ void __launch_bounds__(SATD ? 128 : 256, (!SATD && W >= 16 && W * H <= 256) ? B200_SAD16_MINBLOCKS : 1)
+    me_cand_group_u8(const __grid_constant__ MeArgs a, int G) {
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ int s_box[4];
   __shared__ unsigned long long s_key[kMaxGroup];
@@ -458,9 +493,17 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
   const size_t ngroups = a.ngroups;  // host-computed: no 64-bit division per thread
 
   for (size_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-    const size_t gb0 = grp * G, gb1 = min(gb0 + (size_t)G, a.nblocks);
+    int pi = 0;
+    uint32_t g0 = 0, pb0 = a.pr.block_begin;
+    if (a.pr.n > 1) {
+      pi = pair_lookup(a.pr.group_end, a.pr.n, (uint32_t)grp);
+      if (pi) g0 = a.pr.group_end[pi - 1], pb0 = a.pr.block_end[pi - 1];
+    }
+    const PlaneView cur = a.pr.cur[pi], ref = a.pr.ref[pi];
+    const size_t gb0 = pb0 + (grp - g0) * G, gb1 = min(gb0 + (size_t)G, (size_t)a.pr.block_end[pi]);
     // pass 0 tries the whole group; if its window does not fit, passes 1.. take one block each
     bool whole = true;
+    bool force_bbox = false;  // set when a hinted window turned out too small for the candidates
     size_t b0 = gb0, b1 = gb1;
     while (b0 < gb1) {
       const int nb = (int)(b1 - b0);
@@ -485,8 +528,34 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
       }
       __syncthreads();
       const uint32_t lo = s_off[0], hi = s_off[nb];
-      // ---- bounding box of the in-range candidates (reference coordinates of block top-left)
-      {
+      // ---- window extent.  With a search-range hint (cooperative path only) the window is the
+      // union of the group's blocks grown by the hint: no pass over the candidates, and staging
+      // can start right away; pass 1 verifies every candidate lies inside and the group falls
+      // back to the exact bounding box below if the hint was wrong.  Otherwise: bounding box of
+      // the in-range candidates (reference coordinates of the block top-left).
+      const bool hinted = COOP && a.hint_px > 0 && !force_bbox;
+      // hinted: the first round's candidate is fetched now, under the window staging
+      b200_cand pre;
+      pre.block = 0;
+      pre.mv_row = 0;
+      pre.mv_col = 0;
+      if (hinted && lo + threadIdx.x < hi) pre = a.cands[lo + threadIdx.x];
+      if (hinted) {
+        if (threadIdx.x == 0) {
+          int x0 = INT_MAX, x1 = INT_MIN, y0 = INT_MAX, y1 = INT_MIN;
+          for (int k = 0; k < nb; k++) {  // never beyond what get_mv_range allows (plane padding)
+            const MvRange r = s_rng[k];
+            x0 = min(x0, s_blk[k].x + max(-a.hint_px, r.x_min / 8));
+            x1 = max(x1, s_blk[k].x + min(a.hint_px, r.x_max / 8));
+            y0 = min(y0, s_blk[k].y + max(-a.hint_px, r.y_min / 8));
+            y1 = max(y1, s_blk[k].y + min(a.hint_px, r.y_max / 8));
+          }
+          s_box[0] = x0;
+          s_box[1] = x1;
+          s_box[2] = y0;
+          s_box[3] = y1;
+        }
+      } else {
         int bx0 = INT_MAX, bx1 = INT_MIN, by0 = INT_MAX, by1 = INT_MIN;
         for (uint32_t i = lo + threadIdx.x; i < hi; i += nthr) {
           const b200_cand c = a.cands[i];
@@ -511,7 +580,7 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
       __syncthreads();
       const bool have = s_box[0] != INT_MAX;
       // 16-byte aligned window origin whatever the alignment of pixel (0,0)
-      const int mis = (int)((uintptr_t)a.ref.data & 15);
+      const int mis = (int)((uintptr_t)ref.data & 15);
       const int wx0 = have ? (((s_box[0] + mis) & ~15) - mis) : 0;
       const int wy0 = have ? s_box[2] : 0;
       // +4 bytes: the funnel shift reads one word past the last pixel
@@ -525,6 +594,10 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
         pitch_words = (row_bytes >> 2) | 4;
       }
       const bool fits = (long long)rows * pitch_words * 4 <= (long long)win_bytes;
+      if (!fits && hinted) {  // the exact bounding box may still fit
+        force_bbox = true;
+        continue;
+      }
       if (!fits && nb > 1) {  // uniform: derived from shared state
         whole = false;
         b1 = b0 + 1;
@@ -536,12 +609,12 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
       const bool dense = (long long)(hi - lo) * (W * H) * 2 >= (long long)rows * row_bytes;
       const bool staged = have && fits && dense;
       if (staged)
-        stage_window(win, pitch_words, px<uint8_t>(a.ref, wx0, wy0), a.ref.stride, rows, row_bytes);
+        stage_window(win, pitch_words, px<uint8_t>(ref, wx0, wy0), ref.stride, rows, row_bytes);
       // org blocks -> packed words
       for (int i = threadIdx.x; i < nb * ORGW; i += nthr) {
         const int lb = i / ORGW, wi = i - lb * ORGW;
         const int y = wi / (W / 4), k = wi - y * (W / 4);
-        const uint8_t *p = px<uint8_t>(a.cur, s_blk[lb].x + 4 * k, s_blk[lb].y + y);
+        const uint8_t *p = px<uint8_t>(cur, s_blk[lb].x + 4 * k, s_blk[lb].y + y);
         uint32_t v;
         if (((uintptr_t)p & 3) == 0)
           v = __ldg((const uint32_t *)p);
@@ -566,10 +639,12 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
         const uint32_t lane_win = (uint32_t)(lrow * pitch_words + lword) * 4u;
         const uint32_t lane_org = (uint32_t)(lrow * (W / 4) + lword) * 4u;
         const uint32_t pstep = (uint32_t)(RPP * pitch_words) * 4u;
+        bool hint_failed = false;
         for (uint32_t base = lo; base < hi; base += nthr) {
           const uint32_t i = base + threadIdx.x;
           const bool valid = i < hi;
           bool inr = false;
+          int outside = 0;
           b200_cand cd;
           cd.block = 0;
           cd.mv_row = 0;
@@ -577,43 +652,83 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
           int lb = 0;
           uint4 par = make_uint4(win_s, org_s, 0u, 0u);
           if (valid) {
-            cd = a.cands[i];
+            cd = (hinted && base == lo) ? pre : a.cands[i];
             lb = (int)(cd.block - (uint32_t)b0);
             const MvRange r = s_rng[lb];
             inr = !(cd.mv_col < r.x_min || cd.mv_col > r.x_max || cd.mv_row < r.y_min ||
                     cd.mv_row > r.y_max);
             if (inr) {
               const int off = s_blk[lb].x + cd.mv_col / 8 - wx0;
-              par.x = win_s + (uint32_t)((s_blk[lb].y + cd.mv_row / 8 - wy0) * pitch_words + (off >> 2)) * 4u;
+              const int roff = s_blk[lb].y + cd.mv_row / 8 - wy0;
+              outside = off < 0 || off + W + 4 > row_bytes || roff < 0 || roff + H > rows;
+              par.x = win_s + (uint32_t)(roff * pitch_words + (off >> 2)) * 4u;
               par.y = org_s + (uint32_t)(lb * ORGW) * 4u;
               par.z = (uint32_t)(off & 3) * 8u;
             }
           }
-          __syncthreads();  // previous round's readers of s_par are done
+          // (also retires the previous round's readers of s_par)
+          if (hinted ? __syncthreads_or(outside) : (__syncthreads(), 0)) {
+            hint_failed = true;  // uniform
+            break;
+          }
           s_par[threadIdx.x] = par;
           __syncthreads();
           uint32_t sad = 0;
           const uint32_t par_s = smem_u32(s_par + warp * 32);
+          // When the warp's 32 candidates belong to one block (the usual case: lists are grouped
+          // by block) its org words are loaded into registers once instead of per candidate.
+          // (out-of-range / padding lanes are ignored: their result is discarded anyway)
+          const unsigned live = __ballot_sync(0xffffffffu, inr);
+          const uint32_t org0 = __shfl_sync(0xffffffffu, par.y, live ? __ffs(live) - 1 : 0);
+          const bool one_block = __all_sync(0xffffffffu, !inr || par.y == org0);
+          if (one_block) {
+            uint32_t orgr[P];
 #pragma unroll
-          for (int sidx = 0; sidx < 32; sidx++) {
-            uint32_t qa, qo, qs, qz;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(qa), "=r"(qo), "=r"(qs), "=r"(qz)
-                         : "r"(par_s + (uint32_t)sidx * 16u));
-            uint32_t wa = qa + lane_win;
-            const uint32_t oa = qo + lane_org;
-            uint32_t part = 0;
+            for (int p = 0; p < P; p++)
+              asm volatile("ld.shared.u32 %0, [%1];"
+                           : "=r"(orgr[p])
+                           : "r"(org0 + lane_org + (uint32_t)(p * RPP * (W / 4)) * 4u));
 #pragma unroll
-            for (int p = 0; p < P; p++) {
-              uint32_t w0, w1, o;
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(wa));
-              asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(wa));
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(o) : "r"(oa + (uint32_t)(p * RPP * (W / 4)) * 4u));
-              part = sad4_acc(__funnelshift_r(w0, w1, qs), o, part);
-              wa += pstep;
+            for (int sidx = 0; sidx < 32; sidx++) {
+              uint32_t qa, qo, qs, qz;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(qa), "=r"(qo), "=r"(qs), "=r"(qz)
+                           : "r"(par_s + (uint32_t)sidx * 16u));
+              uint32_t wa = qa + lane_win;
+              uint32_t part = 0;
+#pragma unroll
+              for (int p = 0; p < P; p++) {
+                uint32_t w0, w1;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(wa));
+                asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(wa));
+                part = sad4_acc(__funnelshift_r(w0, w1, qs), orgr[p], part);
+                wa += pstep;
+              }
+              const uint32_t tot = __reduce_add_sync(0xffffffffu, part);
+              if (lane == sidx) sad = tot;
             }
-            const uint32_t tot = __reduce_add_sync(0xffffffffu, part);
-            if (lane == sidx) sad = tot;
+          } else {
+#pragma unroll
+            for (int sidx = 0; sidx < 32; sidx++) {
+              uint32_t qa, qo, qs, qz;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(qa), "=r"(qo), "=r"(qs), "=r"(qz)
+                           : "r"(par_s + (uint32_t)sidx * 16u));
+              uint32_t wa = qa + lane_win;
+              const uint32_t oa = qo + lane_org;
+              uint32_t part = 0;
+#pragma unroll
+              for (int p = 0; p < P; p++) {
+                uint32_t w0, w1, o;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(wa));
+                asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(wa));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(o) : "r"(oa + (uint32_t)(p * RPP * (W / 4)) * 4u));
+                part = sad4_acc(__funnelshift_r(w0, w1, qs), o, part);
+                wa += pstep;
+              }
+              const uint32_t tot = __reduce_add_sync(0xffffffffu, part);
+              if (lane == sidx) sad = tot;
+            }
           }
           unsigned long long cost = kEmptyCost, key = ~0ull;
           if (inr) {
@@ -642,6 +757,10 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
               atomicMin(&s_key[lb], key);
             }
           }
+        }
+        if (hint_failed) {  // redo this pass with the exact bounding box (results are rewritten)
+          force_bbox = true;
+          continue;
         }
       } else {
       // ---- evaluate: each slot of TPC threads takes candidates lo+slot, lo+slot+nslots, ...
@@ -690,10 +809,10 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
             // not staged (sparse set, or a window too large for shared memory): the same word /
             // funnel-shift arithmetic straight from the plane through L1/L2.  Rows are word
             // addressed from a 4-byte aligned base (the row pitch is a multiple of 16 bytes).
-            const uint8_t *rp = px<uint8_t>(a.ref, rx, ry);
+            const uint8_t *rp = px<uint8_t>(ref, rx, ry);
             const int gsh = (int)((uintptr_t)rp & 3);
             const uint32_t *gw = (const uint32_t *)(rp - gsh);
-            const int gpitch = a.ref.stride >> 2;
+            const int gpitch = ref.stride >> 2;
             if (!SATD) {
 #pragma unroll 4
               for (int y = 0; y < H; y++)
@@ -774,6 +893,7 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
       if (whole) break;
       b0 = b1;
       b1 = b0 + 1;
+      force_bbox = false;
     }
   }
 }
@@ -786,7 +906,7 @@ __global__ void __launch_bounds__(SATD ? 128 : 256) me_cand_group_u8(MeArgs a, i
 // block, so org reads are broadcasts), cost + first-min argmin by REDUX over the packed key.  No
 // shared memory, no barriers.
 template <int W, int H, bool SATD>
-__global__ void __launch_bounds__(256) me_cand_warp_u8(MeArgs a) {
+__global__ void __launch_bounds__(256) me_cand_warp_u8(const __grid_constant__ MeArgs a) {
   constexpr int S = (W < 8 || H < 8) ? 4 : 8;
   constexpr int NCH = SATD ? (W / S) * (H / S) : 1;
   constexpr int TPC = NCH < 32 ? NCH : 32;
@@ -795,8 +915,11 @@ __global__ void __launch_bounds__(256) me_cand_warp_u8(MeArgs a) {
   const int slot = lane / TPC, sub = lane - slot * TPC;
   const size_t warp0 = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
-  const int cpitch = a.cur.stride >> 2, rpitch = a.ref.stride >> 2;
-  for (size_t blk = warp0; blk < a.nblocks; blk += nwarps) {
+  const size_t blk_end = a.pr.block_end[a.pr.n - 1];
+  for (size_t blk = a.pr.block_begin + warp0; blk < blk_end; blk += nwarps) {
+    const int pi = a.pr.n > 1 ? pair_lookup(a.pr.block_end, a.pr.n, (uint32_t)blk) : 0;
+    const PlaneView cur = a.pr.cur[pi], ref = a.pr.ref[pi];
+    const int cpitch = cur.stride >> 2, rpitch = ref.stride >> 2;
     const uint32_t lo = a.cand_offsets[blk], hi = a.cand_offsets[blk + 1];
     const b200_block b = a.blocks[blk];
     const MvRange r = b200_mv_range(a.w_in_b, a.h_in_b, b.x / MI_SIZE, b.y / MI_SIZE, W, H);
@@ -806,7 +929,7 @@ __global__ void __launch_bounds__(256) me_cand_warp_u8(MeArgs a) {
       p0r = p[0], p0c = p[1], p1r = p[2], p1c = p[3];
     }
     // org block: word-addressed from a 4-byte aligned base
-    const uint8_t *op = px<uint8_t>(a.cur, b.x, b.y);
+    const uint8_t *op = px<uint8_t>(cur, b.x, b.y);
     const int osh = (int)((uintptr_t)op & 3);
     const uint32_t *ow = (const uint32_t *)(op - osh);
     unsigned long long best = ~0ull;
@@ -822,7 +945,7 @@ __global__ void __launch_bounds__(256) me_cand_warp_u8(MeArgs a) {
                                   c.mv_row > r.y_max);
       uint32_t acc = 0;
       if (inr) {
-        const uint8_t *rp = px<uint8_t>(a.ref, b.x + c.mv_col / 8, b.y + c.mv_row / 8);
+        const uint8_t *rp = px<uint8_t>(ref, b.x + c.mv_col / 8, b.y + c.mv_row / 8);
         const int gsh = (int)((uintptr_t)rp & 3);
         const uint32_t *gw = (const uint32_t *)(rp - gsh);
         if (!SATD) {
@@ -1107,13 +1230,15 @@ int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px) {
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kCandSmemBytes);
   });
   B200_CUDA(ctx, attr_err);
+  bool cur_word_pitch = true;
+  for (int k = 0; k < a.pr.n; k++) cur_word_pitch = cur_word_pitch && (a.pr.cur[k].stride & 3) == 0;
   {
     // Sparse lists: when a block's candidates cover less than a quarter of the window the
     // grouped kernel would stage for it, take the warp-per-block kernel (no staging at all).
     const int hint0 = window_hint_px > 0 ? window_hint_px : 32;
     const double win_bytes = (double)(2 * hint0 + W) * (2 * hint0 + H);
     const double avg0 = a.nblocks ? (double)a.ncands / (double)a.nblocks : 0.0;
-    if (avg0 * W * H * 4 < win_bytes && (a.cur.stride & 3) == 0) {
+    if (avg0 * W * H * 4 < win_bytes && cur_word_pitch) {
       const int wpc = 8;
       const int grid = (int)std::min<size_t>((a.nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms * 16);
       me_cand_warp_u8<W, H, SATD><<<grid, wpc * 32, 0, ctx->stream>>>(a);
@@ -1146,8 +1271,16 @@ int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px) {
   size_t smem = pitch * 4 * (size_t)(2 * hint + H) + (size_t)G * W * H;
   smem = std::min<size_t>(std::max<size_t>(smem, 16 * 1024), (size_t)kCandSmemBytes);
   a.smem_bytes = (int)smem;
-  const size_t ngroups = (a.nblocks + G - 1) / G;
+  // groups never straddle a plane pair
+  size_t ngroups = 0;
+  uint32_t b0 = a.pr.block_begin;
+  for (int k = 0; k < a.pr.n; k++) {
+    ngroups += (a.pr.block_end[k] - b0 + G - 1) / G;
+    a.pr.group_end[k] = (uint32_t)ngroups;
+    b0 = a.pr.block_end[k];
+  }
   a.ngroups = ngroups;
+  if (ngroups == 0) return B200_OK;
   const int grid = (int)std::min<size_t>(ngroups, (size_t)ctx->num_sms * 32);
   me_cand_group_u8<W, H, SATD><<<grid, threads, smem, ctx->stream>>>(a, G);
   B200_LAUNCH_CHECK(ctx);
@@ -1188,24 +1321,39 @@ int check_planes(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
 
 }  // namespace
 
-extern "C" int b200_me_candidates_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
-                                      const b200_block *d_blocks, size_t nblocks,
-                                      const b200_cand *d_cands, size_t ncands,
-                                      const uint32_t *d_cand_offsets, const int16_t *d_pmv,
-                                      const b200_me_params *p, uint32_t *d_sad, uint64_t *d_cost,
-                                      b200_me_result *d_best) {
+namespace {
+
+// Candidate-list evaluation over `npairs` plane pairs.  Pair k owns blocks
+// [block_end[k-1], block_end[k]) and candidates [cand_end[k-1], cand_end[k]) of the concatenated
+// arrays (candidates carry global block indices).
+int me_candidates_pairs(b200_ctx *ctx, size_t npairs, const b200_plane *curs, const b200_plane *refs,
+                        const uint32_t *block_end, const uint32_t *cand_end,
+                        const b200_block *d_blocks, size_t nblocks, const b200_cand *d_cands,
+                        size_t ncands, const uint32_t *d_cand_offsets, const int16_t *d_pmv,
+                        const b200_me_params *p, uint32_t *d_sad, uint64_t *d_cost,
+                        b200_me_result *d_best) {
   B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
-  if (int st = check_planes(ctx, cur, ref, p)) return st;
+  B200_REQUIRE(ctx, npairs >= 1 && curs && refs && block_end && cand_end, "NULL plane pair table");
+  bool fast_planes = true;
+  for (size_t k = 0; k < npairs; k++) {
+    if (int st = check_planes(ctx, &curs[k], &refs[k], p)) return st;
+    B200_REQUIRE(ctx, curs[k].bpp == curs[0].bpp, "plane pairs must share bpp");
+    B200_REQUIRE(ctx, block_end[k] >= (k ? block_end[k - 1] : 0) && cand_end[k] >= (k ? cand_end[k - 1] : 0),
+                 "pair %zu: block/candidate ends must be non-decreasing", k);
+    fast_planes = fast_planes && (refs[k].stride & 15) == 0;
+  }
+  B200_REQUIRE(ctx, block_end[npairs - 1] == nblocks && cand_end[npairs - 1] == ncands,
+               "last pair must end at nblocks / ncands");
   B200_REQUIRE(ctx, d_best == nullptr || d_cand_offsets != nullptr,
                "d_best needs CSR d_cand_offsets (candidates grouped by block)");
-  B200_REQUIRE(ctx, ncands < (1ull << 32), "ncands must fit 32 bits");
+  B200_REQUIRE(ctx, ncands < (1ull << 32) && nblocks < (1ull << 32), "ncands / nblocks must fit 32 bits");
   if (ncands == 0 && (nblocks == 0 || !d_best)) return B200_OK;
   B200_REQUIRE(ctx, d_blocks && (d_cands || ncands == 0), "NULL blocks/cands");
   B200_CUDA(ctx, cudaSetDevice(ctx->device));
 
-  MeArgs a;
-  a.cur = {cur->data, cur->stride};
-  a.ref = {ref->data, ref->stride};
+  MeArgs a{};
+  a.cur = {curs[0].data, curs[0].stride};
+  a.ref = {refs[0].data, refs[0].stride};
   a.blocks = d_blocks;
   a.cands = d_cands;
   a.cand_offsets = d_cand_offsets;
@@ -1224,14 +1372,16 @@ extern "C" int b200_me_candidates_dev(b200_ctx *ctx, const b200_plane *cur, cons
   a.use_satd = p->use_satd;
   a.smem_bytes = 0;
   a.ngroups = 0;
+  a.hint_px = p->window_hint_px;
 
-  // Fast path: 8-bit, candidates grouped by block (CSR), block sizes up to 64x64.
-  if (cur->bpp == 1 && d_cand_offsets && nblocks > 0 && (ref->stride & 15) == 0 &&
+  // Fast path: 8-bit, candidates grouped by block (CSR), block sizes up to 64x64; kMaxPairs plane
+  // pairs per launch.
+  if (curs[0].bpp == 1 && d_cand_offsets && nblocks > 0 && fast_planes &&
       ncands <= (1ull << kKeyIdxBits)) {
-#define B200_CASE(W_, H_)                                                            \
-  if (p->w == W_ && p->h == H_)                                                      \
-    return p->use_satd ? launch_cand_group<W_, H_, true>(ctx, a, p->window_hint_px)  \
-                       : launch_cand_group<W_, H_, false>(ctx, a, p->window_hint_px);
+    int (*launch)(b200_ctx *, MeArgs, int) = nullptr;
+#define B200_CASE(W_, H_)            \
+  if (p->w == W_ && p->h == H_)      \
+    launch = p->use_satd ? launch_cand_group<W_, H_, true> : launch_cand_group<W_, H_, false>;
     B200_CASE(4, 4)
     B200_CASE(8, 8)
     B200_CASE(16, 16)
@@ -1246,9 +1396,27 @@ extern "C" int b200_me_candidates_dev(b200_ctx *ctx, const b200_plane *cur, cons
     B200_CASE(32, 64)
     B200_CASE(64, 32)
 #undef B200_CASE
+    if (launch) {
+      for (size_t k0 = 0; k0 < npairs; k0 += kMaxPairs) {
+        const int n = (int)std::min<size_t>(kMaxPairs, npairs - k0);
+        a.pr.n = n;
+        a.pr.block_begin = k0 ? block_end[k0 - 1] : 0;
+        for (int k = 0; k < n; k++) {
+          a.pr.block_end[k] = block_end[k0 + k];
+          a.pr.cur[k] = {curs[k0 + k].data, curs[k0 + k].stride};
+          a.pr.ref[k] = {refs[k0 + k].data, refs[k0 + k].stride};
+        }
+        // per-launch totals steer the kernel choice and the group size
+        a.nblocks = a.pr.block_end[n - 1] - a.pr.block_begin;
+        a.ncands = cand_end[k0 + n - 1] - (k0 ? cand_end[k0 - 1] : 0);
+        if (a.nblocks == 0) continue;
+        if (int st = launch(ctx, a, p->window_hint_px)) return st;
+      }
+      return B200_OK;
+    }
   }
 
-  // Generic path: per-candidate values, then (optionally) the segmented argmin.
+  // Generic path: per-candidate values pair by pair, then (optionally) the segmented argmin.
   unsigned long long *cost_buf = a.out_cost;
   uint32_t *sad_buf = a.out_sad;
   if (d_best && ncands) {
@@ -1265,13 +1433,19 @@ extern "C" int b200_me_candidates_dev(b200_ctx *ctx, const b200_plane *cur, cons
       if (!sad_buf) sad_buf = (uint32_t *)wsp;
     }
   }
-  if (ncands) {
-    a.out_cost = cost_buf;
-    a.out_sad = sad_buf;
+  for (size_t k = 0; k < npairs; k++) {
+    const size_t c0 = k ? cand_end[k - 1] : 0, c1 = cand_end[k];
+    if (c1 == c0) continue;
+    a.cur = {curs[k].data, curs[k].stride};
+    a.ref = {refs[k].data, refs[k].stride};
+    a.cands = d_cands + c0;
+    a.ncands = c1 - c0;
+    a.out_cost = cost_buf ? cost_buf + c0 : nullptr;
+    a.out_sad = sad_buf ? sad_buf + c0 : nullptr;
     const int warps_per_cta = 8;
-    const size_t want = (ncands + warps_per_cta - 1) / warps_per_cta;
+    const size_t want = (a.ncands + warps_per_cta - 1) / warps_per_cta;
     const int grid = (int)std::min<size_t>(want, (size_t)ctx->num_sms * 16);
-    if (cur->bpp == 1)
+    if (curs[0].bpp == 1)
       me_cand_generic<uint8_t><<<grid, warps_per_cta * 32, 0, ctx->stream>>>(a);
     else
       me_cand_generic<uint16_t><<<grid, warps_per_cta * 32, 0, ctx->stream>>>(a);
@@ -1285,6 +1459,35 @@ extern "C" int b200_me_candidates_dev(b200_ctx *ctx, const b200_plane *cur, cons
     B200_LAUNCH_CHECK(ctx);
   }
   return B200_OK;
+}
+
+}  // namespace
+
+extern "C" int b200_me_candidates_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                                      const b200_block *d_blocks, size_t nblocks,
+                                      const b200_cand *d_cands, size_t ncands,
+                                      const uint32_t *d_cand_offsets, const int16_t *d_pmv,
+                                      const b200_me_params *p, uint32_t *d_sad, uint64_t *d_cost,
+                                      b200_me_result *d_best) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  B200_REQUIRE(ctx, cur && ref && p, "NULL plane/params");
+  B200_REQUIRE(ctx, ncands < (1ull << 32) && nblocks < (1ull << 32), "ncands / nblocks must fit 32 bits");
+  const uint32_t be = (uint32_t)nblocks, ce = (uint32_t)ncands;
+  return me_candidates_pairs(ctx, 1, cur, ref, &be, &ce, d_blocks, nblocks, d_cands, ncands,
+                             d_cand_offsets, d_pmv, p, d_sad, d_cost, d_best);
+}
+
+extern "C" int b200_me_candidates_multi_dev(b200_ctx *ctx, size_t npairs, const b200_plane *curs,
+                                            const b200_plane *refs, const uint32_t *pair_block_end,
+                                            const uint32_t *pair_cand_end, const b200_block *d_blocks,
+                                            size_t nblocks, const b200_cand *d_cands, size_t ncands,
+                                            const uint32_t *d_cand_offsets, const int16_t *d_pmv,
+                                            const b200_me_params *p, uint32_t *d_sad,
+                                            uint64_t *d_cost, b200_me_result *d_best) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  B200_REQUIRE(ctx, p != nullptr, "NULL params");
+  return me_candidates_pairs(ctx, npairs, curs, refs, pair_block_end, pair_cand_end, d_blocks, nblocks,
+                             d_cands, ncands, d_cand_offsets, d_pmv, p, d_sad, d_cost, d_best);
 }
 
 // Residual of each block against the reference displaced by a full-pel motion vector:

@@ -125,6 +125,152 @@ def test_candidate_list_matches_oracle(w, h, dtype, bd, use_satd, per_block, max
         c.plane_free(pl)
 
 
+@pytest.mark.parametrize("hint", [4, 12, 1000])
+def test_candidate_list_wrong_window_hint(hint):
+    """window_hint_px is advisory: a hint smaller (or absurdly larger) than the candidates'
+    reach must not change any result (the grouped kernel re-derives the window)."""
+    W, H, PAD, w, h = 352, 288, 160, 16, 16
+    cur, ref = G.make_planes(W, H, PAD, np.uint8, seed=91)
+    ocur, dcur = G.both_planes(cur, PAD)
+    oref, dref = G.both_planes(ref, PAD)
+    blocks = G.grid_blocks(W, H, w, h)
+    cands, offs = G.random_cands(len(blocks), 64, 40, seed=17)
+    want_sad, want_cost = O.fullpel_candidates(ocur, oref, blocks, cands, w, h, False, 321)
+    c = G.ctx()
+    p = B.me_params(w, h, W, H, 321, window_hint_px=hint)
+    d_blocks, d_cands, d_offs = map(G.to_dev, (blocks, cands, offs))
+    d_sad, d_cost = G.dev_empty(4 * len(cands)), G.dev_empty(8 * len(cands))
+    d_best = G.dev_empty(16 * len(blocks))
+    c.me_candidates_dev(dcur, dref, d_blocks, len(blocks), d_cands, len(cands), p, d_offs, None,
+                        d_sad, d_cost, d_best)
+    c.synchronize()
+    np.testing.assert_array_equal(G.from_dev(d_sad, np.uint32)[:len(cands)], want_sad)
+    np.testing.assert_array_equal(G.from_dev(d_cost, np.uint64)[:len(cands)], want_cost)
+    best = G.from_dev(d_best, B.ME_RESULT_DTYPE)[:len(blocks)]
+    for b in range(len(blocks)):
+        lo, hi = int(offs[b]), int(offs[b + 1])
+        assert best[b]["cost"] == want_cost[lo:hi].min()
+    for pl in (dcur, dref):
+        c.plane_free(pl)
+
+
+MULTI_CASES = [
+    # (w, h, dtype, bit_depth, use_satd, per_block, max_px)
+    (16, 16, np.uint8, 8, False, 64, 40),     # grouped cooperative kernel
+    (16, 16, np.uint8, 8, True, 6, 30),       # warp-per-block kernel (sparse lists)
+    (8, 8, np.uint8, 8, False, 40, 16),       # grouped, thread per candidate
+    (32, 32, np.uint8, 8, True, 20, 30),
+    (16, 12, np.uint8, 8, False, 9, 12),      # non-canonical size: generic kernel, pair by pair
+    (16, 16, np.uint16, 10, False, 12, 20),   # high bit depth: generic kernel
+]
+
+
+@pytest.mark.parametrize("w,h,dtype,bd,use_satd,per_block,max_px", MULTI_CASES)
+def test_multi_pair_launch_matches_oracle(w, h, dtype, bd, use_satd, per_block, max_px):
+    """b200_me_candidates_multi_dev: several (cur, ref) pairs with different images, different
+    block subsets (one of them empty) in one call == the oracle pair by pair."""
+    W, H, PAD = 320, 192, 96
+    grid = G.grid_blocks(W, H, w, h)
+    subsets = [grid, grid[5:37], grid[:0], grid[::3].copy(), grid[-9:]]
+    lam = 555
+    curs, refs, blocks, cands, offs, want_sad, want_cost, want_best = [], [], [], [], [np.zeros(1, np.uint32)], [], [], []
+    nb_tot = nc_tot = 0
+    block_end, cand_end = [], []
+    rng = np.random.default_rng(77)
+    pmvs = []
+    for k, sub in enumerate(subsets):
+        cur, ref = G.make_planes(W, H, PAD, dtype, seed=300 + k, bit_depth=bd, shift=(k - 2, 2 - k))
+        ocur, dcur = G.both_planes(cur, PAD)
+        oref, dref = G.both_planes(ref, PAD)
+        curs.append(dcur)
+        refs.append(dref)
+        sub = np.ascontiguousarray(sub)
+        c, o = G.random_cands(len(sub), per_block, max_px, seed=40 + k, fullpel=True)
+        pmv = (rng.integers(-32, 33, (len(sub), 4)) * 4).astype(np.int16)
+        if len(sub):
+            ws, wc = O.fullpel_candidates(ocur, oref, sub, c, w, h, use_satd, lam, pmv)
+        else:
+            ws, wc = np.zeros(0, np.uint32), np.zeros(0, np.uint64)
+        want_sad.append(ws)
+        want_cost.append(wc)
+        cg = c.copy()
+        cg["block"] += nb_tot
+        blocks.append(sub)
+        cands.append(cg)
+        offs.append((o[1:].astype(np.uint64) + nc_tot).astype(np.uint32))
+        pmvs.append(pmv)
+        nb_tot += len(sub)
+        nc_tot += len(c)
+        block_end.append(nb_tot)
+        cand_end.append(nc_tot)
+    blocks, cands, offs = np.concatenate(blocks), np.concatenate(cands), np.concatenate(offs)
+    pmv = np.concatenate(pmvs)
+    want_sad, want_cost = np.concatenate(want_sad), np.concatenate(want_cost)
+    c = G.ctx()
+    p = B.me_params(w, h, W, H, lam, use_satd=use_satd, bit_depth=bd, window_hint_px=max_px)
+    d_blocks, d_cands, d_offs, d_pmv = map(G.to_dev, (blocks, cands, offs, pmv))
+    d_sad, d_cost, d_best = G.dev_empty(4 * nc_tot), G.dev_empty(8 * nc_tot), G.dev_empty(16 * nb_tot)
+    c.me_candidates_multi_dev(B.PlanePairs(curs, refs, block_end, cand_end), d_blocks, nb_tot,
+                              d_cands, nc_tot, p, d_offs, d_pmv, d_sad, d_cost, d_best)
+    c.synchronize()
+    np.testing.assert_array_equal(G.from_dev(d_sad, np.uint32)[:nc_tot], want_sad)
+    np.testing.assert_array_equal(G.from_dev(d_cost, np.uint64)[:nc_tot], want_cost)
+    best = G.from_dev(d_best, B.ME_RESULT_DTYPE)[:nb_tot]
+    for b in range(nb_tot):
+        lo, hi = int(offs[b]), int(offs[b + 1])
+        if lo == hi or want_cost[lo:hi].min() == np.uint64(2**64 - 1):
+            assert best[b]["cost"] == np.uint64(2**64 - 1)
+            continue
+        k = lo + int(np.argmin(want_cost[lo:hi]))
+        assert best[b]["cost"] == want_cost[k] and best[b]["sad"] == want_sad[k]
+        assert (best[b]["mv_row"], best[b]["mv_col"]) == (cands[k]["mv_row"], cands[k]["mv_col"])
+    for pl in curs + refs:
+        c.plane_free(pl)
+
+
+def test_multi_pair_more_pairs_than_one_launch_holds():
+    """40 pairs > the 32-entry table of one launch: split internally, same results as 40 calls."""
+    W, H, PAD, w, h = 128, 96, 64, 16, 16
+    grid = G.grid_blocks(W, H, w, h)
+    nb = len(grid)
+    c = G.ctx()
+    NP = 40
+    imgs = [G.make_planes(W, H, PAD, np.uint8, seed=500 + k) for k in range(3)]
+    dplanes = [(c.plane_from_host(cu, PAD), c.plane_from_host(re, PAD)) for cu, re in imgs]
+    curs = [dplanes[k % 3][0] for k in range(NP)]
+    refs = [dplanes[(k + 1) % 3][1] for k in range(NP)]
+    cl, ol = [], [np.zeros(1, np.uint32)]
+    for k in range(NP):
+        cc, oo = G.random_cands(nb, 48, 24, seed=600 + k, jitter=False)
+        cc["block"] += k * nb
+        cl.append(cc)
+        ol.append(oo[1:] + np.uint32(k * nb * 48))
+    cands, offs = np.concatenate(cl), np.concatenate(ol)
+    blocks = np.tile(grid, NP)
+    p = B.me_params(w, h, W, H, 900, window_hint_px=24)
+    d_blocks, d_cands, d_offs = map(G.to_dev, (blocks, cands, offs))
+    d_best = G.dev_empty(16 * nb * NP)
+    pairs = B.PlanePairs(curs, refs, [(k + 1) * nb for k in range(NP)],
+                         [(k + 1) * nb * 48 for k in range(NP)])
+    c.me_candidates_multi_dev(pairs, d_blocks, nb * NP, d_cands, len(cands), p, d_offs, None, None,
+                              None, d_best)
+    c.synchronize()
+    got = G.from_dev(d_best, B.ME_RESULT_DTYPE)[:nb * NP].copy()
+    d_one = G.dev_empty(16 * nb)
+    d_grid = G.to_dev(grid)
+    for k in range(NP):
+        ck = cl[k].copy()
+        ck["block"] -= k * nb
+        c.me_candidates_dev(curs[k], refs[k], d_grid, nb, G.to_dev(ck), len(ck), p,
+                            G.to_dev(np.arange(nb + 1, dtype=np.uint32) * 48), None, None, None, d_one)
+        c.synchronize()
+        one = G.from_dev(d_one, B.ME_RESULT_DTYPE)[:nb]
+        np.testing.assert_array_equal(got[k * nb:(k + 1) * nb], one)
+    for a, b in dplanes:
+        c.plane_free(a)
+        c.plane_free(b)
+
+
 def test_candidate_list_host_buffers():
     """The `_batch` form (host pointers, copies inside) gives the same numbers."""
     W, H, PAD, w, h = 320, 192, 96, 16, 16

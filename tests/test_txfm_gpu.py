@@ -119,6 +119,48 @@ def test_fused_residual_transform(dtype, bd):
     np.testing.assert_array_equal(d_out.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("dtype,bd,npairs", [(np.uint8, 8, 3), (np.uint16, 10, 2), (np.uint8, 8, 35)])
+def test_fused_residual_transform_multi_pair(dtype, bd, npairs):
+    """b200_fwd_txfm_residual_multi_dev over several plane pairs == one
+    b200_fwd_txfm_residual_dev call per pair (itself pinned to the oracle above)."""
+    import torch
+    c = G.ctx()
+    W, H, PAD = 128, 64, 64
+    imgs = [G.make_planes(W, H, PAD, dtype, seed=70 + k, bit_depth=bd) for k in range(3)]
+    dpl = [(c.plane_from_host(a, PAD), c.plane_from_host(b, PAD)) for a, b in imgs]
+    curs = [dpl[k % 3][0] for k in range(npairs)]
+    refs = [dpl[(k + 2) % 3][1] for k in range(npairs)]
+    grid = G.grid_blocks(W, H, 16, 16)
+    rng = np.random.default_rng(3)
+    subs = [np.ascontiguousarray(grid[: int(rng.integers(0, len(grid) + 1))]) for _ in range(npairs)]
+    blocks = np.concatenate(subs)
+    n = len(blocks)
+    best = np.zeros(n, B.ME_RESULT_DTYPE)
+    best["mv_col"] = rng.integers(-20, 21, n) * 8
+    best["mv_row"] = rng.integers(-20, 21, n) * 8
+    ends = np.cumsum([len(x) for x in subs]).astype(np.uint32)
+    i32 = bd > 8
+    dt = torch.int32 if i32 else torch.int16
+    d_blocks, d_best = G.to_dev(blocks), G.to_dev(best)
+    d_out = torch.zeros((n, 256), dtype=dt, device="cuda")
+    c.fwd_txfm_residual_multi_dev(B.PlanePairs(curs, refs, ends, ends), d_blocks, n, d_best, d_out, 2, 0, bd)
+    c.synchronize()
+    got = d_out.cpu().numpy()
+    lo = 0
+    for k, sub in enumerate(subs):
+        if len(sub) == 0:
+            continue
+        d_one = torch.zeros((len(sub), 256), dtype=dt, device="cuda")
+        c.fwd_txfm_residual_dev(curs[k], refs[k], G.to_dev(sub), len(sub), G.to_dev(best[lo:lo + len(sub)]),
+                                d_one, 2, 0, bd)
+        c.synchronize()
+        np.testing.assert_array_equal(got[lo:lo + len(sub)], d_one.cpu().numpy())
+        lo += len(sub)
+    for a, b in dpl:
+        c.plane_free(a)
+        c.plane_free(b)
+
+
 @pytest.mark.parametrize("dtype,bd", [(np.uint8, 8), (np.uint16, 10)])
 def test_subpel_predict_diff_transform_chain(dtype, bd):
     """BASELINE config 4 chain on the device: put_8tap at sub-pel vectors -> residual against the
