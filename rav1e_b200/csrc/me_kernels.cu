@@ -16,9 +16,11 @@
 //   me_full_search_u8<W,H>  8-bit fast path: window staged in smem so that every candidate
 //                           column is word aligned; each thread evaluates NP adjacent positions
 //                           sharing their loaded words.
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through the runtime)
 #include <cuda_runtime.h>
 
 #include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -90,6 +92,51 @@ struct MeArgs {
   int hint_px;     // caller's bound on |mv|/8 (0 = unknown)
   MePairs pr;
 };
+
+// Tensor maps (TMA descriptors) of the reference planes of one launch: the grouped SAD kernel
+// fetches its search window with ONE cp.async.bulk.tensor per group (box_w bytes x box_h rows,
+// dense rows in shared memory, out-of-plane parts zero-filled) instead of load/store loops.
+// Coordinates are pixels relative to the tensor origin (-ox, -oy) of each plane.
+struct MeTma {
+  int enabled;
+  int box_w, box_h;
+  short ox[kMaxPairs], oy[kMaxPairs];
+  alignas(64) CUtensorMap map[kMaxPairs];
+};
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// One thread: order the CTA's earlier generic-proxy reads of the window before the async-proxy
+// write, arm the barrier with the box size and start the copy.
+__device__ __forceinline__ void tma_load_window(uint32_t dst, const CUtensorMap *map, int x, int y,
+                                                uint32_t bar, uint32_t bytes) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+
+// All threads: wait for the copy armed with parity `parity`.  Bounded: a copy that never lands
+// (a descriptor / byte-count bug) traps instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0;; spin++) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin > (1u << 24)) __trap();
+  }
+}
 
 // ---------------------------------------------------------------- Hadamard (dist.rs:55-149)
 // In-register butterflies on an array the compiler keeps in registers (fully unrolled).
@@ -465,9 +512,10 @@ __device__ __forceinline__ unsigned long long pack_key(unsigned long long cost, 
 // single block that still does not fit reads the reference plane directly.
 template <int W, int H, bool SATD>
 __global__ void __launch_bounds__(SATD ? 128 : 256, (!SATD && W >= 16 && W * H <= 256) ? B200_SAD16_MINBLOCKS : 1)
-    me_cand_group_u8(const __grid_constant__ MeArgs a, int G) {
-  extern __shared__ __align__(16) uint32_t smem[];
-  __shared__ int s_box[4];
+    me_cand_group_u8(const __grid_constant__ MeArgs a, int G, const __grid_constant__ MeTma tm) {
+  extern __shared__ __align__(128) uint32_t smem[];
+  __shared__ int s_box[5];  // x0, x1, y0, y1 of the window's block origins; [4]: fetched by TMA
+  __shared__ __align__(8) unsigned long long s_mbar;
   __shared__ unsigned long long s_key[kMaxGroup];
   __shared__ b200_block s_blk[kMaxGroup];
   __shared__ MvRange s_rng[kMaxGroup];
@@ -491,6 +539,13 @@ __global__ void __launch_bounds__(SATD ? 128 : 256, (!SATD && W >= 16 && W * H <
   uint32_t *const win = smem + G * ORGW;
   const int win_bytes = a.smem_bytes - G * ORGW * 4;
   const size_t ngroups = a.ngroups;  // host-computed: no 64-bit division per thread
+  const bool tma_on = COOP && tm.enabled;
+  const uint32_t mbar = smem_u32(&s_mbar);
+  uint32_t tma_parity = 0;
+  if (tma_on) {
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+  }
 
   for (size_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     int pi = 0;
@@ -554,6 +609,21 @@ __global__ void __launch_bounds__(SATD ? 128 : 256, (!SATD && W >= 16 && W * H <
           s_box[1] = x1;
           s_box[2] = y0;
           s_box[3] = y1;
+          // TMA: the fixed box must cover the extent, and the set must be dense enough to stage
+          int by_tma = 0;
+          if (tma_on) {
+            const bool dense0 = (long long)(hi - lo) * (W * H) * 2 >= (long long)tm.box_h * tm.box_w;
+            // the box starts on a 16-byte column of the tensor (measured: any other x faults)
+            const int cx = (x0 + tm.ox[pi]) & ~15;
+            const int wx = cx - tm.ox[pi];
+            by_tma = dense0 && x1 - wx + W + 4 <= tm.box_w && y1 - y0 + H <= tm.box_h;
+            if (by_tma) {
+              tma_load_window(smem_u32(win), &tm.map[pi], cx, y0 + tm.oy[pi], mbar,
+                              (uint32_t)(tm.box_w * tm.box_h));
+              s_box[0] = wx;
+            }
+          }
+          s_box[4] = by_tma;
         }
       } else {
         int bx0 = INT_MAX, bx1 = INT_MIN, by0 = INT_MAX, by1 = INT_MIN;
@@ -579,15 +649,18 @@ __global__ void __launch_bounds__(SATD ? 128 : 256, (!SATD && W >= 16 && W * H <
       }
       __syncthreads();
       const bool have = s_box[0] != INT_MAX;
-      // 16-byte aligned window origin whatever the alignment of pixel (0,0)
+      const bool by_tma = hinted && tma_on && s_box[4];
+      // 16-byte aligned window origin whatever the alignment of pixel (0,0) (TMA: any origin)
       const int mis = (int)((uintptr_t)ref.data & 15);
-      const int wx0 = have ? (((s_box[0] + mis) & ~15) - mis) : 0;
+      const int wx0 = by_tma ? s_box[0] : have ? (((s_box[0] + mis) & ~15) - mis) : 0;
       const int wy0 = have ? s_box[2] : 0;
       // +4 bytes: the funnel shift reads one word past the last pixel
-      const int row_bytes = have ? (int)b200_align_up((size_t)(s_box[1] + W + 4 - wx0), 16) : 0;
-      const int rows = have ? s_box[3] - wy0 + H : 0;
+      const int row_bytes = by_tma ? tm.box_w : have ? (int)b200_align_up((size_t)(s_box[1] + W + 4 - wx0), 16) : 0;
+      const int rows = by_tma ? tm.box_h : have ? s_box[3] - wy0 + H : 0;
       int pitch_words;
-      if (COOP) {  // == LPR (mod 32): conflict-free cooperative loads, rows stay 16-byte aligned
+      if (by_tma) {       // dense box rows; the host picked box_w / 4 == LPR * odd (conflict-free)
+        pitch_words = row_bytes >> 2;
+      } else if (COOP) {  // == LPR (mod 32): conflict-free cooperative loads, rows stay 16-byte aligned
         pitch_words = ((row_bytes >> 2) & ~31) + LPR;
         if (pitch_words < (row_bytes >> 2)) pitch_words += 32;
       } else {     // 16-byte aligned rows, odd multiple of 4 words
@@ -608,7 +681,7 @@ __global__ void __launch_bounds__(SATD ? 128 : 256, (!SATD && W >= 16 && W * H <
       // move: stage only when the candidates' own footprints exceed half the window.
       const bool dense = (long long)(hi - lo) * (W * H) * 2 >= (long long)rows * row_bytes;
       const bool staged = have && fits && dense;
-      if (staged)
+      if (staged && !by_tma)
         stage_window(win, pitch_words, px<uint8_t>(ref, wx0, wy0), ref.stride, rows, row_bytes);
       // org blocks -> packed words
       for (int i = threadIdx.x; i < nb * ORGW; i += nthr) {
@@ -669,10 +742,18 @@ __global__ void __launch_bounds__(SATD ? 128 : 256, (!SATD && W >= 16 && W * H <
           // (also retires the previous round's readers of s_par)
           if (hinted ? __syncthreads_or(outside) : (__syncthreads(), 0)) {
             hint_failed = true;  // uniform
+            if (by_tma && base == lo) {  // the copy in flight must land before the window is reused
+              mbar_wait(mbar, tma_parity);
+              tma_parity ^= 1;
+            }
             break;
           }
           s_par[threadIdx.x] = par;
           __syncthreads();
+          if (by_tma && base == lo) {  // window bytes arrive here, behind pass 1
+            mbar_wait(mbar, tma_parity);
+            tma_parity ^= 1;
+          }
           uint32_t sad = 0;
           const uint32_t par_s = smem_u32(s_par + warp * 32);
           // When the warp's 32 candidates belong to one block (the usual case: lists are grouped
@@ -1123,7 +1204,7 @@ constexpr int kFsSmemBytes = 200 * 1024;
 
 template <int W, int H, int NP>
 __global__ void __launch_bounds__(256) me_full_search_u8(FsArgs a) {
-  extern __shared__ __align__(16) uint32_t smem[];
+  extern __shared__ __align__(128) uint32_t smem[];
   __shared__ uint32_t s_org[H * W / 4];
   __shared__ Best s_red[32];
   const int step = a.step;
@@ -1219,8 +1300,86 @@ __global__ void __launch_bounds__(256) me_full_search_u8(FsArgs a) {
 }
 
 // ---------------------------------------------------------------- host-side dispatch
+// ---- tensor maps of reference planes (host).  cuTensorMapEncodeTiled comes from the driver
+// through the runtime (no link-time dependency on libcuda); encoded maps are cached by geometry.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn tma_encoder() {
+  static EncodeTiledFn fn = [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    (void)cudaGetLastError();
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+struct TmaKey {
+  const void *base;
+  uint64_t w, h, stride;
+  uint32_t bw, bh;
+  bool operator==(const TmaKey &o) const {
+    return base == o.base && w == o.w && h == o.h && stride == o.stride && bw == o.bw && bh == o.bh;
+  }
+};
+struct TmaKeyHash {
+  size_t operator()(const TmaKey &k) const {
+    size_t x = (size_t)k.base;
+    for (uint64_t v : {k.w, k.h, k.stride, (uint64_t)k.bw, (uint64_t)k.bh})
+      x = x * 1099511628211ull ^ (size_t)v;
+    return x;
+  }
+};
+
+// Tensor map of an 8-bit plane's readable area (pixels [-pad, dim + pad)) with a bw x bh box.
+// False when the plane cannot be described (unaligned base / pitch): the caller stages by hand.
+bool tma_plane_map(const b200_plane &p, uint32_t bw, uint32_t bh, CUtensorMap *out, short *ox, short *oy) {
+  EncodeTiledFn enc = tma_encoder();
+  if (!enc || p.bpp != 1 || p.pad < 0 || p.pad > 16384 || (p.stride & 15) || bw > 256 || bh > 256 ||
+      (bw & 15))
+    return false;
+  // origin: the allocation's first column when known (b200_plane_alloc keeps it 256-byte
+  // aligned), else pixel (-pad, -pad)
+  long long lead = p.pad;
+  if (p.alloc) {
+    const long long off = (const uint8_t *)p.data - (const uint8_t *)p.alloc - (long long)p.pad * p.stride;
+    if (off >= p.pad && off < p.stride) lead = off;
+  }
+  const uint8_t *base = (const uint8_t *)p.data - (long long)p.pad * p.stride - lead;
+  if ((uintptr_t)base & 15) return false;
+  TmaKey key{base, (uint64_t)(lead + p.width + p.pad), (uint64_t)(p.height + 2 * p.pad), (uint64_t)p.stride, bw, bh};
+  static std::mutex mu;
+  static std::unordered_map<TmaKey, CUtensorMap, TmaKeyHash> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {key.w, key.h};
+    const cuuint64_t strides[1] = {key.stride};
+    const cuuint32_t box[2] = {bw, bh};
+    const cuuint32_t estr[2] = {1, 1};
+    if (key.w > key.stride ||
+        enc(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)base, dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+    if (cache.size() > 8192) cache.clear();
+    it = cache.emplace(key, m).first;
+  }
+  *out = it->second;
+  *ox = (short)lead;
+  *oy = (short)p.pad;
+  return true;
+}
+
 template <int W, int H, bool SATD>
-int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px) {
+int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px, const b200_plane *refs) {
   // opt in to the largest dynamic shared memory this kernel may be launched with, once
   // (thread safe: contexts on several host threads launch concurrently)
   static std::once_flag attr_once;
@@ -1281,8 +1440,30 @@ int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px) {
   }
   a.ngroups = ngroups;
   if (ngroups == 0) return B200_OK;
+  // Window by TMA (cooperative SAD with a search-range hint): box = the hint window, widened to
+  // a multiple of 16 bytes whose word pitch is LPR * odd (conflict-free like the padded pitch).
+  static thread_local MeTma tm;
+  tm.enabled = 0;
+  if (COOP && window_hint_px > 0 && !getenv("B200_NO_TMA")) {
+    // + up to 15 bytes in front of the window to start the box on a 16-byte column; none when
+    // hint and block width keep every window origin aligned (groups that are not fall back to
+    // staging by hand inside the kernel)
+    const int slack = (hint % 16 == 0 && W % 16 == 0) ? 0 : 15;
+    uint32_t bw = (uint32_t)b200_align_up((size_t)(2 * hint + G * W + 4 + slack), 16);
+    while (((bw / 4) / LPR) % 2 == 0 || (bw / 4) % LPR) bw += 16;
+    const uint32_t bh = (uint32_t)(2 * hint + H);
+    if ((size_t)bw * bh + (size_t)G * W * H <= smem) {
+      bool ok = true;
+      for (int k = 0; k < a.pr.n && ok; k++) ok = tma_plane_map(refs[k], bw, bh, &tm.map[k], &tm.ox[k], &tm.oy[k]);
+      if (ok) {
+        tm.enabled = 1;
+        tm.box_w = (int)bw;
+        tm.box_h = (int)bh;
+      }
+    }
+  }
   const int grid = (int)std::min<size_t>(ngroups, (size_t)ctx->num_sms * 32);
-  me_cand_group_u8<W, H, SATD><<<grid, threads, smem, ctx->stream>>>(a, G);
+  me_cand_group_u8<W, H, SATD><<<grid, threads, smem, ctx->stream>>>(a, G, tm);
   B200_LAUNCH_CHECK(ctx);
   return B200_OK;
 }
@@ -1378,7 +1559,7 @@ int me_candidates_pairs(b200_ctx *ctx, size_t npairs, const b200_plane *curs, co
   // pairs per launch.
   if (curs[0].bpp == 1 && d_cand_offsets && nblocks > 0 && fast_planes &&
       ncands <= (1ull << kKeyIdxBits)) {
-    int (*launch)(b200_ctx *, MeArgs, int) = nullptr;
+    int (*launch)(b200_ctx *, MeArgs, int, const b200_plane *) = nullptr;
 #define B200_CASE(W_, H_)            \
   if (p->w == W_ && p->h == H_)      \
     launch = p->use_satd ? launch_cand_group<W_, H_, true> : launch_cand_group<W_, H_, false>;
@@ -1410,7 +1591,7 @@ int me_candidates_pairs(b200_ctx *ctx, size_t npairs, const b200_plane *curs, co
         a.nblocks = a.pr.block_end[n - 1] - a.pr.block_begin;
         a.ncands = cand_end[k0 + n - 1] - (k0 ? cand_end[k0 - 1] : 0);
         if (a.nblocks == 0) continue;
-        if (int st = launch(ctx, a, p->window_hint_px)) return st;
+        if (int st = launch(ctx, a, p->window_hint_px, refs + k0)) return st;
       }
       return B200_OK;
     }

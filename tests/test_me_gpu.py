@@ -271,6 +271,33 @@ def test_multi_pair_more_pairs_than_one_launch_holds():
         c.plane_free(b)
 
 
+@pytest.mark.parametrize("hint,dx", [(32, 4), (32, 0), (48, 12), (24, 8)])
+def test_candidate_list_unaligned_block_columns(hint, dx):
+    """Blocks that do not start on 16-pixel columns (4x4-unit offsets inside a superblock) and
+    hints that are / are not multiples of 16: the TMA-staged window, its 16-byte column rule and
+    the hand-staged fall back must all give the oracle's numbers."""
+    W, H, PAD, w, h = 352, 288, 160, 16, 16
+    cur, ref = G.make_planes(W, H, PAD, np.uint8, seed=123)
+    ocur, dcur = G.both_planes(cur, PAD)
+    oref, dref = G.both_planes(ref, PAD)
+    blocks = G.grid_blocks(W - 16, H - 16, w, h)
+    blocks["x"] += dx
+    blocks["y"] += 4
+    cands, offs = G.random_cands(len(blocks), 64, hint, seed=29)
+    want_sad, want_cost = O.fullpel_candidates(ocur, oref, blocks, cands, w, h, False, 700)
+    c = G.ctx()
+    p = B.me_params(w, h, W, H, 700, window_hint_px=hint)
+    d_blocks, d_cands, d_offs = map(G.to_dev, (blocks, cands, offs))
+    d_sad, d_cost = G.dev_empty(4 * len(cands)), G.dev_empty(8 * len(cands))
+    c.me_candidates_dev(dcur, dref, d_blocks, len(blocks), d_cands, len(cands), p, d_offs, None,
+                        d_sad, d_cost, None)
+    c.synchronize()
+    np.testing.assert_array_equal(G.from_dev(d_sad, np.uint32)[:len(cands)], want_sad)
+    np.testing.assert_array_equal(G.from_dev(d_cost, np.uint64)[:len(cands)], want_cost)
+    for pl in (dcur, dref):
+        c.plane_free(pl)
+
+
 def test_candidate_list_host_buffers():
     """The `_batch` form (host pointers, copies inside) gives the same numbers."""
     W, H, PAD, w, h = 320, 192, 96, 16, 16
