@@ -368,7 +368,9 @@ def run_b200(args, rank, world, local_rank):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         with open(tp) as fh:
-            traffic = json.load(fh).get("me_cand_smem_u8_16x16_dram_bytes_per_launch")
+            traffic = json.load(fh).get("me_cand_group_u8_16x16_dram_bytes_per_frame_pair")
+            if traffic is not None:
+                traffic = int(traffic * pairs_per_launch)
 
     out = None
     if rank == 0:

@@ -24,6 +24,9 @@
 
 #include "common.cuh"
 
+#ifndef B200_SAD_THREADS
+#define B200_SAD_THREADS 256  // CTA size of the SAD instantiations of the grouped kernel
+#endif
 #ifndef B200_SAD16_MINBLOCKS
 // Resident CTAs per SM the 16x16 SAD kernel is register-capped for: 4 (64 registers, no spills)
 // measured 0.850 ms per 32-pair launch against 0.931 ms at 5 (48 registers, 66 B of spills).
@@ -511,7 +514,7 @@ __device__ __forceinline__ unsigned long long pack_key(unsigned long long cost, 
 // shared atomicMin per warp.  Windows that do not fit fall back to one block per pass, and a
 // single block that still does not fit reads the reference plane directly.
 template <int W, int H, bool SATD>
-__global__ void __launch_bounds__(SATD ? 128 : 256, (!SATD && W >= 16 && W * H <= 256) ? B200_SAD16_MINBLOCKS : 1)
+__global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 16 && W * H <= 256) ? B200_SAD16_MINBLOCKS : 1)
     me_cand_group_u8(const __grid_constant__ MeArgs a, int G, const __grid_constant__ MeTma tm) {
   extern __shared__ __align__(128) uint32_t smem[];
   __shared__ int s_box[5];  // x0, x1, y0, y1 of the window's block origins; [4]: fetched by TMA
@@ -533,7 +536,7 @@ __global__ void __launch_bounds__(SATD ? 128 : 256, (!SATD && W >= 16 && W * H <
   constexpr bool COOP = !SATD && W >= 16 && W <= 64 && (LPR * H) >= 32 && (LPR * H) % 32 == 0;
   constexpr int RPP = COOP ? 32 / LPR : 1;
   constexpr int P = COOP ? H / RPP : 1;
-  constexpr int nthr = SATD ? 128 : 256;  // must match launch_cand_group
+  constexpr int nthr = SATD ? 128 : B200_SAD_THREADS;  // must match launch_cand_group
   const int lane = threadIdx.x & 31;
   uint32_t *const s_org = smem;                               // [G][ORGW]
   uint32_t *const win = smem + G * ORGW;
@@ -660,9 +663,9 @@ __global__ void __launch_bounds__(SATD ? 128 : 256, (!SATD && W >= 16 && W * H <
       int pitch_words;
       if (by_tma) {       // dense box rows; the host picked box_w / 4 == LPR * odd (conflict-free)
         pitch_words = row_bytes >> 2;
-      } else if (COOP) {  // == LPR (mod 32): conflict-free cooperative loads, rows stay 16-byte aligned
-        pitch_words = ((row_bytes >> 2) & ~31) + LPR;
-        if (pitch_words < (row_bytes >> 2)) pitch_words += 32;
+      } else if (COOP) {  // LPR * odd: conflict-free cooperative loads, rows stay 16-byte aligned
+        pitch_words = ((row_bytes >> 2) + LPR - 1) & ~(LPR - 1);
+        if (((pitch_words / LPR) & 1) == 0) pitch_words += LPR;
       } else {     // 16-byte aligned rows, odd multiple of 4 words
         pitch_words = (row_bytes >> 2) | 4;
       }
@@ -1410,24 +1413,50 @@ int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px, const b200_pl
   constexpr int S = (W < 8 || H < 8) ? 4 : 8;
   constexpr int NCH = SATD ? (W / S) * (H / S) : 1;
   constexpr int TPC = NCH < 32 ? NCH : 32;
-  const int threads = SATD ? 128 : 256;  // SATD holds a 64-entry chunk per thread: smaller CTAs, more of them
+  const int threads = SATD ? 128 : B200_SAD_THREADS;  // SATD holds a 64-entry chunk per thread: smaller CTAs, more of them
   int G = (int)std::min<size_t>(kMaxGroup, std::max<size_t>(1, (threads / TPC) / std::max<size_t>(avg, 1)));
   G = std::max(1, std::min(G, 16384 / (W * H)));  // org tiles <= 16 KB
   // Shared window sized from the caller's search-range hint (+ the group's extent along x);
   // groups/blocks that do not fit degrade inside the kernel, never fail.
   const int hint = window_hint_px > 0 ? window_hint_px : 32;
-  // mirror the kernel's pitch choice for the widest window the hint allows
-  const size_t words = b200_align_up((size_t)(2 * hint + G * W + 4 + 15), 16) >> 2;
   constexpr int LPR = W / 4;
   constexpr bool COOP = !SATD && W >= 16 && W <= 64 && (LPR * H) >= 32 && (LPR * H) % 32 == 0;
-  size_t pitch;
-  if (COOP) {
-    pitch = (words & ~(size_t)31) + LPR;
-    if (pitch < words) pitch += 32;
-  } else {
-    pitch = words | 4;
+  // Window by TMA (cooperative SAD with a search-range hint): box = the hint window, widened to
+  // a multiple of 16 bytes whose word pitch is LPR * odd (conflict-free like the padded pitch).
+  static thread_local MeTma tm;
+  tm.enabled = 0;
+  size_t smem = 0;
+  if (COOP && window_hint_px > 0 && !getenv("B200_NO_TMA")) {
+    // + up to 15 bytes in front of the window to start the box on a 16-byte column; none when
+    // hint and block width keep every window origin aligned (groups that are not fall back to
+    // staging by hand inside the kernel)
+    const int slack = (hint % 16 == 0 && W % 16 == 0) ? 0 : 15;
+    uint32_t bw = (uint32_t)b200_align_up((size_t)(2 * hint + G * W + 4 + slack), 16);
+    while (((bw / 4) / LPR) % 2 == 0 || (bw / 4) % LPR) bw += 16;
+    const uint32_t bh = (uint32_t)(2 * hint + H);
+    smem = (size_t)bw * bh + (size_t)G * W * H;
+    if (smem <= (size_t)kCandSmemBytes) {
+      bool ok = true;
+      for (int k = 0; k < a.pr.n && ok; k++) ok = tma_plane_map(refs[k], bw, bh, &tm.map[k], &tm.ox[k], &tm.oy[k]);
+      if (ok) {
+        tm.enabled = 1;
+        tm.box_w = (int)bw;
+        tm.box_h = (int)bh;
+      }
+    }
   }
-  size_t smem = pitch * 4 * (size_t)(2 * hint + H) + (size_t)G * W * H;
+  if (!tm.enabled) {
+    // mirror the kernel's pitch choice for the widest hand-staged window the hint allows
+    const size_t words = b200_align_up((size_t)(2 * hint + G * W + 4 + 15), 16) >> 2;
+    size_t pitch;
+    if (COOP) {
+      pitch = (words + LPR - 1) & ~(size_t)(LPR - 1);
+      if (((pitch / LPR) & 1) == 0) pitch += LPR;
+    } else {
+      pitch = words | 4;
+    }
+    smem = pitch * 4 * (size_t)(2 * hint + H) + (size_t)G * W * H;
+  }
   smem = std::min<size_t>(std::max<size_t>(smem, 16 * 1024), (size_t)kCandSmemBytes);
   a.smem_bytes = (int)smem;
   // groups never straddle a plane pair
@@ -1440,28 +1469,6 @@ int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px, const b200_pl
   }
   a.ngroups = ngroups;
   if (ngroups == 0) return B200_OK;
-  // Window by TMA (cooperative SAD with a search-range hint): box = the hint window, widened to
-  // a multiple of 16 bytes whose word pitch is LPR * odd (conflict-free like the padded pitch).
-  static thread_local MeTma tm;
-  tm.enabled = 0;
-  if (COOP && window_hint_px > 0 && !getenv("B200_NO_TMA")) {
-    // + up to 15 bytes in front of the window to start the box on a 16-byte column; none when
-    // hint and block width keep every window origin aligned (groups that are not fall back to
-    // staging by hand inside the kernel)
-    const int slack = (hint % 16 == 0 && W % 16 == 0) ? 0 : 15;
-    uint32_t bw = (uint32_t)b200_align_up((size_t)(2 * hint + G * W + 4 + slack), 16);
-    while (((bw / 4) / LPR) % 2 == 0 || (bw / 4) % LPR) bw += 16;
-    const uint32_t bh = (uint32_t)(2 * hint + H);
-    if ((size_t)bw * bh + (size_t)G * W * H <= smem) {
-      bool ok = true;
-      for (int k = 0; k < a.pr.n && ok; k++) ok = tma_plane_map(refs[k], bw, bh, &tm.map[k], &tm.ox[k], &tm.oy[k]);
-      if (ok) {
-        tm.enabled = 1;
-        tm.box_w = (int)bw;
-        tm.box_h = (int)bh;
-      }
-    }
-  }
   const int grid = (int)std::min<size_t>(ngroups, (size_t)ctx->num_sms * 32);
   me_cand_group_u8<W, H, SATD><<<grid, threads, smem, ctx->stream>>>(a, G, tm);
   B200_LAUNCH_CHECK(ctx);
