@@ -178,6 +178,33 @@ int b200_me_candidates_multi_dev(b200_ctx *ctx, size_t npairs, const b200_plane 
                                  const b200_me_params *params, uint32_t *d_sad, uint64_t *d_cost,
                                  b200_me_result *d_best);
 
+/* The move-to-best search stages of full_pixel_me (me.rs:692-856) for every block, on the device:
+ * per predictor subset get_best_predictor (:884-909) + fullpel_diamond_search (:955-998), the
+ * extensive ladder's early exits (`best.rd.sad < thresh`, :777-790) and uneven_multi_hex_search
+ * (:1170-1303, ends in hexagon_search :1055-1135).  The exhaustive grid that may follow
+ * (:822-846) is b200_me_full_search_dev.
+ *   nsubsets 1: non-extensive search, d_preds holds `subsets.all_mvs()` per block (:757-759);
+ *   nsubsets 3: extensive search, subsets = {median (skipped when empty), subset_b, subset_c},
+ *               d_thresh[nblocks] = the caller's `thresh` (:771-772), umh_range = 24 (:806) or 0
+ *               to stop before the UMH stage.
+ * d_subset_offsets: nblocks * nsubsets + 1 offsets into d_preds (b200_cand.block is ignored).
+ * Predictor gathering (get_subset_predictors, :381-533) stays with the caller: it reads the
+ * neighbouring blocks' results of the same pass.  A block whose candidates are all out of range
+ * (where the reference would assert) yields the empty result. */
+int b200_me_search_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                       const b200_block *d_blocks, size_t nblocks, const b200_cand *d_preds,
+                       const uint32_t *d_subset_offsets, int nsubsets, const int16_t *d_pmv,
+                       const uint32_t *d_thresh, const b200_me_params *params, int umh_range,
+                       b200_me_result *d_best);
+/* The same over `npairs` plane pairs in one launch (block ranges as in
+ * b200_me_candidates_multi_dev; offsets, pmv, thresh and results follow the concatenated blocks). */
+int b200_me_search_multi_dev(b200_ctx *ctx, size_t npairs, const b200_plane *curs,
+                             const b200_plane *refs, const uint32_t *pair_block_end,
+                             const b200_block *d_blocks, size_t nblocks, const b200_cand *d_preds,
+                             const uint32_t *d_subset_offsets, int nsubsets, const int16_t *d_pmv,
+                             const uint32_t *d_thresh, const b200_me_params *params, int umh_range,
+                             b200_me_result *d_best);
+
 /* get_subpel_mv_rd (me.rs:1411-1442) over a candidate list of SUB-PEL vectors: each candidate is
  * predicted with the 8-tap filter `filter_mode` (fi.default_filter; predict_inter_single,
  * predict.rs:304-336) and measured with SAD or SATD against the source block — the unit of work

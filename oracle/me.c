@@ -206,3 +206,212 @@ void orc_subpel_candidates(const void *cur0, ptrdiff_t cur_stride, const void *r
     if (out_cost) out_cost[i] = cost;
   }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Search stages of full_pixel_me (me.rs:692-856): get_best_predictor :884-909,
+ * fullpel_diamond_search :955-998, hexagon_search :1055-1135, uneven_multi_hex_search
+ * :1170-1303, driven per block like the `try_cands` closure (:722-762) and its callers.
+ * MotionVector arithmetic is i16 (mc.rs:57-100; release builds wrap).  No stored vector in the
+ * reference pins these stages ("parity unpinned"); they are compositions of get_fullpel_mv_rd,
+ * whose SAD is pinned, with the strict-`<` update rule restated line by line.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void *org; /* block pixel (0,0) in cur */
+  ptrdiff_t org_stride;
+  const void *ref0;
+  ptrdiff_t ref_stride;
+  int bpp, w, h, po_x, po_y;
+  int mvx_min, mvx_max, mvy_min, mvy_max;
+  uint32_t lambda;
+  orc_mv pmv0, pmv1;
+  int allow_hp;
+} srch;
+
+static inline orc_mv mv_add(orc_mv a, orc_mv b) {
+  orc_mv r = {(int16_t)(a.row + b.row), (int16_t)(a.col + b.col)};
+  return r;
+}
+static inline orc_mv mv_mul(orc_mv a, int16_t k) {
+  orc_mv r = {(int16_t)(a.row * k), (int16_t)(a.col * k)};
+  return r;
+}
+static inline orc_mv mv_shl(orc_mv a, int s) {
+  orc_mv r = {(int16_t)((int)a.row * (1 << s)), (int16_t)((int)a.col * (1 << s))};
+  return r;
+}
+static inline orc_me_result res_empty(void) { /* MotionSearchResult::empty(), me.rs:111-116 */
+  orc_me_result r;
+  r.cost = UINT64_MAX;
+  r.sad = UINT32_MAX;
+  r.mv.row = 0;
+  r.mv.col = 0;
+  return r;
+}
+
+/* get_fullpel_mv_rd, me.rs:1386-1409 (use_satd = false in every full-pel stage) */
+static orc_me_result fullpel_rd(const srch *s, orc_mv mv) {
+  orc_me_result r = res_empty();
+  r.mv = mv;
+  if (mv.col < s->mvx_min || mv.col > s->mvx_max || mv.row < s->mvy_min || mv.row > s->mvy_max)
+    return r;
+  r.sad = dist_any(s->org, s->org_stride,
+                   px_at(s->ref0, s->ref_stride, s->bpp, s->po_x + mv.col / 8, s->po_y + mv.row / 8),
+                   s->ref_stride, s->bpp, s->w, s->h, 0);
+  r.cost = orc_mv_cost(r.sad, mv, s->pmv0, s->pmv1, s->lambda, s->allow_hp);
+  return r;
+}
+
+/* me.rs:884-909 */
+static orc_me_result best_predictor(const srch *s, const orc_cand *preds, size_t n) {
+  orc_me_result best = res_empty();
+  for (size_t i = 0; i < n; i++) {
+    orc_mv mv = {preds[i].mv_row, preds[i].mv_col};
+    orc_me_result rd = fullpel_rd(s, mv);
+    if (rd.cost < best.cost) best = rd;
+  }
+  return best;
+}
+
+#define FP(c, r) {(int16_t)((r) * 8), (int16_t)((c) * 8)} /* search_pattern!: {row, col} << 3 */
+static const orc_mv DIAMOND_R1[4] = {FP(0, 1), FP(1, 0), FP(0, -1), FP(-1, 0)}; /* me.rs:944-947 */
+static const orc_mv HEXAGON[6] = {FP(0, -2), FP(2, -1), FP(2, 1), FP(0, 2), FP(-2, 1), FP(-2, -1)}; /* :1022-1025 */
+static const orc_mv SQUARE_REFINE[8] = {FP(-1, 1), FP(0, 1),  FP(1, 1),  FP(-1, 0),
+                                        FP(1, 0),  FP(-1, -1), FP(0, -1), FP(1, -1)}; /* :1035-1038 */
+static const orc_mv UMH[16] = {FP(-2, 4), FP(-1, 4), FP(0, 4),  FP(1, 4),  FP(2, 4),  FP(3, 2),
+                               FP(4, 0),  FP(3, -2), FP(2, -4), FP(1, -4), FP(0, -4), FP(-1, -4),
+                               FP(-2, -4), FP(3, -2), FP(-4, 0), FP(-3, 2)}; /* :1153-1156 */
+
+/* me.rs:955-998 */
+static void fullpel_diamond(const srch *s, orc_me_result *current) {
+  int radius_log2 = 1;
+  const int end_log2 = 0;
+  for (;;) {
+    orc_me_result best_cand = res_empty();
+    for (int k = 0; k < 4; k++) {
+      orc_me_result rd = fullpel_rd(s, mv_add(current->mv, mv_shl(DIAMOND_R1[k], radius_log2)));
+      if (rd.cost < best_cand.cost) best_cand = rd;
+    }
+    if (current->cost <= best_cand.cost) {
+      if (radius_log2 == end_log2) break;
+      radius_log2--;
+    } else {
+      *current = best_cand;
+    }
+  }
+}
+
+/* me.rs:1055-1135 */
+static void hexagon(const srch *s, orc_me_result *current) {
+  int best_idx = 0;
+  orc_me_result best_cand = res_empty();
+  for (int i = 0; i < 6; i++) {
+    orc_me_result rd = fullpel_rd(s, mv_add(current->mv, HEXAGON[i]));
+    if (rd.cost < best_cand.cost) {
+      best_idx = i;
+      best_cand = rd;
+    }
+  }
+  while (best_cand.cost < current->cost) {
+    *current = best_cand;
+    best_cand = res_empty();
+    const int center_idx = best_idx;
+    for (int off = 5; off <= 7; off++) {
+      const int i = (center_idx + off) % 6;
+      orc_me_result rd = fullpel_rd(s, mv_add(current->mv, HEXAGON[i]));
+      if (rd.cost < best_cand.cost) {
+        best_idx = i;
+        best_cand = rd;
+      }
+    }
+  }
+  best_cand = res_empty();
+  for (int k = 0; k < 8; k++) {
+    orc_me_result rd = fullpel_rd(s, mv_add(current->mv, SQUARE_REFINE[k]));
+    if (rd.cost < best_cand.cost) best_cand = rd;
+  }
+  if (best_cand.cost < current->cost) *current = best_cand;
+}
+
+/* me.rs:1170-1303.  Quirks kept as they are: the "horizontal" line steps the ROW component
+ * (:1195-1198), and the 5x5 stage adds raw {row, col} in 1/8 pel, not full pixels (:1240-1246). */
+static void umh(const srch *s, orc_me_result *current, int me_range) {
+  orc_mv center = current->mv;
+  for (int i = 1; i <= me_range; i += 2) {
+    static const orc_mv line[2] = {FP(0, -1), FP(0, 1)};
+    for (int k = 0; k < 2; k++) {
+      orc_me_result rd = fullpel_rd(s, mv_add(center, mv_mul(line[k], (int16_t)i)));
+      if (rd.cost < current->cost) *current = rd;
+    }
+  }
+  for (int i = 1; i <= (me_range >> 1); i += 2) {
+    static const orc_mv line[2] = {FP(-1, 0), FP(1, 0)};
+    for (int k = 0; k < 2; k++) {
+      orc_me_result rd = fullpel_rd(s, mv_add(center, mv_mul(line[k], (int16_t)i)));
+      if (rd.cost < current->cost) *current = rd;
+    }
+  }
+  center = current->mv;
+  for (int row = -2; row <= 2; row++)
+    for (int col = -2; col <= 2; col++) {
+      if (row == 0 && col == 0) continue;
+      orc_mv off = {(int16_t)row, (int16_t)col};
+      orc_me_result rd = fullpel_rd(s, mv_add(center, off));
+      if (rd.cost < current->cost) *current = rd;
+    }
+  center = current->mv;
+  const int iterations = me_range >> 2;
+  for (int i = 1; i <= iterations; i++)
+    for (int k = 0; k < 16; k++) {
+      orc_me_result rd = fullpel_rd(s, mv_add(center, mv_mul(UMH[k], (int16_t)i)));
+      if (rd.cost < current->cost) *current = rd;
+    }
+  hexagon(s, current);
+}
+
+/* full_pixel_me (me.rs:692-856) for every block, full resolution (ssdec = 0), without the final
+ * exhaustive grid (orc_full_search_blocks).  Predictor subsets come from the caller
+ * (get_subset_predictors reads neighbouring blocks' results): nsubsets = 1 -> `all_mvs`
+ * (non-extensive, :757-759); nsubsets = 3 -> {median (skipped when empty, :774), subset_b,
+ * subset_c} with the early exits `best.rd.sad < thresh` (:777-790) and the UMH stage (:794-812).
+ * subset_offsets: nblocks * nsubsets + 1 offsets into preds.  Where the reference would hit
+ * `assert!(!current.is_empty())` (no candidate in range at all) the result stays empty. */
+void orc_full_pixel_me_blocks(const void *cur0, ptrdiff_t cur_stride, const void *ref0,
+                              ptrdiff_t ref_stride, int bpp, int frame_w_in_b, int frame_h_in_b,
+                              const orc_block *blocks, size_t nblocks, const orc_cand *preds,
+                              const uint32_t *subset_offsets, int nsubsets, const orc_mv *pmv,
+                              const uint32_t *thresh, int w, int h, uint32_t lambda, int allow_hp,
+                              int umh_range, orc_me_result *out, int threads) {
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads > 0 ? threads : orc_num_threads())
+  for (ptrdiff_t i = 0; i < (ptrdiff_t)nblocks; i++) {
+    const orc_block b = blocks[i];
+    srch s;
+    s.org = px_at(cur0, cur_stride, bpp, b.x, b.y);
+    s.org_stride = cur_stride;
+    s.ref0 = ref0;
+    s.ref_stride = ref_stride;
+    s.bpp = bpp;
+    s.w = w;
+    s.h = h;
+    s.po_x = b.x;
+    s.po_y = b.y;
+    orc_get_mv_range(frame_w_in_b, frame_h_in_b, b.x / MI_SIZE, b.y / MI_SIZE, w, h, &s.mvx_min,
+                     &s.mvx_max, &s.mvy_min, &s.mvy_max);
+    s.lambda = lambda;
+    orc_mv z = {0, 0};
+    s.pmv0 = pmv ? pmv[2 * i] : z;
+    s.pmv1 = pmv ? pmv[2 * i + 1] : z;
+    s.allow_hp = allow_hp;
+    orc_me_result best = res_empty();
+    int done = 0;
+    for (int k = 0; k < nsubsets && !done; k++) {
+      const uint32_t lo = subset_offsets[i * nsubsets + k], hi = subset_offsets[i * nsubsets + k + 1];
+      if (nsubsets == 3 && k == 0 && lo == hi) continue; /* `if let Some(median)` */
+      orc_me_result r = best_predictor(&s, preds + lo, hi - lo);
+      fullpel_diamond(&s, &r);
+      if (r.cost < best.cost) best = r;
+      if (nsubsets == 3 && best.sad < thresh[i]) done = 1;
+    }
+    if (nsubsets == 3 && !done && umh_range > 0 && best.cost != UINT64_MAX) umh(&s, &best, umh_range);
+    out[i] = best;
+  }
+}

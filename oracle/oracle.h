@@ -98,6 +98,16 @@ void orc_full_search_blocks(const void *cur0, ptrdiff_t cur_stride, const void *
                             int range_y, int step, uint32_t lambda, int allow_hp,
                             orc_me_result *out, int threads);
 
+/* full_pixel_me (me.rs:692-856) minus the final exhaustive grid: get_best_predictor +
+ * fullpel_diamond_search per predictor subset, early exits, uneven_multi_hex_search (+
+ * hexagon_search).  nsubsets 1 = non-extensive, 3 = extensive (median | subset_b | subset_c). */
+void orc_full_pixel_me_blocks(const void *cur0, ptrdiff_t cur_stride, const void *ref0,
+                              ptrdiff_t ref_stride, int bpp, int frame_w_in_b, int frame_h_in_b,
+                              const orc_block *blocks, size_t nblocks, const orc_cand *preds,
+                              const uint32_t *subset_offsets, int nsubsets, const orc_mv *pmv,
+                              const uint32_t *thresh, int w, int h, uint32_t lambda, int allow_hp,
+                              int umh_range, orc_me_result *out, int threads);
+
 /* -------------------------------------------------------------- transform/ */
 /* forward.rs:71-161.  coeff_is_i32: 0 -> int16_t out (8-bit pixels), 1 -> int32_t out. */
 int orc_valid_av1_transform(int tx_size, int tx_type);

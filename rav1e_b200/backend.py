@@ -119,6 +119,8 @@ def lib():
             f.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t] + extra
             f.restype = u32
     L.b200_me_candidates_dev.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
+    L.b200_me_search_dev.argtypes = [vp, pp, pp, vp, sz, vp, vp, i32, vp, vp, pmp, i32, vp]
+    L.b200_me_search_multi_dev.argtypes = [vp, sz, vp, vp, vp, vp, sz, vp, vp, i32, vp, vp, pmp, i32, vp]
     L.b200_me_candidates_multi_dev.argtypes = [vp, sz, vp, vp, vp, vp, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
     L.b200_me_subpel_candidates_dev.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, i32, vp, vp, vp]
     L.b200_me_full_search_dev.argtypes = [vp, pp, pp, vp, sz, pmp, i32, i32, i32, vp]
@@ -229,6 +231,21 @@ class Context:
             pairs.block_end.ctypes.data, pairs.cand_end.ctypes.data,
             _dev_ptr(d_blocks), nblocks, _dev_ptr(d_cands), ncands, _dev_ptr(d_offsets),
             _dev_ptr(d_pmv), C.byref(params), _dev_ptr(d_sad), _dev_ptr(d_cost), _dev_ptr(d_best)))
+
+    def me_search_dev(self, cur, ref, d_blocks, nblocks, d_preds, d_subset_offsets, nsubsets, params,
+                      d_best, d_pmv=None, d_thresh=None, umh_range=0):
+        """full_pixel_me's search stages for every block (include/b200rdo.h)."""
+        self.check(self.L.b200_me_search_dev(
+            self.h, C.byref(cur), C.byref(ref), _dev_ptr(d_blocks), nblocks, _dev_ptr(d_preds),
+            _dev_ptr(d_subset_offsets), nsubsets, _dev_ptr(d_pmv), _dev_ptr(d_thresh), C.byref(params),
+            umh_range, _dev_ptr(d_best)))
+
+    def me_search_multi_dev(self, pairs, d_blocks, nblocks, d_preds, d_subset_offsets, nsubsets, params,
+                            d_best, d_pmv=None, d_thresh=None, umh_range=0):
+        self.check(self.L.b200_me_search_multi_dev(
+            self.h, pairs.n, C.addressof(pairs.curs), C.addressof(pairs.refs), pairs.block_end.ctypes.data,
+            _dev_ptr(d_blocks), nblocks, _dev_ptr(d_preds), _dev_ptr(d_subset_offsets), nsubsets,
+            _dev_ptr(d_pmv), _dev_ptr(d_thresh), C.byref(params), umh_range, _dev_ptr(d_best)))
 
     def me_subpel_candidates_dev(self, cur, ref, d_blocks, nblocks, d_cands, ncands, params, filter_mode=0,
                                  d_offsets=None, d_pmv=None, d_sad=None, d_cost=None, d_best=None):

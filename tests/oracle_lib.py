@@ -213,6 +213,28 @@ def full_search_blocks(cur: Plane, ref: Plane, blocks, w, h, range_x, range_y, s
     return out
 
 
+def full_pixel_me_blocks(cur: Plane, ref: Plane, blocks, preds, subset_offsets, nsubsets, w, h, lambda_,
+                         pmv=None, thresh=None, umh_range=0, allow_hp=False, threads=0):
+    """full_pixel_me's search stages per block (oracle/me.c: orc_full_pixel_me_blocks)."""
+    L = lib()
+    out = np.zeros(len(blocks), ME_RESULT_DTYPE)
+    w_in_b = 2 * ((cur.width + 7) >> 3)
+    h_in_b = 2 * ((cur.height + 7) >> 3)
+    preds = np.ascontiguousarray(preds)
+    subset_offsets = np.ascontiguousarray(subset_offsets, np.uint32)
+    pm = None if pmv is None else np.ascontiguousarray(pmv, np.int16)
+    th = None if thresh is None else np.ascontiguousarray(thresh, np.uint32)
+    L.orc_full_pixel_me_blocks.restype = None
+    L.orc_full_pixel_me_blocks(
+        C.c_void_p(cur.origin_ptr()), C.c_ssize_t(cur.stride), C.c_void_p(ref.origin_ptr()),
+        C.c_ssize_t(ref.stride), C.c_int(cur.bpp), C.c_int(w_in_b), C.c_int(h_in_b),
+        C.c_void_p(ptr(blocks)), C.c_size_t(len(blocks)), C.c_void_p(ptr(preds) if len(preds) else None),
+        C.c_void_p(ptr(subset_offsets)), C.c_int(nsubsets), C.c_void_p(ptr(pm) if pm is not None else None),
+        C.c_void_p(ptr(th) if th is not None else None), C.c_int(w), C.c_int(h), C.c_uint32(int(lambda_)),
+        C.c_int(int(allow_hp)), C.c_int(umh_range), C.c_void_p(ptr(out)), C.c_int(threads))
+    return out
+
+
 # ---------------------------------------------------------------- forward transform
 TX_SIZES = [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (4, 8), (8, 4), (8, 16), (16, 8),
             (16, 32), (32, 16), (32, 64), (64, 32), (4, 16), (16, 4), (8, 32), (32, 8),
