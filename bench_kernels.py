@@ -161,6 +161,37 @@ def main():
     emit("winner put_8tap + residual + fwd_txfm 16x16 10-bit", nb, "blocks", ms, 2598,
          "SURVEY §8d fused MC->SATD->txfm figure (2598 B/block)")
 
+    # ---- device-side search stages of full_pixel_me (me.rs:692-856), 1080p, 16x16 blocks.
+    # Structured content (low-passed noise displaced by (+6, -3) px + noise) so the walks are real;
+    # predictors scatter within +-8 px of the true motion like neighbouring blocks' vectors do.
+    from scipy.ndimage import uniform_filter
+    base = uniform_filter(rng.integers(0, 256, (H + 64, W + 64)).astype(np.float32), 9)
+    base = (base - base.min()) / (base.max() - base.min()) * 255
+    s_ref = np.rint(base[32:32 + H, 32:32 + W]).astype(np.uint8)
+    s_cur = np.clip(np.rint(base[32 - 3:32 - 3 + H, 32 + 6:32 + 6 + W] + rng.normal(0, 1.5, (H, W))), 0, 255).astype(np.uint8)
+    os_cur, os_ref = O.Plane(W, H, PAD), O.Plane(W, H, PAD)
+    os_cur.fill_from(s_cur)
+    os_ref.fill_from(s_ref)
+    ds_cur, ds_ref = ctx.plane_from_host(s_cur, PAD), ctx.plane_from_host(s_ref, PAD)
+    p_srch = B.me_params(16, 16, W, H, 1600)
+    d_sbest = torch.empty(nb * 16, dtype=torch.uint8, device="cuda")
+    for label, nsub, per, umh_range in (("predictors + diamond (non-extensive)", 1, (10,), 0),
+                                        ("extensive ladder through UMH-24 + hexagon", 3, (1, 5, 4), 24)):
+        counts = np.tile(np.array(per), nb)
+        soffs = np.zeros(nb * nsub + 1, np.uint32)
+        soffs[1:] = np.cumsum(counts)
+        spreds = np.zeros(int(soffs[-1]), B.CAND_DTYPE)
+        smv = (np.array([-3, 6]) + rng.integers(-8, 9, (len(spreds), 2))) * 8
+        spreds["mv_row"], spreds["mv_col"] = smv[:, 0], smv[:, 1]
+        sthresh = np.zeros(nb, np.uint32)                     # never exit early: every stage runs
+        d_sp, d_so, d_st = dev(spreds), dev(soffs), dev(sthresh)
+        ms = timed(lambda: ctx.me_search_dev(ds_cur, ds_ref, d_blocks, nb, d_sp, d_so, nsub, p_srch, d_sbest,
+                                             None, d_st if nsub == 3 else None, umh_range), reps=10)
+        cpu = cpu_rate(lambda: O.full_pixel_me_blocks(os_cur, os_ref, blocks, spreds, soffs, nsub, 16, 16, 1600,
+                                                      None, sthresh if nsub == 3 else None, umh_range, threads=TH), nb)
+        emit(f"me_search 16x16 8-bit: {label}", nb, "blocks", ms, 0,
+             "data-dependent number of SAD evaluations per block (no SURVEY byte figure); one warp per block", cpu)
+
     # ---- intra: 13 modes per 16x16 block
     edges = rng.integers(0, 256, (nb, 257)).astype(np.uint8)
     modes = [(0, 3, 0), (2, 3, 180), (1, 3, 90), (9, 3, 0), (11, 3, 0), (10, 3, 0), (12, 3, 0), (3, 3, 45),

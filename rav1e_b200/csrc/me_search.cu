@@ -22,6 +22,10 @@
 
 #include "common.cuh"
 
+#ifndef B200_SEARCH_MINBLOCKS
+#define B200_SEARCH_MINBLOCKS 6  // CTAs of 4 warps per SM the search kernel is register-capped for (80 regs; 4/5/6 measured: 2.47/2.20/2.15 ms per 8 pairs)
+#endif
+
 namespace {
 
 constexpr unsigned long long kEmptyCost = ~0ull;  // MVCandidateRD::empty(), me.rs:139-146
@@ -81,8 +85,10 @@ __constant__ signed char kSquare[8][2] = {{1, -1}, {1, 0}, {1, 1}, {0, -1}, {0, 
 __constant__ signed char kUmh[16][2] = {{4, -2}, {4, -1}, {4, 0},  {4, 1},   {4, 2},   {2, 3},  {0, 4},  {-2, 3},
                                         {-4, 2}, {-4, 1}, {-4, 0}, {-4, -1}, {-4, -2}, {-2, 3}, {0, -4}, {2, -3}};
 
+constexpr int kOrgRegs = 16;  // org words a lane keeps in registers (blocks up to 512 bytes)
+
 struct BlockCtx {
-  const uint8_t *org;  // block pixel (0,0), bytes
+  const uint8_t *org;   // block pixel (0,0), bytes
   long long org_pitch;  // bytes
   const uint8_t *ref0;
   long long ref_pitch;  // bytes
@@ -90,180 +96,92 @@ struct BlockCtx {
   MvRange rng;
   int p0r, p0c, p1r, p1c;
   int w, h;
+  int log_nw;  // log2(words per block row)
+  int total;   // words per block
+  bool cached;  // the lane's org words are in orgw[]
+  uint32_t orgw[kOrgRegs];
   uint32_t lambda;
   int allow_hp;
 };
 
-// sum |org - ref| over rows sub, sub+8, ... of the block displaced by (dx, dy) full pixels
+// word `i` (row-major, nw words per row) of the w x h area whose pixel (0,0) is at byte address
+// `p0` (any alignment; the row pitch is a multiple of 4 bytes)
+__device__ __forceinline__ uint32_t load_word(const uint8_t *p0, long long pitch, int y, int k) {
+  const uint8_t *p = p0 + (long long)y * pitch + 4 * k;
+  const int sh = (int)((uintptr_t)p & 3);
+  const uint32_t *q = (const uint32_t *)(p - sh);
+  const uint32_t lo = __ldg(q);
+  return sh ? __funnelshift_r(lo, __ldg(q + 1), sh * 8) : lo;
+}
+
+template <typename T>
+__device__ __forceinline__ uint32_t word_sad(uint32_t a, uint32_t b, uint32_t acc) {
+  if (sizeof(T) == 1) return sad4_acc(a, b, acc);
+  const uint32_t d = __vabsdiffu2(a, b);  // two u16 lanes, no carry between them
+  return acc + (d & 0xffffu) + (d >> 16);
+}
+
+// The 8 lanes of a candidate's group walk the block's words 8 at a time (lane = word index mod 8:
+// neighbouring lanes read neighbouring bytes, so one load touches few cache lines).  The word to the
+// right - needed to realign an unaligned reference row - comes from the neighbouring lane by
+// shuffle; only the last lane of a row segment loads it.  Called by all 32 lanes (candidates that
+// are out of range evaluate the zero vector and are discarded by the caller).
 template <typename T>
 __device__ __forceinline__ uint32_t partial_sad(const BlockCtx &c, int dx, int dy, int sub) {
+  const uint8_t *r0 = c.ref0 + (long long)(c.po_y + dy) * c.ref_pitch + (long long)(c.po_x + dx) * (long long)sizeof(T);
+  const int rsh = (int)((uintptr_t)r0 & 3);
+  const uint32_t *rw = (const uint32_t *)(r0 - rsh);
+  const long long rpw = c.ref_pitch >> 2;
+  const int nw = 1 << c.log_nw, seg = nw < 8 ? nw : 8;  // words of one row a group covers per step
   uint32_t acc = 0;
-  if (sizeof(T) == 1) {
-    const uint8_t *r0 = c.ref0 + (long long)(c.po_y + dy) * c.ref_pitch + (c.po_x + dx);
-    const int rsh = (int)((uintptr_t)r0 & 3), osh = (int)((uintptr_t)c.org & 3);
-    // pitches are multiples of 4 bytes (checked on the host), so the shifts hold for every row
-    const uint32_t *rw = (const uint32_t *)(r0 - rsh) + (long long)sub * (c.ref_pitch >> 2);
-    const uint32_t *ow = (const uint32_t *)(c.org - osh) + (long long)sub * (c.org_pitch >> 2);
-    const int nw = c.w >> 2;
-    for (int y = sub; y < c.h; y += 8) {
-      uint32_t rlo = __ldg(rw), olo = __ldg(ow);
-      for (int k = 0; k < nw; k++) {
-        const uint32_t rhi = __ldg(rw + k + 1), ohi = __ldg(ow + k + 1);
-        acc = sad4_acc(__funnelshift_r(rlo, rhi, rsh * 8), __funnelshift_r(olo, ohi, osh * 8), acc);
-        rlo = rhi;
-        olo = ohi;
-      }
-      rw += 2 * c.ref_pitch;  // 8 rows, in words
-      ow += 2 * c.org_pitch;
+  if (c.cached) {
+#pragma unroll
+    for (int j = 0; j < kOrgRegs; j++) {
+      const int i = sub + 8 * j;
+      const bool on = i < c.total;  // uniform per step except in blocks smaller than 8 words
+      const int y = i >> c.log_nw, k = i & (nw - 1);
+      const uint32_t *q = rw + (on ? (long long)y * rpw + k : 0);
+      const uint32_t w0 = __ldg(q);
+      uint32_t w1 = __shfl_down_sync(0xffffffffu, w0, 1);
+      if (rsh && ((k & (seg - 1)) == seg - 1 || !on)) w1 = __ldg(q + 1);
+      if (on) acc = word_sad<T>(__funnelshift_r(w0, w1, rsh * 8), c.orgw[j], acc);
+      if (8 * (j + 1) >= c.total) break;  // uniform
     }
   } else {
-    const uint16_t *r0 = (const uint16_t *)(c.ref0 + (long long)(c.po_y + dy) * c.ref_pitch) + (c.po_x + dx);
-    const uint16_t *o0 = (const uint16_t *)c.org;
-    for (int y = sub; y < c.h; y += 8) {
-      const uint16_t *rr = (const uint16_t *)((const uint8_t *)r0 + (long long)y * c.ref_pitch);
-      const uint16_t *oo = (const uint16_t *)((const uint8_t *)o0 + (long long)y * c.org_pitch);
-      for (int x = 0; x < c.w; x++) {
-        const int d = (int)oo[x] - (int)rr[x];
-        acc += (uint32_t)(d < 0 ? -d : d);
-      }
+    for (int i = sub; i < c.total; i += 8) {  // total is a multiple of 8 here
+      const int y = i >> c.log_nw, k = i & (nw - 1);
+      const uint32_t *q = rw + (long long)y * rpw + k;
+      const uint32_t w0 = __ldg(q);
+      uint32_t w1 = __shfl_down_sync(0xffffffffu, w0, 1);
+      if (rsh && (k & 7) == 7) w1 = __ldg(q + 1);
+      acc = word_sad<T>(__funnelshift_r(w0, w1, rsh * 8), load_word(c.org, c.org_pitch, y, k), acc);
     }
   }
   return acc;
 }
 
-// First-minimum argmin of get_fullpel_mv_rd (me.rs:1386-1409) over candidates gen(0..n): what
-// `for cand { if rd.cost < best.cost { best = rd } }` starting from empty() leaves in `best`.
-// Every lane returns the same result.
-template <typename T, typename Gen>
-__device__ __forceinline__ Best set_best(const BlockCtx &c, int n, Gen gen) {
-  const int lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
-  Best b = best_empty();
-  for (int k0 = 0; k0 < n; k0 += 4) {
-    const int k = k0 + g;
-    int row = 0, col = 0;
-    bool inr = false;
-    if (k < n) {
-      gen(k, row, col);
-      inr = !(col < c.rng.x_min || col > c.rng.x_max || row < c.rng.y_min || row > c.rng.y_max);
-    }
-    uint32_t acc = 0;
-    if (inr) acc = partial_sad<T>(c, col / 8, row / 8, sub);  // trunc toward zero, me.rs:1402-1403
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    if (inr) {
-      const unsigned long long cost =
-          b200_mv_cost(acc, row, col, c.p0r, c.p0c, c.p1r, c.p1c, c.lambda, c.allow_hp);
-      if (cost < b.cost) {
-        b.cost = cost;
-        b.sad = acc;
-        b.row = row;
-        b.col = col;
-        b.idx = k;
-      }
-    }
-  }
-  // the four groups: lowest cost, ties to the lowest index (the serial scan's strict `<`)
-#pragma unroll
-  for (int o = 8; o <= 16; o <<= 1) {
-    Best q;
-    q.cost = __shfl_xor_sync(0xffffffffu, b.cost, o);
-    q.sad = __shfl_xor_sync(0xffffffffu, b.sad, o);
-    q.row = __shfl_xor_sync(0xffffffffu, b.row, o);
-    q.col = __shfl_xor_sync(0xffffffffu, b.col, o);
-    q.idx = __shfl_xor_sync(0xffffffffu, b.idx, o);
-    if (q.cost < b.cost || (q.cost == b.cost && q.idx < b.idx)) b = q;
-  }
-  return b;
-}
-
 __device__ __forceinline__ int s16(int v) { return (int)(short)v; }  // i16 wrap (release builds)
 
-// me.rs:955-998
-template <typename T>
-__device__ __forceinline__ void fullpel_diamond(const BlockCtx &c, Best &cur) {
-  int radius_log2 = 1;
-  for (;;) {
-    const int cr = cur.row, cc = cur.col, sh = radius_log2 + 3;
-    const Best b = set_best<T>(c, 4, [&](int k, int &row, int &col) {
-      row = s16(cr + s16(kDiamond[k][0] * (1 << sh)));
-      col = s16(cc + s16(kDiamond[k][1] * (1 << sh)));
-    });
-    if (cur.cost <= b.cost) {
-      if (radius_log2 == 0) break;
-      radius_log2--;
-    } else {
-      cur = b;
-    }
-  }
-}
-
-// me.rs:1055-1135
-template <typename T>
-__device__ __forceinline__ void hexagon(const BlockCtx &c, Best &cur) {
-  Best b = set_best<T>(c, 6, [&](int k, int &row, int &col) {
-    row = s16(cur.row + kHexagon[k][0] * 8);
-    col = s16(cur.col + kHexagon[k][1] * 8);
-  });
-  int best_idx = b.cost != kEmptyCost ? b.idx : 0;
-  while (b.cost < cur.cost) {
-    cur = b;
-    const int center_idx = best_idx;
-    b = set_best<T>(c, 3, [&](int k, int &row, int &col) {
-      const int i = (center_idx + 5 + k) % 6;
-      row = s16(cur.row + kHexagon[i][0] * 8);
-      col = s16(cur.col + kHexagon[i][1] * 8);
-    });
-    if (b.cost != kEmptyCost) best_idx = (center_idx + 5 + b.idx) % 6;
-  }
-  b = set_best<T>(c, 8, [&](int k, int &row, int &col) {
-    row = s16(cur.row + kSquare[k][0] * 8);
-    col = s16(cur.col + kSquare[k][1] * 8);
-  });
-  if (b.cost < cur.cost) cur = b;
-}
-
-// me.rs:1170-1303 (quirks kept: the first line of the cross steps the ROW component, :1195-1198;
-// the 5x5 stage adds raw {row, col} eighth-pels, :1240-1246)
-template <typename T>
-__device__ __forceinline__ void umh(const BlockCtx &c, Best &cur, int me_range) {
-  int cr = cur.row, cc = cur.col;
-  const int n_row = (me_range + 1) >> 1;         // i = 1, 3, ... <= me_range
-  const int n_col = ((me_range >> 1) + 1) >> 1;  // i = 1, 3, ... <= me_range / 2
-  Best b = set_best<T>(c, 2 * (n_row + n_col), [&](int k, int &row, int &col) {
-    row = cr;
-    col = cc;
-    if (k < 2 * n_row) {
-      const int i = 1 + 2 * (k >> 1);
-      row = s16(cr + s16(((k & 1) ? 8 : -8) * i));
-    } else {
-      const int kk = k - 2 * n_row, i = 1 + 2 * (kk >> 1);
-      col = s16(cc + s16(((kk & 1) ? 8 : -8) * i));
-    }
-  });
-  if (b.cost < cur.cost) cur = b;
-  cr = cur.row, cc = cur.col;
-  b = set_best<T>(c, 24, [&](int k, int &row, int &col) {
-    const int idx = k < 12 ? k : k + 1;  // row-major 5x5 without its centre
-    row = s16(cr + idx / 5 - 2);
-    col = s16(cc + idx % 5 - 2);
-  });
-  if (b.cost < cur.cost) cur = b;
-  cr = cur.row, cc = cur.col;
-  b = set_best<T>(c, 16 * (me_range >> 2), [&](int k, int &row, int &col) {
-    const int i = 1 + (k >> 4), p = k & 15;
-    row = s16(cr + s16(kUmh[p][0] * 8 * i));
-    col = s16(cc + s16(kUmh[p][1] * 8 * i));
-  });
-  if (b.cost < cur.cost) cur = b;
-  hexagon<T>(c, cur);
-}
+// The stages as a state machine with ONE evaluation site: every stage is "evaluate a candidate
+// set, keep its first minimum" (what `for cand { if rd.cost < best.cost { best = rd } }` leaves
+// when started from empty(), me.rs:884-909 and every pattern loop), followed by a transition.
+enum Stage {
+  S_PRED,     // get_best_predictor over a subset                         me.rs:884-909
+  S_DIAMOND,  // fullpel_diamond_search, radius 2 then 1                  me.rs:955-998
+  S_CROSS,    // uneven_multi_hex_search: both lines of the cross         me.rs:1187-1234
+  S_FIVE,     //   5x5 (raw eighth-pel offsets)                           me.rs:1237-1253
+  S_UMH,      //   16-point hexagons x (me_range >> 2) scales             me.rs:1281-1296
+  S_HEX6,     // hexagon_search: first iteration                          me.rs:1070-1083
+  S_HEX3,     //   following iterations (3 new points)                    me.rs:1087-1115
+  S_SQUARE,   //   square refinement                                      me.rs:1118-1132
+  S_DONE
+};
 
 template <typename T>
-__global__ void __launch_bounds__(128) me_search_kernel(const __grid_constant__ SearchArgs a) {
+__global__ void __launch_bounds__(128, B200_SEARCH_MINBLOCKS) me_search_kernel(const __grid_constant__ SearchArgs a) {
   const size_t warp0 = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
   for (size_t blk = warp0; blk < a.nblocks; blk += nwarps) {
     int pi = 0;
     if (a.npairs > 1) {  // first pair with blk < block_end
@@ -295,24 +213,196 @@ __global__ void __launch_bounds__(128) me_search_kernel(const __grid_constant__ 
     }
     c.lambda = a.lambda;
     c.allow_hp = a.allow_hp;
-
-    Best best = best_empty();
-    bool done = false;
-    for (int k = 0; k < a.nsubsets && !done; k++) {
-      const uint32_t lo = a.subset_offsets[blk * a.nsubsets + k];
-      const uint32_t hi = a.subset_offsets[blk * a.nsubsets + k + 1];
-      if (a.nsubsets == 3 && k == 0 && lo == hi) continue;  // `if let Some(median)`, me.rs:774
-      const b200_cand *pp = a.preds + lo;
-      Best r = set_best<T>(c, (int)(hi - lo), [&](int j, int &row, int &col) {
-        const b200_cand q = pp[j];
-        row = q.mv_row;
-        col = q.mv_col;
-      });
-      fullpel_diamond<T>(c, r);
-      if (r.cost < best.cost) best = r;
-      if (a.nsubsets == 3 && best.sad < a.thresh[blk]) done = true;  // me.rs:777-790
+    {
+      const int nw = a.w * (int)sizeof(T) / 4;  // power of two (host-checked)
+      c.log_nw = 31 - __clz(nw);
+      c.total = nw * a.h;
+      c.cached = c.total <= 8 * kOrgRegs;
+      if (c.cached) {
+#pragma unroll
+        for (int j = 0; j < kOrgRegs; j++) {
+          const int i = sub + 8 * j;
+          c.orgw[j] = i < c.total ? load_word(c.org, c.org_pitch, i >> c.log_nw, i & (nw - 1)) : 0u;
+        }
+      }
     }
-    if (a.nsubsets == 3 && !done && a.umh_range > 0 && best.cost != kEmptyCost) umh<T>(c, best, a.umh_range);
+    const int n_row = (a.umh_range + 1) >> 1;         // cross, first line: i = 1, 3, ... <= me_range
+    const int n_col = ((a.umh_range >> 1) + 1) >> 1;  // second line: i = 1, 3, ... <= me_range / 2
+    const uint32_t thresh = a.nsubsets == 3 ? a.thresh[blk] : 0u;
+
+    Best best = best_empty();  // full_pixel_me's `best`
+    Best cur = best_empty();   // the running stage's `current` / `results`
+    int subset = 0, radius_log2 = 1, center_idx = 0, best_idx = 0;
+    int cr = 0, cc = 0;        // centre the running pattern is laid around
+    uint32_t plo = 0;          // first predictor of the running subset
+    int stage = S_DONE, n = 0;
+
+    // pick the next predictor subset (or what follows the last one)
+    auto next_subset = [&]() {
+      while (subset < a.nsubsets) {
+        const uint32_t lo = a.subset_offsets[blk * a.nsubsets + subset];
+        const uint32_t hi = a.subset_offsets[blk * a.nsubsets + subset + 1];
+        if (a.nsubsets == 3 && subset == 0 && lo == hi) {  // `if let Some(median)`, me.rs:774
+          subset++;
+          continue;
+        }
+        plo = lo;
+        n = (int)(hi - lo);
+        stage = S_PRED;
+        return;
+      }
+      if (a.nsubsets == 3 && a.umh_range > 0 && best.cost != kEmptyCost) {  // me.rs:794-812
+        cur = best;
+        cr = cur.row, cc = cur.col;
+        n = 2 * (n_row + n_col);
+        stage = S_CROSS;
+      } else {
+        stage = S_DONE;
+      }
+    };
+    next_subset();
+
+    while (stage != S_DONE) {
+      // ---- evaluate the stage's candidate set, four candidates at a time (8 lanes each)
+      Best b = best_empty();
+      for (int k0 = 0; k0 < n; k0 += 4) {
+        const int k = k0 + g;
+        int row = cr, col = cc;
+        switch (stage) {
+          case S_PRED:
+            if (k < n) {
+              const b200_cand q = a.preds[plo + k];
+              row = q.mv_row, col = q.mv_col;
+            }
+            break;
+          case S_DIAMOND:
+            row = s16(cr + s16(kDiamond[k & 3][0] * (8 << radius_log2)));
+            col = s16(cc + s16(kDiamond[k & 3][1] * (8 << radius_log2)));
+            break;
+          case S_CROSS:  // quirk kept: the first ("horizontal") line steps the ROW, me.rs:1195-1198
+            if (k < 2 * n_row) {
+              row = s16(cr + s16(((k & 1) ? 8 : -8) * (1 + 2 * (k >> 1))));
+            } else {
+              const int kk = k - 2 * n_row;
+              col = s16(cc + s16(((kk & 1) ? 8 : -8) * (1 + 2 * (kk >> 1))));
+            }
+            break;
+          case S_FIVE: {  // row-major 5x5 without its centre, raw {row, col} (me.rs:1240-1246)
+            const int idx = k < 12 ? k : k + 1;
+            row = s16(cr + idx / 5 - 2);
+            col = s16(cc + idx % 5 - 2);
+            break;
+          }
+          case S_UMH:
+            row = s16(cr + s16(kUmh[k & 15][0] * 8 * (1 + (k >> 4))));
+            col = s16(cc + s16(kUmh[k & 15][1] * 8 * (1 + (k >> 4))));
+            break;
+          case S_HEX6:
+            row = s16(cr + kHexagon[k % 6][0] * 8);
+            col = s16(cc + kHexagon[k % 6][1] * 8);
+            break;
+          case S_HEX3: {
+            const int i = (center_idx + 5 + k) % 6;
+            row = s16(cr + kHexagon[i][0] * 8);
+            col = s16(cc + kHexagon[i][1] * 8);
+            break;
+          }
+          default:  // S_SQUARE
+            row = s16(cr + kSquare[k & 7][0] * 8);
+            col = s16(cc + kSquare[k & 7][1] * 8);
+            break;
+        }
+        // get_fullpel_mv_rd, me.rs:1386-1409
+        const bool inr = k < n && !(col < c.rng.x_min || col > c.rng.x_max || row < c.rng.y_min || row > c.rng.y_max);
+        uint32_t acc = partial_sad<T>(c, inr ? col / 8 : 0, inr ? row / 8 : 0, sub);  // trunc toward zero
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (inr) {
+          const unsigned long long cost =
+              b200_mv_cost(acc, row, col, c.p0r, c.p0c, c.p1r, c.p1c, c.lambda, c.allow_hp);
+          if (cost < b.cost) {
+            b.cost = cost;
+            b.sad = acc;
+            b.row = row;
+            b.col = col;
+            b.idx = k;
+          }
+        }
+      }
+      // the four groups: lowest cost, ties to the lowest index (the serial scan's strict `<`)
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        Best q;
+        q.cost = __shfl_xor_sync(0xffffffffu, b.cost, o);
+        q.sad = __shfl_xor_sync(0xffffffffu, b.sad, o);
+        q.row = __shfl_xor_sync(0xffffffffu, b.row, o);
+        q.col = __shfl_xor_sync(0xffffffffu, b.col, o);
+        q.idx = __shfl_xor_sync(0xffffffffu, b.idx, o);
+        if (q.cost < b.cost || (q.cost == b.cost && q.idx < b.idx)) b = q;
+      }
+
+      // ---- transition (warp-uniform: every lane holds the same b / cur / best)
+      switch (stage) {
+        case S_PRED:
+          cur = b;
+          radius_log2 = 1;
+          stage = S_DIAMOND;
+          n = 4;
+          break;
+        case S_DIAMOND:
+          if (cur.cost <= b.cost) {
+            if (radius_log2 == 0) {                                  // end of try_cands, me.rs:750-752
+              if (cur.cost < best.cost) best = cur;
+              if (a.nsubsets == 3 && best.sad < thresh) {            // me.rs:777-790
+                stage = S_DONE;
+              } else {
+                subset++;
+                next_subset();
+              }
+            } else {
+              radius_log2--;
+            }
+          } else {
+            cur = b;
+          }
+          break;
+        case S_CROSS:
+          if (b.cost < cur.cost) cur = b;
+          stage = S_FIVE;
+          n = 24;
+          break;
+        case S_FIVE:
+          if (b.cost < cur.cost) cur = b;
+          stage = S_UMH;
+          n = 16 * (a.umh_range >> 2);
+          break;
+        case S_UMH:
+          if (b.cost < cur.cost) cur = b;
+          stage = S_HEX6;
+          n = 6;
+          break;
+        case S_HEX6:
+        case S_HEX3:
+          if (b.cost != kEmptyCost) best_idx = stage == S_HEX6 ? b.idx : (center_idx + 5 + b.idx) % 6;
+          if (b.cost < cur.cost) {
+            cur = b;
+            center_idx = best_idx;
+            stage = S_HEX3;
+            n = 3;
+          } else {
+            stage = S_SQUARE;
+            n = 8;
+          }
+          break;
+        default:  // S_SQUARE: end of hexagon_search = end of uneven_multi_hex_search
+          if (b.cost < cur.cost) cur = b;
+          best = cur;
+          stage = S_DONE;
+          break;
+      }
+      cr = cur.row, cc = cur.col;
+    }
     if (lane == 0) {
       b200_me_result res;
       res.cost = best.cost;
@@ -333,16 +423,16 @@ int search_pairs(b200_ctx *ctx, size_t npairs, const b200_plane *curs, const b20
   B200_REQUIRE(ctx, p != nullptr && npairs >= 1 && curs && refs && block_end, "NULL params / plane pair table");
   B200_REQUIRE(ctx, nsubsets == 1 || nsubsets == 3, "nsubsets must be 1 (all_mvs) or 3 (median|b|c), got %d", nsubsets);
   B200_REQUIRE(ctx, nsubsets == 1 || d_thresh != nullptr, "the extensive ladder needs per-block thresholds");
-  B200_REQUIRE(ctx, p->w > 0 && p->h > 0 && p->w <= 128 && p->h <= 128 && (p->w & 3) == 0,
-               "block size %dx%d out of range (<= 128, width multiple of 4)", p->w, p->h);
+  B200_REQUIRE(ctx, p->w >= 4 && p->h > 0 && p->w <= 128 && p->h <= 128 && (p->w & (p->w - 1)) == 0,
+               "block size %dx%d out of range (<= 128, width a power of two >= 4)", p->w, p->h);
   B200_REQUIRE(ctx, umh_range >= 0 && umh_range <= 64, "umh_range %d out of range", umh_range);
   B200_REQUIRE(ctx, nblocks < (1ull << 32), "nblocks must fit 32 bits");
   for (size_t k = 0; k < npairs; k++) {
     B200_REQUIRE(ctx, curs[k].data && refs[k].data, "pair %zu: plane has no device memory", k);
     B200_REQUIRE(ctx, curs[k].bpp == refs[k].bpp && curs[k].bpp == curs[0].bpp && (curs[0].bpp == 1 || curs[0].bpp == 2),
                  "plane pairs must share bpp (1 or 2)");
-    B200_REQUIRE(ctx, curs[0].bpp == 2 || ((curs[k].stride & 3) == 0 && (refs[k].stride & 3) == 0),
-                 "8-bit planes need a row pitch that is a multiple of 4");
+    B200_REQUIRE(ctx, ((curs[k].stride * curs[0].bpp) & 3) == 0 && ((refs[k].stride * curs[0].bpp) & 3) == 0,
+                 "planes need a row pitch that is a multiple of 4 bytes");
     B200_REQUIRE(ctx, block_end[k] >= (k ? block_end[k - 1] : 0), "pair %zu: block ends must be non-decreasing", k);
   }
   B200_REQUIRE(ctx, block_end[npairs - 1] == nblocks, "last pair must end at nblocks");
