@@ -262,6 +262,34 @@ int b200_me_full_search_batch(b200_ctx *ctx, const b200_host_plane *cur,
                               size_t nblocks, const b200_me_params *params, int range_x,
                               int range_y, int step, b200_me_result *best);
 
+/* ---------------------------------------------------------------- RDO distortion kernels
+ * get_weighted_sse (dist.rs:234-283; asm `rav1e_weighted_sse_{W}x{H}`, asm/x86/dist/sse.rs:18-35)
+ * and cdef_dist_kernel (dist.rs:302-372; asm `rav1e_cdef_dist_kernel_{W}x{H}`,
+ * asm/x86/dist/cdef_dist.rs:18-52) — the distortion terms of compute_distortion / sse_wxh /
+ * cdef_dist_wxh (rdo.rs:142-330).
+ *
+ * Per-call forms: HOST pointers, BYTE strides, like the asm symbols.  `scale`: one Q14
+ * DistortionScale per 4x4 chunk, rows `scale_stride_bytes` apart.  b200_cdef_dist_kernel returns
+ * apply_ssim_boost(sse, svar, dvar) (activity.rs:159-186) and, when ret != NULL, the asm kernels'
+ * raw triple {svar, dvar, sse}. */
+uint64_t b200_weighted_sse(const void *src, ptrdiff_t src_stride, const void *dst, ptrdiff_t dst_stride,
+                           const uint32_t *scale, ptrdiff_t scale_stride_bytes, int w, int h, int bpp);
+uint32_t b200_cdef_dist_kernel(const void *src, ptrdiff_t src_stride, const void *dst, ptrdiff_t dst_stride,
+                               int w, int h, int bit_depth, uint32_t ret[3]);
+/* Batched, device-resident: block i = the w x h area at d_blocks[i] of both planes.
+ * d_scale: one DistortionScale per 4x4 chunk of the PLANE (chunk (cx, cy) at
+ * d_scale[cy * scale_stride + cx], entries); blocks sit on multiples of 4 pixels.
+ * d_out[i] = get_weighted_sse of block i. */
+int b200_weighted_sse_dev(b200_ctx *ctx, const b200_plane *src1, const b200_plane *src2,
+                          const b200_block *d_blocks, size_t nblocks, int w, int h,
+                          const uint32_t *d_scale, size_t scale_stride, uint64_t *d_out);
+/* cdef_dist_kernel for many blocks (w, h <= 8; cdef_dist_wxh walks a block in 8x8 steps,
+ * rdo.rs:152-170).  d_out[i] (may be NULL) = the boosted distortion, d_raw[3*i..] (may be NULL) =
+ * {svar, dvar, sse}. */
+int b200_cdef_dist_dev(b200_ctx *ctx, const b200_plane *src, const b200_plane *dst,
+                       const b200_block *d_blocks, size_t nblocks, int w, int h, int bit_depth,
+                       uint32_t *d_out, uint32_t *d_raw);
+
 /* ------------------------------------------------ forward transform (transform/forward.rs)
  * The reference has no extern-C symbol here: the boundary is the generic Rust fn
  *   forward_transform<T: Coefficient>(input: &[i16], output: &mut [MaybeUninit<T>],

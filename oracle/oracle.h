@@ -108,6 +108,21 @@ void orc_full_pixel_me_blocks(const void *cur0, ptrdiff_t cur_stride, const void
                               const uint32_t *thresh, int w, int h, uint32_t lambda, int allow_hp,
                               int umh_range, orc_me_result *out, int threads);
 
+/* ------------------------------------------------- RDO distortion (dist.rs, activity.rs) */
+/* get_weighted_sse dist.rs:234-283: one DistortionScale (Q14) per 4x4 chunk. */
+uint64_t orc_weighted_sse_u8(const uint8_t *src1, ptrdiff_t stride1, const uint8_t *src2,
+                             ptrdiff_t stride2, const uint32_t *scale, size_t scale_stride, int w, int h);
+uint64_t orc_weighted_sse_u16(const uint16_t *src1, ptrdiff_t stride1, const uint16_t *src2,
+                              ptrdiff_t stride2, const uint32_t *scale, size_t scale_stride, int w, int h);
+/* cdef_dist_kernel dist.rs:302-372 (w, h <= 8); raw (may be NULL) receives {svar, dvar, sse},
+ * what the asm kernels return (asm/x86/dist/cdef_dist.rs:18-24). */
+uint32_t orc_cdef_dist_kernel_u8(const uint8_t *src, ptrdiff_t ss, const uint8_t *dst, ptrdiff_t ds,
+                                 int w, int h, int bit_depth, uint32_t raw[3]);
+uint32_t orc_cdef_dist_kernel_u16(const uint16_t *src, ptrdiff_t ss, const uint16_t *dst, ptrdiff_t ds,
+                                  int w, int h, int bit_depth, uint32_t raw[3]);
+uint32_t orc_apply_ssim_boost(uint32_t input, uint32_t svar, uint32_t dvar, int bit_depth);
+uint64_t orc_distortion_scale_mul(uint32_t scale, uint64_t dist);
+
 /* -------------------------------------------------------------- transform/ */
 /* forward.rs:71-161.  coeff_is_i32: 0 -> int16_t out (8-bit pixels), 1 -> int32_t out. */
 int orc_valid_av1_transform(int tx_size, int tx_type);

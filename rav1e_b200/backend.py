@@ -119,6 +119,12 @@ def lib():
             f.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t] + extra
             f.restype = u32
     L.b200_me_candidates_dev.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
+    L.b200_weighted_sse.restype = C.c_uint64
+    L.b200_weighted_sse.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t, vp, C.c_ssize_t, i32, i32, i32]
+    L.b200_cdef_dist_kernel.restype = u32
+    L.b200_cdef_dist_kernel.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t, i32, i32, i32, vp]
+    L.b200_weighted_sse_dev.argtypes = [vp, pp, pp, vp, sz, i32, i32, vp, sz, vp]
+    L.b200_cdef_dist_dev.argtypes = [vp, pp, pp, vp, sz, i32, i32, i32, vp, vp]
     L.b200_me_search_dev.argtypes = [vp, pp, pp, vp, sz, vp, vp, i32, vp, vp, pmp, i32, vp]
     L.b200_me_search_multi_dev.argtypes = [vp, sz, vp, vp, vp, vp, sz, vp, vp, i32, vp, vp, pmp, i32, vp]
     L.b200_me_candidates_multi_dev.argtypes = [vp, sz, vp, vp, vp, vp, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
@@ -263,6 +269,15 @@ class Context:
         self.check(self.L.b200_block_residual_dev(self.h, C.byref(cur), C.byref(ref),
                                                   _dev_ptr(d_blocks), nblocks, _dev_ptr(d_mv_src),
                                                   w, h, _dev_ptr(d_out)))
+
+    # ---- RDO distortion
+    def weighted_sse_dev(self, src1, src2, d_blocks, n, w, h, d_scale, scale_stride, d_out):
+        self.check(self.L.b200_weighted_sse_dev(self.h, C.byref(src1), C.byref(src2), _dev_ptr(d_blocks), n,
+                                                w, h, _dev_ptr(d_scale), scale_stride, _dev_ptr(d_out)))
+
+    def cdef_dist_dev(self, src, dst, d_blocks, n, w, h, bit_depth, d_out=None, d_raw=None):
+        self.check(self.L.b200_cdef_dist_dev(self.h, C.byref(src), C.byref(dst), _dev_ptr(d_blocks), n, w, h,
+                                             bit_depth, _dev_ptr(d_out), _dev_ptr(d_raw)))
 
     # ---- motion compensation
     def mc_blocks_dev(self, ref, d_blocks, d_mvs, n, w, h, mode_x, mode_y, bit_depth, xdec, ydec,
