@@ -424,7 +424,8 @@ def run_e2e(ctx0, blocks, args):
     import torch
     from rav1e_b200 import backend as B
     nb = len(blocks)
-    Fe, NCTX = 12, 3
+    NCTX = int(os.environ.get("B200_E2E_CONTEXTS", "3"))
+    Fe = 4 * NCTX
     pinned = lambda n, dt=np.uint8: torch.empty(n, dtype=torch.uint8).pin_memory().numpy().view(dt)
     ctxs = [B.Context(ctx0.device) for _ in range(NCTX)]
     slots = []
@@ -448,10 +449,11 @@ def run_e2e(ctx0, blocks, args):
         hc[:], hr[:] = cur_img[PAD:PAD + H, PAD:PAD + W], ref_img[PAD:PAD + H, PAD:PAD + W]
         c, offs = cand_list(nb, CAND_SAD, 900 + f)
         c2, offs2 = cand_list(nb, CAND_SATD, 1900 + f)
-        hcand = pinned(c.nbytes).view(B.CAND_DTYPE)
-        hcand[:] = c
-        hcand2 = pinned(c2.nbytes).view(B.CAND_DTYPE)
-        hcand2[:] = c2
+        # candidates travel as MotionVector lists (row, col: 4 B each); the CSR names the block
+        hcand = pinned(len(c) * 4).view(np.int16).reshape(len(c), 2)
+        hcand[:, 0], hcand[:, 1] = c["mv_row"], c["mv_col"]
+        hcand2 = pinned(len(c2) * 4).view(np.int16).reshape(len(c2), 2)
+        hcand2[:, 0], hcand2[:, 1] = c2["mv_row"], c2["mv_col"]
         hoffs, hoffs2 = pinned(offs.nbytes).view(np.uint32), pinned(offs2.nbytes).view(np.uint32)
         hoffs[:], hoffs2[:] = offs, offs2
         best = pinned(nb * 16).view(B.ME_RESULT_DTYPE)
@@ -475,8 +477,8 @@ def run_e2e(ctx0, blocks, args):
             hc, hr, c, c2, o, o2, best, best2, coef = frames[f]
             cx.plane_upload(pc, hc)
             cx.plane_upload(pr, hr)
-            cx.me_candidates_resident(qc, qr, hblocks, c, p_sad, o, (None, None, best))
-            cx.me_candidates_resident(qc, qr, hblocks, c2, p_satd, o2, (None, None, best2))
+            cx.me_mvs_resident(qc, qr, hblocks, c, p_sad, o, (None, None, best))
+            cx.me_mvs_resident(qc, qr, hblocks, c2, p_satd, o2, (None, None, best2))
             cx.fwd_txfm_residual_resident(qc, qr, hblocks, best, coef, 2, 0, 8)
             nb_h2d += hc.nbytes + hr.nbytes + c.nbytes + c2.nbytes + 3 * hblocks.nbytes + o.nbytes + o2.nbytes + best.nbytes
             nb_d2h += best.nbytes + best2.nbytes + coef.nbytes
@@ -497,11 +499,25 @@ def run_e2e(ctx0, blocks, args):
     dt = time.perf_counter() - t0
     launches = sum(cx.launches for cx in ctxs) - l0
     units = Fe * nb * (CAND_SAD + CAND_SATD + 1)
+    # what the link itself sustains on this box: pinned host -> device, 256 MB, CUDA events
+    big = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    dbig = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    dbig.copy_(big, non_blocking=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(4):
+        dbig.copy_(big, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 4 * big.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    del big, dbig
     res = {"value": units * reps / dt, "unit": "blocks/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "frames_per_step": Fe, "kernel_launches_per_step": launches // reps,
-           "api": "per frame: b200_plane_upload x2 + b200_me_candidates_resident x2 (winners out) + "
-                  "b200_fwd_txfm_residual_resident (coefficients out); 3 contexts in async mode, one host "
-                  "thread each"}
+           "h2d_GBps_achieved": h2d * reps / dt / 1e9, "h2d_GBps_link_measured": h2d_gbs,
+           "api": "per frame: b200_plane_upload x2 + b200_me_mvs_resident x2 (MotionVector lists in, winners "
+                  f"out) + b200_fwd_txfm_residual_resident (coefficients out); {NCTX} contexts in async mode, "
+                  "one host thread each"}
     pool.shutdown()
     for c, pl in zip(ctxs, slots):
         for p, q in pl:

@@ -257,6 +257,15 @@ int b200_me_candidates_resident(b200_ctx *ctx, const b200_plane *cur, const b200
                                 size_t ncands, const uint32_t *cand_offsets, const int16_t *pmv,
                                 const b200_me_params *params, uint32_t *sad, uint64_t *cost,
                                 b200_me_result *best);
+/* The same with the candidates as plain MotionVector lists: mvs[2*i] = row, mvs[2*i+1] = col of
+ * candidate i (1/8 pel), the lists of consecutive blocks concatenated and delimited by
+ * cand_offsets (required) — the `&[MotionVector]` a search stage holds per block, 4 bytes per
+ * candidate over PCIe instead of 8. */
+int b200_me_mvs_resident(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                         const b200_block *blocks, size_t nblocks, const int16_t *mvs, size_t ncands,
+                         const uint32_t *cand_offsets, const int16_t *pmv,
+                         const b200_me_params *params, uint32_t *sad, uint64_t *cost,
+                         b200_me_result *best);
 int b200_me_full_search_batch(b200_ctx *ctx, const b200_host_plane *cur,
                               const b200_host_plane *ref, const b200_block *blocks,
                               size_t nblocks, const b200_me_params *params, int range_x,

@@ -133,6 +133,7 @@ def lib():
     L.b200_block_residual_dev.argtypes = [vp, pp, pp, vp, sz, vp, i32, i32, vp]
     L.b200_me_candidates_batch.argtypes = [vp, php, php, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
     L.b200_me_candidates_resident.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
+    L.b200_me_mvs_resident.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
     L.b200_fwd_txfm_residual_resident.argtypes = [vp, pp, pp, vp, sz, vp, vp, i32, i32, i32]
     L.b200_me_full_search_batch.argtypes = [vp, php, php, vp, sz, pmp, i32, i32, i32, vp]
     L.b200_valid_av1_transform.argtypes = [i32, i32]
@@ -375,6 +376,14 @@ class Context:
             self.h, C.byref(cur), C.byref(ref), _np_ptr(blocks), len(blocks), _np_ptr(cands),
             len(cands), _np_ptr(offsets), _np_ptr(pmv), C.byref(params), _np_ptr(sad), _np_ptr(cost),
             _np_ptr(best)))
+
+    def me_mvs_resident(self, cur, ref, blocks, mvs, params, offsets, out, pmv=None):
+        """Like me_candidates_resident with the candidates as an (n, 2) int16 array of
+        (row, col) MotionVectors; the CSR `offsets` names each candidate's block."""
+        sad, cost, best = out
+        self.check(self.L.b200_me_mvs_resident(
+            self.h, C.byref(cur), C.byref(ref), _np_ptr(blocks), len(blocks), _np_ptr(mvs), len(mvs),
+            _np_ptr(offsets), _np_ptr(pmv), C.byref(params), _np_ptr(sad), _np_ptr(cost), _np_ptr(best)))
 
     def fwd_txfm_residual_resident(self, cur, ref, blocks, mv_src, out, tx_size, tx_type, bd):
         self.check(self.L.b200_fwd_txfm_residual_resident(

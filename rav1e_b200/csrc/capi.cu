@@ -196,20 +196,59 @@ __global__ void pad_plane_kernel(T *p0, int stride, int width, int height, int p
   }
 }
 
+// The same from a packed copy of the visible area (row pitch = width): every pixel of the padded
+// plane, border included, is written from `packed` in one pass.
+template <typename T>
+__global__ void unpack_pad_plane_kernel(T *p0, int stride, int width, int height, int pad, const T *packed) {
+  const int total_w = width + 2 * pad;
+  const int total_h = height + 2 * pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+       i < (long long)total_w * total_h; i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / total_w) - pad;
+    const int x = (int)(i % total_w) - pad;
+    const int sx = min(max(x, 0), width - 1);
+    const int sy = min(max(y, 0), height - 1);
+    p0[(long long)y * stride + x] = packed[(long long)sy * width + sx];
+  }
+}
+
 extern "C" int b200_plane_upload(b200_ctx *ctx, const b200_plane *p, const void *host,
                                  ptrdiff_t host_stride_bytes) {
   B200_REQUIRE(ctx, ctx && p && host && p->data, "b200_plane_upload: NULL argument");
-  B200_CUDA(ctx, cudaMemcpy2DAsync(p->data, (size_t)p->stride * p->bpp, host,
-                                   (size_t)host_stride_bytes, (size_t)p->width * p->bpp,
-                                   p->height, cudaMemcpyHostToDevice, ctx->stream));
-  if (p->pad > 0) {
-    if (p->bpp == 1)
-      pad_plane_kernel<uint8_t><<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(
-          (uint8_t *)p->data, p->stride, p->width, p->height, p->pad);
-    else
-      pad_plane_kernel<uint16_t><<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(
-          (uint16_t *)p->data, p->stride, p->width, p->height, p->pad);
-    B200_LAUNCH_CHECK(ctx);
+  B200_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t row_bytes = (size_t)p->width * p->bpp;
+  if ((size_t)host_stride_bytes == row_bytes) {
+    // contiguous source: ONE linear copy (a pitched copy is a DMA descriptor per row and reaches a
+    // fraction of the link rate), then unpack + replicate the border on the device
+    void *packed = nullptr;
+    const size_t bytes = row_bytes * p->height;
+    B200_CUDA(ctx, cudaMallocAsync(&packed, bytes, ctx->stream));
+    cudaError_t e = cudaMemcpyAsync(packed, host, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+      if (p->bpp == 1)
+        unpack_pad_plane_kernel<uint8_t><<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(
+            (uint8_t *)p->data, p->stride, p->width, p->height, p->pad, (const uint8_t *)packed);
+      else
+        unpack_pad_plane_kernel<uint16_t><<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(
+            (uint16_t *)p->data, p->stride, p->width, p->height, p->pad, (const uint16_t *)packed);
+      ctx->launches++;
+      e = cudaGetLastError();
+    }
+    cudaFreeAsync(packed, ctx->stream);
+    B200_CUDA(ctx, e);
+  } else {
+    B200_CUDA(ctx, cudaMemcpy2DAsync(p->data, (size_t)p->stride * p->bpp, host,
+                                     (size_t)host_stride_bytes, row_bytes, p->height,
+                                     cudaMemcpyHostToDevice, ctx->stream));
+    if (p->pad > 0) {
+      if (p->bpp == 1)
+        pad_plane_kernel<uint8_t><<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(
+            (uint8_t *)p->data, p->stride, p->width, p->height, p->pad);
+      else
+        pad_plane_kernel<uint16_t><<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(
+            (uint16_t *)p->data, p->stride, p->width, p->height, p->pad);
+      B200_LAUNCH_CHECK(ctx);
+    }
   }
   if (!ctx->async_batch) B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return B200_OK;

@@ -62,10 +62,28 @@ struct Carver {
 }  // namespace
 
 // Host descriptors in / host results out; planes either host (copied) or device-resident.
+// MotionVector lists (4 bytes per candidate, the block implied by the CSR) -> b200_cand records.
+__global__ void expand_mvs_kernel(const short2 *mvs, const uint32_t *offs, size_t nblocks, b200_cand *out) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+  for (size_t b = warp0; b < nblocks; b += nwarps) {
+    const uint32_t lo = offs[b], hi = offs[b + 1];
+    for (uint32_t i = lo + lane; i < hi; i += 32) {
+      const short2 m = mvs[i];  // {row, col}
+      b200_cand c;
+      c.block = (uint32_t)b;
+      c.mv_row = m.x;
+      c.mv_col = m.y;
+      out[i] = c;
+    }
+  }
+}
+
 static int me_candidates_host_impl(b200_ctx *ctx, const b200_host_plane *cur,
                                    const b200_host_plane *ref, const b200_plane *rcur,
                                    const b200_plane *rref, const b200_block *blocks,
-                                   size_t nblocks, const b200_cand *cands, size_t ncands,
+                                   size_t nblocks, const b200_cand *cands, const int16_t *mvs, size_t ncands,
                                    const uint32_t *cand_offsets, const int16_t *pmv,
                                    const b200_me_params *params, uint32_t *sad,
                                    uint64_t *cost, b200_me_result *best) {
@@ -76,7 +94,8 @@ static int me_candidates_host_impl(b200_ctx *ctx, const b200_host_plane *cur,
   } else {
     B200_REQUIRE(ctx, rcur->data && rref && rref->data, "bad resident planes");
   }
-  B200_REQUIRE(ctx, params && blocks && (cands || !ncands), "NULL params/blocks/cands");
+  B200_REQUIRE(ctx, params && blocks && (cands || mvs || !ncands), "NULL params/blocks/cands");
+  B200_REQUIRE(ctx, !mvs || cand_offsets, "MotionVector lists need cand_offsets (the CSR names the block)");
   B200_REQUIRE(ctx, best == nullptr || cand_offsets != nullptr, "best needs cand_offsets");
   B200_CUDA(ctx, cudaSetDevice(ctx->device));
 
@@ -86,7 +105,7 @@ static int me_candidates_host_impl(b200_ctx *ctx, const b200_host_plane *cur,
   size_t total = cur_bytes + ref_bytes + nblocks * sizeof(b200_block) + ncands * sizeof(b200_cand) +
                  (cand_offsets ? (nblocks + 1) * 4 : 0) + (pmv ? nblocks * 8 : 0) +
                  (sad ? ncands * 4 : 0) + (cost ? ncands * 8 : 0) +
-                 (best ? nblocks * sizeof(b200_me_result) : 0) + 16 * 256;
+                 (best ? nblocks * sizeof(b200_me_result) : 0) + (mvs ? ncands * 4 : 0) + 16 * 256;
   // leave room for the generic path's internal cost/sad scratch (b200_reserve_dwork is
   // grow-only and shared): carve our buffers from a private allocation instead.
   void *dbase = nullptr;
@@ -103,6 +122,7 @@ static int me_candidates_host_impl(b200_ctx *ctx, const b200_host_plane *cur,
   }
   b200_block *d_blocks = (b200_block *)c.take(nblocks * sizeof(b200_block));
   b200_cand *d_cands = (b200_cand *)c.take(ncands * sizeof(b200_cand));
+  short2 *d_mvs = mvs ? (short2 *)c.take(ncands * 4) : nullptr;
   uint32_t *d_offs = cand_offsets ? (uint32_t *)c.take((nblocks + 1) * 4) : nullptr;
   int16_t *d_pmv = pmv ? (int16_t *)c.take(nblocks * 8) : nullptr;
   uint32_t *d_sad = sad ? (uint32_t *)c.take(ncands * 4) : nullptr;
@@ -119,8 +139,17 @@ static int me_candidates_host_impl(b200_ctx *ctx, const b200_host_plane *cur,
     return fail(b200_fail(ctx, B200_ERR_CUDA, "H2D copy failed: %s",                           \
                           cudaGetErrorString(cudaGetLastError())));
   H2D(d_blocks, blocks, nblocks * sizeof(b200_block));
-  H2D(d_cands, cands, ncands * sizeof(b200_cand));
+  if (d_mvs) {
+    H2D(d_mvs, mvs, ncands * 4);
+  } else {
+    H2D(d_cands, cands, ncands * sizeof(b200_cand));
+  }
   if (d_offs) H2D(d_offs, cand_offsets, (nblocks + 1) * 4);
+  if (d_mvs && ncands) {
+    const int grid = (int)std::min<size_t>((nblocks + 7) / 8, (size_t)ctx->num_sms * 16);
+    expand_mvs_kernel<<<grid, 256, 0, ctx->stream>>>(d_mvs, d_offs, nblocks, d_cands);
+    ctx->launches++;
+  }
   if (d_pmv) H2D(d_pmv, pmv, nblocks * 8);
 #undef H2D
   st = b200_me_candidates_dev(ctx, &dcur, &dref, d_blocks, nblocks, d_cands, ncands, d_offs, d_pmv,
@@ -146,7 +175,7 @@ extern "C" int b200_me_candidates_batch(b200_ctx *ctx, const b200_host_plane *cu
                                         const uint32_t *cand_offsets, const int16_t *pmv,
                                         const b200_me_params *params, uint32_t *sad,
                                         uint64_t *cost, b200_me_result *best) {
-  return me_candidates_host_impl(ctx, cur, ref, nullptr, nullptr, blocks, nblocks, cands, ncands,
+  return me_candidates_host_impl(ctx, cur, ref, nullptr, nullptr, blocks, nblocks, cands, nullptr, ncands,
                                  cand_offsets, pmv, params, sad, cost, best);
 }
 
@@ -158,7 +187,19 @@ extern "C" int b200_me_candidates_resident(b200_ctx *ctx, const b200_plane *cur,
                                            uint64_t *cost, b200_me_result *best) {
   B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
   B200_REQUIRE(ctx, cur && ref, "NULL planes");
-  return me_candidates_host_impl(ctx, nullptr, nullptr, cur, ref, blocks, nblocks, cands, ncands,
+  return me_candidates_host_impl(ctx, nullptr, nullptr, cur, ref, blocks, nblocks, cands, nullptr, ncands,
+                                 cand_offsets, pmv, params, sad, cost, best);
+}
+
+extern "C" int b200_me_mvs_resident(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                                    const b200_block *blocks, size_t nblocks, const int16_t *mvs,
+                                    size_t ncands, const uint32_t *cand_offsets, const int16_t *pmv,
+                                    const b200_me_params *params, uint32_t *sad, uint64_t *cost,
+                                    b200_me_result *best) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  B200_REQUIRE(ctx, cur && ref, "NULL planes");
+  B200_REQUIRE(ctx, mvs || !ncands, "NULL mvs");
+  return me_candidates_host_impl(ctx, nullptr, nullptr, cur, ref, blocks, nblocks, nullptr, mvs, ncands,
                                  cand_offsets, pmv, params, sad, cost, best);
 }
 

@@ -24,6 +24,9 @@
 
 #include "common.cuh"
 
+#ifndef B200_WARP_SATD_MINBLOCKS
+#define B200_WARP_SATD_MINBLOCKS 1  // register cap of the warp-per-block SATD kernel (CTAs of 8 warps per SM)
+#endif
 #ifndef B200_SAD_THREADS
 #define B200_SAD_THREADS 256  // CTA size of the SAD instantiations of the grouped kernel
 #endif
@@ -990,7 +993,7 @@ __global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 
 // block, so org reads are broadcasts), cost + first-min argmin by REDUX over the packed key.  No
 // shared memory, no barriers.
 template <int W, int H, bool SATD>
-__global__ void __launch_bounds__(256) me_cand_warp_u8(const __grid_constant__ MeArgs a) {
+__global__ void __launch_bounds__(256, SATD ? B200_WARP_SATD_MINBLOCKS : 1) me_cand_warp_u8(const __grid_constant__ MeArgs a) {
   constexpr int S = (W < 8 || H < 8) ? 4 : 8;
   constexpr int NCH = SATD ? (W / S) * (H / S) : 1;
   constexpr int TPC = NCH < 32 ? NCH : 32;

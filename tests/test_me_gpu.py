@@ -298,6 +298,30 @@ def test_candidate_list_unaligned_block_columns(hint, dx):
         c.plane_free(pl)
 
 
+def test_mv_list_resident_equals_candidate_records():
+    """b200_me_mvs_resident (4-byte MotionVector lists, block from the CSR) == the same lists
+    as b200_cand records through b200_me_candidates_resident."""
+    W, H, PAD, w, h = 320, 192, 96, 16, 16
+    cur, ref = G.make_planes(W, H, PAD, np.uint8, seed=21)
+    c = G.ctx()
+    dcur, dref = c.plane_from_host(cur, PAD), c.plane_from_host(ref, PAD)
+    blocks = G.grid_blocks(W, H, w, h)
+    cands, offs = G.random_cands(len(blocks), 40, 30, seed=4)
+    mvs = np.stack([cands["mv_row"], cands["mv_col"]], axis=1).astype(np.int16).copy()
+    p = B.me_params(w, h, W, H, 450, window_hint_px=30)
+    n, nb = len(cands), len(blocks)
+    out_a = (np.zeros(n, np.uint32), np.zeros(n, np.uint64), np.zeros(nb, B.ME_RESULT_DTYPE))
+    out_b = (np.zeros(n, np.uint32), np.zeros(n, np.uint64), np.zeros(nb, B.ME_RESULT_DTYPE))
+    c.me_candidates_resident(dcur, dref, blocks, cands, p, offs, out_a)
+    c.me_mvs_resident(dcur, dref, blocks, mvs, p, offs, out_b)
+    c.synchronize()
+    for x, y in zip(out_a, out_b):
+        np.testing.assert_array_equal(x, y)
+    assert (out_a[2]["cost"] != np.uint64(2**64 - 1)).all()
+    for pl in (dcur, dref):
+        c.plane_free(pl)
+
+
 def test_candidate_list_host_buffers():
     """The `_batch` form (host pointers, copies inside) gives the same numbers."""
     W, H, PAD, w, h = 320, 192, 96, 16, 16
