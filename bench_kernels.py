@@ -216,6 +216,18 @@ def main():
                                                       16, 16, 8, W, H, hout.ctypes.data), len(items))
     emit("predict_intra 16x16 x 13 modes 8-bit", len(items), "predictions", ms, 257 + 256, cpu=cpu)
 
+    # ---- RDO distortion kernels on the 1080p 8-bit planes: every 16x16 block / every 8x8 block
+    d_scale = dev(rng.integers(1 << 12, 1 << 16, ((H + 3) // 4, W // 4)).astype(np.uint32))
+    d_wsse = torch.empty(nb * 8, dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: ctx.weighted_sse_dev(cur8, ref8, d_blocks, nb, 16, 16, d_scale, W // 4, d_wsse), reps=10)
+    emit("get_weighted_sse 16x16 8-bit", nb, "blocks", ms, 2 * 256 + 16 * 4 + 8,
+         "two 16x16 blocks + 16 chunk scales in, one u64 out")
+    b8 = grid_blocks(W, H, 8, 8)
+    d_b8 = dev(b8)
+    d_cd = torch.empty(len(b8) * 4, dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: ctx.cdef_dist_dev(cur8, ref8, d_b8, len(b8), 8, 8, 8, d_cd, None), reps=10)
+    emit("cdef_dist_kernel 8x8 8-bit (+ ssim boost)", len(b8), "8x8 blocks", ms, 2 * 64 + 4)
+
     # ---- config 5: CDEF on a 4K frame (luma + one 4:2:0 chroma plane)
     W4, H4 = 3840, 2160
     luma = rng.integers(0, 256, (H4, W4)).astype(np.uint8)

@@ -17,6 +17,9 @@
  *   fwd txfm / mc / cdef filt : no stored vectors in the reference (only asm==rust random
  *                               tests that need rustc) -> "parity unpinned" for those, with
  *                               independent cross-checks documented per module.
+ *   search stages, RDO dist   : likewise unpinned; checked against an independent Python model
+ *                               (tests/test_oracle_search.py) and the reference tests' float
+ *                               formulas (tests/test_oracle_rdo_dist.py).
  *
  * All strides are in ELEMENTS (pixels), pointers address pixel (0,0) of a region; planes
  * may be addressed at negative coordinates when the caller padded them.
