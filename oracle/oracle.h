@@ -136,6 +136,20 @@ void orc_forward_transform_batch(const int16_t *input, void *output, size_t nblo
 int orc_tx_width(int tx_size);
 int orc_tx_height(int tx_size);
 
+/* ------------------------------------------------- quantize/ (encoder.rs:1556-1655) */
+int orc_get_log_tx_scale(int tx_size);
+void orc_divu_gen(uint32_t d, uint32_t out[3]);
+uint32_t orc_divu_pair(uint32_t x, const uint32_t d[3]);
+int orc_coded_tx_area(int tx_size);
+int orc_scan_kind(int tx_type); /* 0 default, 1 mrow, 2 mcol */
+void orc_scan_order(int tx_size, int tx_type, uint16_t *scan, uint16_t *iscan /* may be NULL */);
+/* quantize (quantize/mod.rs:269-361) -> dequantize (:368-392) -> raw tx-domain distortion
+ * (encoder.rs:1611-1640) for nblocks blocks; dc_quant / ac_quant = dc_q() / ac_q() of the qindex. */
+void orc_quantize_chain_batch(const void *coeffs, size_t nblocks, int tx_size, int tx_type,
+                              uint32_t dc_quant, uint32_t ac_quant, int is_intra, int coeff_is_i32,
+                              void *qcoeffs, void *rcoeffs, uint16_t *eob, uint64_t *tx_dist,
+                              int threads);
+
 /* ------------------------------------------------------------------- mc.rs */
 /* put_8tap mc.rs:250-353; prep_8tap :360-451; mc_avg :454-479.  mode_x/mode_y = FilterMode
  * (0 REGULAR, 1 SMOOTH, 2 SHARP, 3 BILINEAR); col_frac/row_frac 0..15. */

@@ -8,6 +8,9 @@ Sources (xiph/rav1e @ 564ae3b):
   src/predict.rs:1523-1566  4x4 DC / DC_TOP / DC_LEFT / DC_128 / V / H / Paeth / smooth x3
   src/predict.rs:1569-1602  27 directional angles and their expected 4x4 outputs
   src/cdef.rs:304-309     first_max_element
+  src/quantize/mod.rs:186-215  test_tx_log_scale (TxSize, log_tx_scale) pairs
+  src/scan_order.rs:28-947     the 42 scan tables (sha256 of each, as little-endian u16) and the
+                               (TxSize, TxType) -> table map of av1_scan_orders :949-1321
 The Rust test code is parsed textually; nothing is executed (no rustc in this image).
 """
 import json
@@ -43,8 +46,26 @@ def main():
     c = cdef[cdef.index("fn check_max_element"):]
     fme = [{"input": [int(x) for x in re.findall(r"-?\d+", inp)], "expect": [int(i), int(v)]}
            for inp, i, v in re.findall(r"first_max_element\(&\[([^\]]+)\]\),\s*\((\d+),\s*(-?\d+)\)", c)]
+    import hashlib
+    import struct
+    q = open(os.path.join(REF, "quantize", "mod.rs")).read()
+    qt = q[q.index("fn test_tx_log_scale"):]
+    qt = qt[:qt.index("];")]
+    log_tx_scale = [[name, int(v)] for name, v in re.findall(r"\((TX_\w+),\s*(\d+)\)", qt)]
+    sc = open(os.path.join(REF, "scan_order.rs")).read()
+    tables = {}
+    for m in re.finditer(r"static (\w+)\s*:\s*\[u16;\s*(\d+)\]\s*=\s*\[(.*?)\];", sc, re.S):
+        vals = [int(x) for x in re.findall(r"\d+", m.group(3))]
+        if len(vals) == int(m.group(2)):
+            tables[m.group(1)] = {"n": len(vals), "first8": vals[:8],
+                                  "sha256": hashlib.sha256(struct.pack("<%dH" % len(vals), *vals)).hexdigest()}
+    blk = sc[sc.index("pub static av1_scan_orders"):]
+    scan_map = {sz: re.findall(r"scan: &(\w+),", body) for sz, body in re.findall(r"// (TX_\w+)\n(.*?)\],", blk, re.S)}
+    assert len(tables) == 42 and len(scan_map) == 19 and all(len(v) == 16 for v in scan_map.values())
+    assert len(log_tx_scale) == 19
     out = {
         "source": "xiph/rav1e @ 564ae3b, extracted by tests/golden/make_golden.py",
+        "log_tx_scale": log_tx_scale, "scan_tables": tables, "scan_map": scan_map,
         "dist_pattern": {"org": "(x + y + 24) & 255", "ref": "(x - y + 8) & 255", "block_at": [32, 40],
                          "derivation": "src/dist.rs:384-413 (xpad/ypad 136 and 264; alignment terms cancel)"},
         "sad": triples(sad_part), "satd": triples(satd_part),
