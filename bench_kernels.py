@@ -216,6 +216,26 @@ def main():
                                                       16, 16, 8, W, H, hout.ctypes.data), len(items))
     emit("predict_intra 16x16 x 13 modes 8-bit", len(items), "predictions", ms, 257 + 256, cpu=cpu)
 
+    # ---- quantize -> dequantize -> tx-domain distortion on the 16x16 DCT coefficients of a frame
+    d_coef16 = torch.empty(nb * 256, dtype=torch.int16, device="cuda")
+    ctx.fwd_txfm_residual_dev(cur8, ref8, d_blocks, nb, None, d_coef16, 2, 0, 8)
+    d_q16 = torch.empty(nb * 256, dtype=torch.int16, device="cuda")
+    d_r16 = torch.empty(nb * 256, dtype=torch.int16, device="cuda")
+    d_eob = torch.empty(nb, dtype=torch.int16, device="cuda")
+    d_txd = torch.empty(nb, dtype=torch.int64, device="cuda")
+    ms = timed(lambda: ctx.quantize_dev(d_coef16, nb, 2, 0, 120, 96, False, False, d_q16, d_r16, d_eob, d_txd), reps=10)
+    hcoef = d_coef16.cpu().numpy().reshape(nb, 256)
+    hq, hr = np.zeros_like(hcoef), np.zeros_like(hcoef)
+    he, hd = np.zeros(nb, np.uint16), np.zeros(nb, np.uint64)
+    OLq = O.lib()
+    OLq.orc_quantize_chain_batch.restype = None
+    OLq.orc_quantize_chain_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.c_uint32,
+                                             C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    cpu = cpu_rate(lambda: OLq.orc_quantize_chain_batch(hcoef.ctypes.data, nb, 2, 0, 120, 96, 0, 0, hq.ctypes.data,
+                                                        hr.ctypes.data, he.ctypes.data, hd.ctypes.data, TH), nb)
+    emit("quantize + dequantize + tx-dist 16x16 8-bit (noise residual: long scans)", nb, "blocks", ms,
+         3 * 512 + 10, "coefficients in, qcoeffs + rcoeffs + eob + distortion out", cpu)
+
     # ---- RDO distortion kernels on the 1080p 8-bit planes: every 16x16 block / every 8x8 block
     d_scale = dev(rng.integers(1 << 12, 1 << 16, ((H + 3) // 4, W // 4)).astype(np.uint32))
     d_wsse = torch.empty(nb * 8, dtype=torch.uint8, device="cuda")

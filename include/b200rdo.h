@@ -333,6 +333,23 @@ int b200_fwd_txfm_residual_multi_dev(b200_ctx *ctx, size_t npairs, const b200_pl
                                      const b200_block *d_blocks, size_t nblocks,
                                      const b200_me_result *d_mv_src, void *d_output, int tx_size,
                                      int tx_type, int bd);
+/* ---------------------------------------------------------------- quantize chain
+ * The steps of encode_tx_block after the forward transform (encoder.rs:1556-1655) for nblocks
+ * transform blocks of one (tx_size, tx_type), device-resident:
+ *   QuantizationContext::quantize (quantize/mod.rs:269-361)  -> d_qcoeffs, d_eob
+ *   dequantize (quantize/mod.rs:368-392)                     -> d_rcoeffs   (may be NULL)
+ *   raw transform-domain distortion (encoder.rs:1611-1640)   -> d_tx_dist   (may be NULL)
+ * d_coeffs: nblocks x (w*h) coefficients exactly as b200_fwd_txfm_* writes them (i16, or i32 when
+ * coeff_is_i32); d_qcoeffs / d_rcoeffs: nblocks x b200_coded_tx_area(tx_size) (64-point dimensions
+ * code 32, av1_get_coded_tx_size).  dc_quant / ac_quant are the caller's dc_q() / ac_q() of the
+ * block's qindex (quantize/mod.rs:36-48; the lookup is control plane).  tx_type 0..15 (WHT_WHT is
+ * lossless-only and has no scan order).  The rate estimate and the bias multiplications that
+ * follow (encoder.rs:1642-1652) consume d_tx_dist on the host. */
+int b200_coded_tx_area(int tx_size);
+int b200_quantize_dev(b200_ctx *ctx, const void *d_coeffs, size_t nblocks, int tx_size, int tx_type,
+                      uint32_t dc_quant, uint32_t ac_quant, int is_intra, int coeff_is_i32,
+                      void *d_qcoeffs, void *d_rcoeffs, uint16_t *d_eob, uint64_t *d_tx_dist);
+
 /* Fused residual + transform with resident planes and HOST descriptors / outputs. */
 int b200_fwd_txfm_residual_resident(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
                                     const b200_block *blocks, size_t nblocks,

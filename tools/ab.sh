@@ -1,1 +1,1 @@
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_r1_final_2gpu.json 2> gpurun_out/bench_r1_final_2gpu.err
+timeout 600 python -m pytest tests/test_quantize_gpu.py -m gpu -x -q 2>&1 | tail -15 > gpurun_out/ab_tests.log
