@@ -11,6 +11,8 @@ Sources (xiph/rav1e @ 564ae3b):
   src/quantize/mod.rs:186-215  test_tx_log_scale (TxSize, log_tx_scale) pairs
   src/scan_order.rs:28-947     the 42 scan tables (sha256 of each, as little-endian u16) and the
                                (TxSize, TxType) -> table map of av1_scan_orders :949-1321
+  tests/small_input.y4m   BASELINE config 0's input: the luma planes of its 5 frames (64x64, 8 bit)
+                          -> tests/golden/small_input_luma.npy
 The Rust test code is parsed textually; nothing is executed (no rustc in this image).
 """
 import json
@@ -78,6 +80,23 @@ def main():
     with open(OUT, "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", OUT)
+    # config 0: YUV4MPEG2 W64 H64 ... C420jpeg, 5 x ("FRAME\n" + 4096 Y + 1024 U + 1024 V)
+    import numpy as np
+    raw = open(os.path.join(os.path.dirname(REF), "tests", "small_input.y4m"), "rb").read()
+    header, rest = raw.split(b"\n", 1)
+    fields = dict((t[:1].decode(), t[1:].decode()) for t in header.split()[1:])
+    w, h = int(fields["W"]), int(fields["H"])
+    assert (w, h) == (64, 64) and fields["C"].startswith("420")
+    frames = []
+    while rest:
+        assert rest.startswith(b"FRAME\n")
+        rest = rest[6:]
+        frames.append(np.frombuffer(rest[:w * h], np.uint8).reshape(h, w).copy())
+        rest = rest[w * h * 3 // 2:]
+    luma = np.stack(frames)
+    assert luma.shape == (5, 64, 64)
+    np.save(os.path.join(os.path.dirname(OUT), "small_input_luma.npy"), luma)
+    print("wrote small_input_luma.npy", luma.shape, int(luma.sum()))
 
 
 if __name__ == "__main__":
