@@ -14,7 +14,9 @@
  *   SAD / SATD                : pinned by src/dist.rs:418-441, :477-500 (22 sizes, u8+u16)
  *   intra 4x4 predictors      : pinned by src/predict.rs:1514-1693
  *   cdef first_max_element    : pinned by src/cdef.rs:304-309
- *   fwd txfm / mc / cdef filt : no stored vectors in the reference (only asm==rust random
+ *   fwd + inverse transform   : pinned jointly by the reference's round-trip test
+ *                               (transform/mod.rs:479-617, 44 (size, type, tolerance) triples)
+ *   mc / cdef filter          : no stored vectors in the reference (only asm==rust random
  *                               tests that need rustc) -> "parity unpinned" for those, with
  *                               independent cross-checks documented per module.
  *   search stages, RDO dist   : likewise unpinned; checked against an independent Python model
@@ -135,6 +137,14 @@ void orc_forward_transform_batch(const int16_t *input, void *output, size_t nblo
                                  int tx_type, int bd, int coeff_is_i32, int threads);
 int orc_tx_width(int tx_size);
 int orc_tx_height(int tx_size);
+
+/* ------------------------------------------------- transform/inverse.rs */
+/* 1-D inverse transforms (kind = TxType1D: 0 DCT, 1 ADST, 2 FLIPADST, 3 IDTX, 4 WHT); returns 0
+ * for the combinations the reference leaves unimplemented. */
+int orc_inv_txfm_1d(int kind, int n, const int32_t *in, int32_t *out, int range);
+/* rust::inverse_transform_add (inverse.rs:1637-1704): dst += inverse(input), clamped to bd bits. */
+void orc_inverse_transform_add(const void *input, int coeff_is_i32, void *dst, ptrdiff_t dst_stride,
+                               int bpp, int tx_size, int tx_type, int bd);
 
 /* ------------------------------------------------- quantize/ (encoder.rs:1556-1655) */
 int orc_get_log_tx_scale(int tx_size);

@@ -11,6 +11,8 @@ Sources (xiph/rav1e @ 564ae3b):
   src/quantize/mod.rs:186-215  test_tx_log_scale (TxSize, log_tx_scale) pairs
   src/scan_order.rs:28-947     the 42 scan tables (sha256 of each, as little-endian u16) and the
                                (TxSize, TxType) -> table map of av1_scan_orders :949-1321
+  src/transform/mod.rs:519-552  log_tx_ratios (TxSize, rect_ratio_log2) pairs
+  src/transform/mod.rs:555-603  roundtrips: (TxSize, TxType, tolerance) of forward -> inverse_transform_add
   tests/small_input.y4m   BASELINE config 0's input: the luma planes of its 5 frames (64x64, 8 bit)
                           -> tests/golden/small_input_luma.npy
 The Rust test code is parsed textually; nothing is executed (no rustc in this image).
@@ -65,8 +67,16 @@ def main():
     scan_map = {sz: re.findall(r"scan: &(\w+),", body) for sz, body in re.findall(r"// (TX_\w+)\n(.*?)\],", blk, re.S)}
     assert len(tables) == 42 and len(scan_map) == 19 and all(len(v) == 16 for v in scan_map.values())
     assert len(log_tx_scale) == 19
+    tm = open(os.path.join(REF, "transform", "mod.rs")).read()
+    lr = tm[tm.index("fn log_tx_ratios"):tm.index("fn roundtrips")]
+    log_tx_ratios = [[n, int(v)] for n, v in re.findall(r"\(TxSize::(TX_\w+),\s*(-?\d+)\)", lr)]
+    rt = tm[tm.index("fn roundtrips<T: Pixel>"):tm.index("fn roundtrips_u8")]
+    rt = "\n".join(l for l in rt.splitlines() if not l.strip().startswith("//"))
+    roundtrips = [[a, b, int(t)] for a, b, t in re.findall(r"\((TX_\w+),\s*(\w+),\s*(\d+)\)", rt)]
+    assert len(log_tx_ratios) == 19 and len(roundtrips) == 44, (len(log_tx_ratios), len(roundtrips))
     out = {
         "source": "xiph/rav1e @ 564ae3b, extracted by tests/golden/make_golden.py",
+        "log_tx_ratios": log_tx_ratios, "roundtrips": roundtrips,
         "log_tx_scale": log_tx_scale, "scan_tables": tables, "scan_map": scan_map,
         "dist_pattern": {"org": "(x + y + 24) & 255", "ref": "(x - y + 8) & 255", "block_at": [32, 40],
                          "derivation": "src/dist.rs:384-413 (xpad/ypad 136 and 264; alignment terms cancel)"},
