@@ -350,6 +350,16 @@ int b200_quantize_dev(b200_ctx *ctx, const void *d_coeffs, size_t nblocks, int t
                       uint32_t dc_quant, uint32_t ac_quant, int is_intra, int coeff_is_i32,
                       void *d_qcoeffs, void *d_rcoeffs, uint16_t *d_eob, uint64_t *d_tx_dist);
 
+/* inverse_transform_add (transform/inverse.rs:1637-1704) for nblocks blocks of one (tx_size,
+ * tx_type): dst(block i) += inverse(coefficients i), clamped to bd bits — the reconstruction step
+ * of encode_tx_block (encoder.rs:1600-1609).  d_coeffs: b200_coded_tx_area(tx_size) coefficients
+ * per block in the forward transform's layout (i16 for 8-bit planes, i32 for HBD), e.g. the
+ * d_rcoeffs of b200_quantize_dev.  Blocks of one call must not overlap.  tx_type 0..16; pairs the
+ * reference leaves `unimplemented!()` (INV_TXFM_FNS :1593-1623) are rejected. */
+int b200_inverse_transform_add_dev(b200_ctx *ctx, const void *d_coeffs, const b200_plane *dst,
+                                   const b200_block *d_blocks, size_t nblocks, int tx_size, int tx_type,
+                                   int bd);
+
 /* Fused residual + transform with resident planes and HOST descriptors / outputs. */
 int b200_fwd_txfm_residual_resident(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
                                     const b200_block *blocks, size_t nblocks,

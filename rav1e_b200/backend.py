@@ -119,6 +119,7 @@ def lib():
             f.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t] + extra
             f.restype = u32
     L.b200_me_candidates_dev.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
+    L.b200_inverse_transform_add_dev.argtypes = [vp, vp, pp, vp, sz, i32, i32, i32]
     L.b200_quantize_dev.argtypes = [vp, vp, sz, i32, i32, u32, u32, i32, i32, vp, vp, vp, vp]
     L.b200_weighted_sse.restype = C.c_uint64
     L.b200_weighted_sse.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t, vp, C.c_ssize_t, i32, i32, i32]
@@ -278,6 +279,10 @@ class Context:
         self.check(self.L.b200_quantize_dev(self.h, _dev_ptr(d_coeffs), n, tx_size, tx_type, dc_quant, ac_quant,
                                             int(is_intra), int(coeff_i32), _dev_ptr(d_q), _dev_ptr(d_r),
                                             _dev_ptr(d_eob), _dev_ptr(d_dist)))
+
+    def inverse_transform_add_dev(self, d_coeffs, dst, d_blocks, n, tx_size, tx_type, bd):
+        self.check(self.L.b200_inverse_transform_add_dev(self.h, _dev_ptr(d_coeffs), C.byref(dst), _dev_ptr(d_blocks),
+                                                         n, tx_size, tx_type, bd))
 
     # ---- RDO distortion
     def weighted_sse_dev(self, src1, src2, d_blocks, n, w, h, d_scale, scale_stride, d_out):

@@ -8,7 +8,8 @@ the forward direction, this tool RESTATES them mechanically: it parses that rest
 symbolically executes every function (arrays become lists of value ids, nested calls are inlined)
 and emits one flattened single-assignment program per transform into
 
-    oracle/inv_txfm_networks.h     plain C, used by the CPU oracle (oracle/inv_txfm.c)
+    oracle/inv_txfm_networks.h              plain C, used by the CPU oracle (oracle/inv_txfm.c)
+    rav1e_b200/csrc/inv_txfm_networks.cuh   CUDA device functions (rav1e_b200/csrc/inv_txfm.cu)
 
 with every op tagged by the reference line it came from.  The primitives (half_btf with its
 wrapping arithmetic, clamp_value, round_shift: transform/mod.rs:296-315) are written by hand in
@@ -23,6 +24,7 @@ import re
 REF = "/root/reference/src/transform/inverse.rs"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "oracle", "inv_txfm_networks.h")
+OUT_CU = os.path.join(ROOT, "rav1e_b200", "csrc", "inv_txfm_networks.cuh")
 
 TOK = re.compile(r"\s*(?:(//[^\n]*)|(\d+)|([A-Za-z_][A-Za-z_0-9]*!?)|(\.\.|&mut|[-+*/=<>(){}\[\],;:.&|]))")
 
@@ -291,8 +293,19 @@ def main():
            " * statement an op came from.  Primitives (WADD/WSUB/WMUL/WNEG wrap like Rust release builds;",
            " * HALF_BTF, CLAMP_VALUE, ROUND_SHIFT: transform/mod.rs:296-315) are defined by the includer.",
            " * TEST INFRASTRUCTURE ONLY (see oracle.h). */", ""]
+    cu = ["// GENERATED by tools/gen_inv_txfm.py from the staged butterfly listings of rav1e",
+          "// src/transform/inverse.rs:71-1591 (xiph/rav1e @ 564ae3b) - do not edit.  One flattened",
+          "// single-assignment program per 1-D inverse transform over a register array; `L<n>` = reference",
+          "// line of the statement an op came from.  WADD/WSUB/WMUL/WNEG, HALF_BTF, CLAMP_VALUE, ROUND_SHIFT",
+          "// are defined by the includer (inv_txfm.cu).", ""]
     for name, n in names.items():
         lines, outs = em.run(name, n)
+        cu.append(f"__device__ __forceinline__ void d_{name}(const int (&in)[{n}], int (&out)[{n}], int range) {{")
+        if not any("range" in l for l in lines):
+            cu.append("  (void)range;")
+        cu += [l.replace("const int32_t", "const int") for l in lines]
+        cu += [f"  out[{i}] = {o};" for i, o in enumerate(outs)]
+        cu += ["}", ""]
         uses_range = any("range" in l for l in lines)
         out.append(f"static void {name}(const int32_t *in, int32_t *out, int range) {{")
         if not uses_range:
@@ -307,7 +320,9 @@ def main():
         print(f"{name}: {len(lines)} ops")
     with open(OUT, "w") as f:
         f.write("\n".join(out))
-    print("wrote", OUT)
+    with open(OUT_CU, "w") as f:
+        f.write("\n".join(cu))
+    print("wrote", OUT, "and", OUT_CU)
 
 
 if __name__ == "__main__":
