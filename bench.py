@@ -314,7 +314,6 @@ def run_b200(args, rank, world, local_rank):
     l0 = ctx.launches
     ms = timed(step, args.steps)
     launches = ctx.launches - l0
-    clocks = clk.stop() if rank == 0 else None
     units_per_step = world * F * (n_sad + n_satd + nb)
     value = units_per_step * args.steps / (ms * 1e-3)
 
@@ -336,6 +335,8 @@ def run_b200(args, rank, world, local_rank):
             txfm_launch(g)
     txfm_only()
     ms_txfm = timed(txfm_only, args.steps) / (args.steps * NG)
+    # clocks / throttle reasons over the warm-up, the timed step region and the per-leg timings above
+    clocks = clk.stop() if rank == 0 else None
     # ---- extra leg (not part of `value`): the exhaustive grid full_pixel_me falls back to at
     # speed <= 5 (me.rs:822-846): +-192 x +-64 px, step 4 => up to 97 x 33 = 3201 positions/block
     d_fs = torch.empty(nb * 16, dtype=torch.uint8, device="cuda")
