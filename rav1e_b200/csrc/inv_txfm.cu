@@ -15,8 +15,10 @@
 // adds into the destination plane with the pixel clamp (rows of the plane are written by
 // consecutive threads).  Blocks of one call must not overlap.
 //
-// STATUS: written against the oracle after this round's GPU budget was spent — compiled for
-// sm_100a here, its parity test (tests/test_zz_inv_txfm_gpu.py) has not run on hardware yet.
+// STATUS: written after this round's GPU budget was spent.  The per-thread row / column passes
+// below are host+device functions and tests/test_inv_txfm_emul.py replays them on the CPU against
+// the oracle (all 160 valid pairs, 8 and 10 bit: bit exact); the launch itself
+// (tests/test_zz_inv_txfm_gpu.py) has not run on hardware yet.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -39,20 +41,24 @@ const int kTx1D[17][2] = {{0, 0}, {1, 0}, {0, 1}, {1, 1}, {2, 0}, {0, 2}, {2, 2}
 #define WMUL(a, b) ((int)((unsigned)(a) * (unsigned)(b)))
 #define WNEG(a) ((int)(0u - (unsigned)(a)))
 
+// Everything below the launch is host+device so that tests/cpp/test_inv_txfm_emul.cu can run the
+// very same row / column passes on the CPU against the oracle (the product never does).
+#define B200_HDI __host__ __device__ __forceinline__
+
 // transform/mod.rs:296-307 with INV_COS_BIT = 12
-__device__ __forceinline__ int half_btf12(int w0, int in0, int w1, int in1) {
+B200_HDI int half_btf12(int w0, int in0, int w1, int in1) {
   return WADD(WADD(WMUL(w0, in0), WMUL(w1, in1)), 1 << 11) >> 12;
 }
 #define HALF_BTF(w0, in0, w1, in1) half_btf12((w0), (in0), (w1), (in1))
 
 // transform/mod.rs:310-315
-__device__ __forceinline__ int clamp_value(int v, int bit) {
+B200_HDI int clamp_value(int v, int bit) {
   const int hi = (int)((1ll << (bit - 1)) - 1), lo = (int)(-(1ll << (bit - 1)));
   return v < lo ? lo : v > hi ? hi : v;
 }
 #define CLAMP_VALUE(v, range) clamp_value((v), (range))
 
-__device__ __forceinline__ int round_shift_i(int v, int b) { return WADD(v, (1 << b) >> 1) >> b; }
+B200_HDI int round_shift_i(int v, int b) { return WADD(v, (1 << b) >> 1) >> b; }
 #define ROUND_SHIFT(v, b) round_shift_i((v), (b))
 
 #include "inv_txfm_networks.cuh"
@@ -61,7 +67,7 @@ constexpr int kSqrt2 = 5793, kInvSqrt2 = 2896;  // transform/mod.rs:47-49 (12 fr
 
 // INV_TXFM_FNS[kind][log2(N) - 2] (inverse.rs:1593-1623) on a register array
 template <int N>
-__device__ __forceinline__ void run_inv_1d(int kind, const int (&in)[N], int (&out)[N], int range) {
+B200_HDI void run_inv_1d(int kind, const int (&in)[N], int (&out)[N], int range) {
   if (kind == 3) {  // identity: sqrt2, 2, 2 sqrt2, 4
 #pragma unroll
     for (int i = 0; i < N; i++) {
@@ -120,13 +126,64 @@ struct InvArgs {
 
 constexpr int kInvThreads = 128;
 
+// Row pass of one block-transform for "thread" t < H (inverse.rs:1659-1682): row t of the coded
+// coefficients -> scaling + clamp -> 1-D row transform -> row t of the tile.  Rows >= 32 of a
+// 64-point block stay zero.
+template <int W, int H, typename CoefT>
+B200_HDI void inv_row_pass(const InvArgs &a, size_t blk, int t, int *tile) {
+  constexpr int PITCH = W + 1;
+  constexpr int W32 = W < 32 ? W : 32, H32 = H < 32 ? H : 32;
+  int out[W];
+  if (t < H32) {
+    int in[W];
+    const CoefT *src = (const CoefT *)a.coeffs + blk * (size_t)(W32 * H32) + t;
+    const int range = a.bd + 8;
+#pragma unroll
+    for (int c = 0; c < W; c++) {
+      int val = 0;
+      if (c < W32) {
+        const int raw = (int)src[(size_t)c * H32];
+        val = a.rect ? round_shift_i(WMUL(raw, kInvSqrt2), 12) : a.lossless ? raw >> 2 : raw;
+        val = clamp_value(val, range);
+      }
+      in[c] = val;
+    }
+    run_inv_1d<W>(a.row_kind, in, out, range);
+  } else {
+#pragma unroll
+    for (int c = 0; c < W; c++) out[c] = 0;
+  }
+#pragma unroll
+  for (int c = 0; c < W; c++) tile[t * PITCH + c] = out[c];
+}
+
+// Column pass for "thread" t < W (inverse.rs:1684-1703): column t of the tile -> intermediate
+// shift + clamp -> 1-D column transform -> final shift -> add into the plane with the pixel clamp.
+template <int W, int H, typename Px>
+B200_HDI void inv_col_pass(const InvArgs &a, size_t blk, int t, const int *tile) {
+  constexpr int PITCH = W + 1;
+  const int range = a.bd + 6 > 16 ? a.bd + 6 : 16;
+  int in[H], out[H];
+#pragma unroll
+  for (int r = 0; r < H; r++) in[r] = clamp_value(round_shift_i(tile[r * PITCH + t], a.inter_shift), range);
+  run_inv_1d<H>(a.col_kind, in, out, range);
+  const b200_block b = a.blocks[blk];
+  Px *p = (Px *)a.dst + (long long)b.y * a.dst_stride + b.x + t;
+  const int maxv = (1 << a.bd) - 1;
+#pragma unroll
+  for (int r = 0; r < H; r++) {
+    const int rr = a.lossless ? out[r] : round_shift_i(out[r], 4);
+    const int v = WADD((int)p[(long long)r * a.dst_stride], rr);
+    p[(long long)r * a.dst_stride] = (Px)(v < 0 ? 0 : v > maxv ? maxv : v);
+  }
+}
+
 template <int W, int H, typename CoefT, typename Px>
 __global__ void __launch_bounds__(kInvThreads) inv_txfm_add_kernel(const __grid_constant__ InvArgs a) {
   constexpr int T = W > H ? W : H;
   constexpr int PER = kInvThreads / T;
   constexpr int PITCH = W + 1;
   constexpr int REGION = H * PITCH + ((H * PITCH) % 2 == 0 ? 1 : 0);
-  constexpr int W32 = W < 32 ? W : 32, H32 = H < 32 ? H : 32;
   __shared__ int buf[PER * REGION];
   const int slot = threadIdx.x / T, t = threadIdx.x - slot * T;
   int *tile = buf + slot * REGION;
@@ -134,49 +191,9 @@ __global__ void __launch_bounds__(kInvThreads) inv_txfm_add_kernel(const __grid_
   for (size_t base = (size_t)blockIdx.x * PER; base < a.n; base += stride_blk) {
     const size_t blk = base + slot;
     const bool valid = blk < a.n;
-    // ---- rows (inverse.rs:1659-1682); rows >= 32 of a 64-point block stay zero
-    if (valid && t < H) {
-      int out[W];
-      if (t < H32) {
-        int in[W];
-        const CoefT *src = (const CoefT *)a.coeffs + blk * (size_t)(W32 * H32) + t;
-        const int range = a.bd + 8;
-#pragma unroll
-        for (int c = 0; c < W; c++) {
-          int val = 0;
-          if (c < W32) {
-            const int raw = (int)src[(size_t)c * H32];
-            val = a.rect ? round_shift_i(WMUL(raw, kInvSqrt2), 12) : a.lossless ? raw >> 2 : raw;
-            val = clamp_value(val, range);
-          }
-          in[c] = val;
-        }
-        run_inv_1d<W>(a.row_kind, in, out, range);
-      } else {
-#pragma unroll
-        for (int c = 0; c < W; c++) out[c] = 0;
-      }
-#pragma unroll
-      for (int c = 0; c < W; c++) tile[t * PITCH + c] = out[c];
-    }
+    if (valid && t < H) inv_row_pass<W, H, CoefT>(a, blk, t, tile);
     __syncthreads();
-    // ---- columns (inverse.rs:1684-1703)
-    if (valid && t < W) {
-      const int range = a.bd + 6 > 16 ? a.bd + 6 : 16;
-      int in[H], out[H];
-#pragma unroll
-      for (int r = 0; r < H; r++) in[r] = clamp_value(round_shift_i(tile[r * PITCH + t], a.inter_shift), range);
-      run_inv_1d<H>(a.col_kind, in, out, range);
-      const b200_block b = a.blocks[blk];
-      Px *p = (Px *)a.dst + (long long)b.y * a.dst_stride + b.x + t;
-      const int maxv = (1 << a.bd) - 1;
-#pragma unroll
-      for (int r = 0; r < H; r++) {
-        const int rr = a.lossless ? out[r] : round_shift_i(out[r], 4);
-        const int v = WADD((int)p[(long long)r * a.dst_stride], rr);
-        p[(long long)r * a.dst_stride] = (Px)(v < 0 ? 0 : v > maxv ? maxv : v);
-      }
-    }
+    if (valid && t < W) inv_col_pass<W, H, Px>(a, blk, t, tile);
     __syncthreads();
   }
 }

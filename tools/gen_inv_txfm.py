@@ -296,11 +296,11 @@ def main():
     cu = ["// GENERATED by tools/gen_inv_txfm.py from the staged butterfly listings of rav1e",
           "// src/transform/inverse.rs:71-1591 (xiph/rav1e @ 564ae3b) - do not edit.  One flattened",
           "// single-assignment program per 1-D inverse transform over a register array; `L<n>` = reference",
-          "// line of the statement an op came from.  WADD/WSUB/WMUL/WNEG, HALF_BTF, CLAMP_VALUE, ROUND_SHIFT",
-          "// are defined by the includer (inv_txfm.cu).", ""]
+          "// line of the statement an op came from.  B200_HDI (function qualifiers), WADD/WSUB/WMUL/WNEG, HALF_BTF,",
+          "// CLAMP_VALUE, ROUND_SHIFT are defined by the includer (inv_txfm.cu).", ""]
     for name, n in names.items():
         lines, outs = em.run(name, n)
-        cu.append(f"__device__ __forceinline__ void d_{name}(const int (&in)[{n}], int (&out)[{n}], int range) {{")
+        cu.append(f"B200_HDI void d_{name}(const int (&in)[{n}], int (&out)[{n}], int range) {{")
         if not any("range" in l for l in lines):
             cu.append("  (void)range;")
         cu += [l.replace("const int32_t", "const int") for l in lines]
