@@ -333,6 +333,13 @@ int b200_fwd_txfm_residual_multi_dev(b200_ctx *ctx, size_t npairs, const b200_pl
                                      const b200_block *d_blocks, size_t nblocks,
                                      const b200_me_result *d_mv_src, void *d_output, int tx_size,
                                      int tx_type, int bd);
+/* ActivityMask::from_plane + fill_scales (activity.rs:21-100): d_variances[by * wb + bx] =
+ * variance_8x8 of luma block (bx, by), wb = ceil(width / 8), hb = ceil(height / 8) (the plane's
+ * padding must cover the rounding up); d_scales (may be NULL) = ssim_boost(var, var, bit_depth),
+ * the Q14 DistortionScale per importance block. */
+int b200_activity_mask_dev(b200_ctx *ctx, const b200_plane *luma, int bit_depth, uint32_t *d_variances,
+                           uint32_t *d_scales);
+
 /* ---------------------------------------------------------------- quantize chain
  * The steps of encode_tx_block after the forward transform (encoder.rs:1556-1655) for nblocks
  * transform blocks of one (tx_size, tx_type), device-resident:

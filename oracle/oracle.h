@@ -127,6 +127,11 @@ uint32_t orc_cdef_dist_kernel_u16(const uint16_t *src, ptrdiff_t ss, const uint1
                                   int w, int h, int bit_depth, uint32_t raw[3]);
 uint32_t orc_apply_ssim_boost(uint32_t input, uint32_t svar, uint32_t dvar, int bit_depth);
 uint64_t orc_distortion_scale_mul(uint32_t scale, uint64_t dist);
+/* ActivityMask::from_plane + fill_scales (activity.rs:21-100) */
+uint32_t orc_variance_8x8_u8(const uint8_t *src, ptrdiff_t stride);
+uint32_t orc_variance_8x8_u16(const uint16_t *src, ptrdiff_t stride);
+void orc_activity_mask(const void *luma, ptrdiff_t stride, int bpp, int width, int height, int bit_depth,
+                       uint32_t *variances, uint32_t *scales);
 
 /* -------------------------------------------------------------- transform/ */
 /* forward.rs:71-161.  coeff_is_i32: 0 -> int16_t out (8-bit pixels), 1 -> int32_t out. */

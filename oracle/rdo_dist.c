@@ -110,3 +110,43 @@ DEF_CDEF_DIST(orc_cdef_dist_kernel_u16, uint16_t)
 uint64_t orc_distortion_scale_mul(uint32_t scale, uint64_t dist) {
   return ((uint64_t)scale * dist + ((1u << 14) >> 1)) >> 14;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * ActivityMask (src/activity.rs:21-69): variance_8x8 (:71-100) of every 8x8 luma block of the
+ * plane rounded up to whole blocks (the region reads into the plane's padding), and fill_scales
+ * (:58-68): ssim_boost(var, var, bit_depth) = apply_ssim_boost(1 << 14, ..) (:147-154).
+ * ------------------------------------------------------------------------------------------ */
+#define DEF_VAR8(NAME, PIXEL)                                                                 \
+  uint32_t NAME(const PIXEL *src, ptrdiff_t stride) {                                         \
+    uint16_t sum_s_cols[8] = {0};                                                             \
+    uint32_t sum_s2_cols[8] = {0};                                                            \
+    for (int j = 0; j < 8; j++)                                                               \
+      for (int i = 0; i < 8; i++) {                                                           \
+        const uint16_t s = (uint16_t)src[j * stride + i];                                     \
+        sum_s_cols[i] = (uint16_t)(sum_s_cols[i] + s);                                        \
+        sum_s2_cols[i] += (uint32_t)s * (uint32_t)s;                                          \
+      }                                                                                       \
+    uint64_t sum_s = 0, sum_s2 = 0;                                                           \
+    for (int i = 0; i < 8; i++) {                                                             \
+      sum_s += sum_s_cols[i];                                                                 \
+      sum_s2 += sum_s2_cols[i];                                                               \
+    }                                                                                         \
+    const uint64_t v = sum_s2 - ((sum_s * sum_s + 32) >> 6);                                  \
+    return v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)v; /* u32::try_from(..).unwrap_or(MAX) */ \
+  }
+DEF_VAR8(orc_variance_8x8_u8, uint8_t)
+DEF_VAR8(orc_variance_8x8_u16, uint16_t)
+
+/* luma: pixel (0,0), readable up to the next multiple of 8 in both directions.
+ * variances / scales: ceil(w/8) * ceil(h/8) entries, row-major; scales may be NULL. */
+void orc_activity_mask(const void *luma, ptrdiff_t stride, int bpp, int width, int height, int bit_depth,
+                       uint32_t *variances, uint32_t *scales) {
+  const int wb = (width + 7) >> 3, hb = (height + 7) >> 3;
+  for (int y = 0; y < hb; y++)
+    for (int x = 0; x < wb; x++) {
+      const uint32_t v = bpp == 1 ? orc_variance_8x8_u8((const uint8_t *)luma + (ptrdiff_t)(y * 8) * stride + x * 8, stride)
+                                  : orc_variance_8x8_u16((const uint16_t *)luma + (ptrdiff_t)(y * 8) * stride + x * 8, stride);
+      variances[y * wb + x] = v;
+      if (scales) scales[y * wb + x] = orc_apply_ssim_boost(1u << 14, v, v, bit_depth);
+    }
+}

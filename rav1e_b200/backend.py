@@ -125,6 +125,7 @@ def lib():
     L.b200_weighted_sse.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t, vp, C.c_ssize_t, i32, i32, i32]
     L.b200_cdef_dist_kernel.restype = u32
     L.b200_cdef_dist_kernel.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t, i32, i32, i32, vp]
+    L.b200_activity_mask_dev.argtypes = [vp, pp, i32, vp, vp]
     L.b200_weighted_sse_dev.argtypes = [vp, pp, pp, vp, sz, i32, i32, vp, sz, vp]
     L.b200_cdef_dist_dev.argtypes = [vp, pp, pp, vp, sz, i32, i32, i32, vp, vp]
     L.b200_me_search_dev.argtypes = [vp, pp, pp, vp, sz, vp, vp, i32, vp, vp, pmp, i32, vp]
@@ -288,6 +289,10 @@ class Context:
     def weighted_sse_dev(self, src1, src2, d_blocks, n, w, h, d_scale, scale_stride, d_out):
         self.check(self.L.b200_weighted_sse_dev(self.h, C.byref(src1), C.byref(src2), _dev_ptr(d_blocks), n,
                                                 w, h, _dev_ptr(d_scale), scale_stride, _dev_ptr(d_out)))
+
+    def activity_mask_dev(self, luma, bit_depth, d_variances, d_scales=None):
+        self.check(self.L.b200_activity_mask_dev(self.h, C.byref(luma), bit_depth, _dev_ptr(d_variances),
+                                                 _dev_ptr(d_scales)))
 
     def cdef_dist_dev(self, src, dst, d_blocks, n, w, h, bit_depth, d_out=None, d_raw=None):
         self.check(self.L.b200_cdef_dist_dev(self.h, C.byref(src), C.byref(dst), _dev_ptr(d_blocks), n, w, h,

@@ -270,3 +270,66 @@ extern "C" uint32_t b200_cdef_dist_kernel(const void *src, ptrdiff_t src_stride,
   if (ret) ret[0] = host[1], ret[1] = host[2], ret[2] = host[3];
   return host[0];
 }
+
+// ---------------------------------------------------------------- activity mask
+// ActivityMask::from_plane (src/activity.rs:21-55): variance_8x8 (:71-100) of every 8x8 luma
+// block of the plane rounded up to whole blocks, and fill_scales (:58-68): ssim_boost(var, var,
+// bit_depth) = apply_ssim_boost(1 << 14, ..) (:147-154).  One thread per 8x8 block.
+namespace {
+
+// host+device so that tests/cpp/activity_emul.cu can replay it on the CPU against the oracle
+template <typename T>
+__host__ __device__ __forceinline__ uint32_t variance_8x8_px(const T *src, long long stride) {
+  unsigned short sum_s_cols[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // u16 column sums, activity.rs:76
+  uint32_t sum_s2_cols[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int j = 0; j < 8; j++)
+    for (int i = 0; i < 8; i++) {
+      const unsigned short s = (unsigned short)src[j * stride + i];
+      sum_s_cols[i] = (unsigned short)(sum_s_cols[i] + s);
+      sum_s2_cols[i] += (uint32_t)s * (uint32_t)s;
+    }
+  unsigned long long sum_s = 0, sum_s2 = 0;
+  for (int i = 0; i < 8; i++) {
+    sum_s += sum_s_cols[i];
+    sum_s2 += sum_s2_cols[i];
+  }
+  const unsigned long long v = sum_s2 - ((sum_s * sum_s + 32) >> 6);
+  return v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)v;  // u32::try_from(..).unwrap_or(u32::MAX)
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) activity_mask_kernel(PlaneRef luma, int wb, int hb, int bit_depth,
+                                                            uint32_t *variances, uint32_t *scales) {
+  const long long n = (long long)wb * hb;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / wb), x = (int)(i - (long long)y * wb);
+    const uint32_t v = variance_8x8_px<T>(px<T>(luma, 8 * x, 8 * y), luma.stride);
+    variances[i] = v;
+    if (scales) scales[i] = apply_ssim_boost(1u << 14, v, v, bit_depth);
+  }
+}
+
+}  // namespace
+
+extern "C" int b200_activity_mask_dev(b200_ctx *ctx, const b200_plane *luma, int bit_depth,
+                                      uint32_t *d_variances, uint32_t *d_scales) {
+  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+  B200_REQUIRE(ctx, luma && luma->data && (luma->bpp == 1 || luma->bpp == 2), "bad plane");
+  B200_REQUIRE(ctx, bit_depth == 8 || bit_depth == 10 || bit_depth == 12, "bit depth %d not in {8,10,12}", bit_depth);
+  B200_REQUIRE(ctx, (luma->bpp == 1) == (bit_depth == 8), "bpp %d does not match bit depth %d", luma->bpp, bit_depth);
+  const int wb = (luma->width + 7) >> 3, hb = (luma->height + 7) >> 3;
+  // the region is rounded up to whole 8x8 blocks (activity.rs:26-35): it reads into the padding
+  B200_REQUIRE(ctx, luma->pad >= wb * 8 - luma->width && luma->pad >= hb * 8 - luma->height,
+               "plane padding %d too small for the %dx%d region rounded up to 8", luma->pad, luma->width, luma->height);
+  B200_REQUIRE(ctx, d_variances != nullptr, "NULL output");
+  B200_CUDA(ctx, cudaSetDevice(ctx->device));
+  const long long n = (long long)wb * hb;
+  const int grid = (int)std::min<long long>((n + 127) / 128, (long long)ctx->num_sms * 32);
+  PlaneRef p{luma->data, luma->stride};
+  if (luma->bpp == 1)
+    activity_mask_kernel<uint8_t><<<grid, 128, 0, ctx->stream>>>(p, wb, hb, bit_depth, d_variances, d_scales);
+  else
+    activity_mask_kernel<uint16_t><<<grid, 128, 0, ctx->stream>>>(p, wb, hb, bit_depth, d_variances, d_scales);
+  B200_LAUNCH_CHECK(ctx);
+  return B200_OK;
+}
