@@ -74,6 +74,31 @@ std::uint32_t get_satd(const PlaneRegion<T> &plane_org, const PlaneRegion<T> &pl
                        plane_ref.asm_stride(), (int)w, (int)h, (int)sizeof(T));
 }
 
+// dist.rs:234-283 / asm/x86/dist/sse.rs:118-148.  scale: one DistortionScale (Q14) per 4x4 chunk,
+// scale_stride in ENTRIES like the Rust signature.
+template <typename T>
+std::uint64_t get_weighted_sse(const PlaneRegion<T> &src1, const PlaneRegion<T> &src2, const std::uint32_t *scale,
+                               std::size_t scale_stride, std::size_t w, std::size_t h, std::size_t /*bit_depth*/,
+                               CpuFeatureLevel cpu) {
+  require_cuda(cpu);
+  if (w > 128 || h > 128 || (w & 3) || (h & 3)) throw std::invalid_argument("get_weighted_sse: bad block size");
+  if (src1.width < w || src1.height < h || src2.width < w || src2.height < h)
+    throw std::invalid_argument("get_weighted_sse: region smaller than the block");
+  return b200_weighted_sse(src1.data_ptr(), src1.asm_stride(), src2.data_ptr(), src2.asm_stride(), scale,
+                           (std::ptrdiff_t)(scale_stride * sizeof(std::uint32_t)), (int)w, (int)h, (int)sizeof(T));
+}
+
+// dist.rs:302-372 / asm/x86/dist/cdef_dist.rs:56-118 (w, h <= 8)
+template <typename T>
+std::uint32_t cdef_dist_kernel(const PlaneRegion<T> &src, const PlaneRegion<T> &dst, std::size_t w, std::size_t h,
+                               std::size_t bit_depth, CpuFeatureLevel cpu) {
+  require_cuda(cpu);
+  if (w > 8 || h > 8 || w == 0 || h == 0) throw std::invalid_argument("cdef_dist_kernel: w and h must be <= 8");
+  if ((sizeof(T) == 1) != (bit_depth == 8)) throw std::invalid_argument("cdef_dist_kernel: pixel type / bit depth");
+  return b200_cdef_dist_kernel(src.data_ptr(), src.asm_stride(), dst.data_ptr(), dst.asm_stride(), (int)w, (int)h,
+                               (int)bit_depth, nullptr);
+}
+
 // transform/mod.rs:56-123
 enum class TxType : int { DCT_DCT = 0, ADST_DCT, DCT_ADST, ADST_ADST, FLIPADST_DCT, DCT_FLIPADST,
                           FLIPADST_FLIPADST, ADST_FLIPADST, FLIPADST_ADST, IDTX, V_DCT, H_DCT, V_ADST,
