@@ -154,7 +154,10 @@ typedef struct {
  * d_cand_offsets: NULL, or nblocks+1 CSR offsets when cands are grouped by block in
  *   ascending block order — required for d_best (per-block first-minimum winner in list
  *   order, the serial scan's tie-break, me.rs:898,974).
- * Outputs (each may be NULL): d_sad[ncands], d_cost[ncands], d_best[nblocks]. */
+ * Outputs (each may be NULL): d_sad[ncands], d_cost[ncands], d_best[nblocks].
+ * Padding contract (the reference's, frame/mod.rs:22-23 + me.rs:339-362): candidates are accepted
+ * up to get_mv_range's border, 16 + block size pixels outside the frame, so both planes must be
+ * readable that far (b200_plane.pad); nothing checks it per candidate. */
 int b200_me_candidates_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
                            const b200_block *d_blocks, size_t nblocks, const b200_cand *d_cands,
                            size_t ncands, const uint32_t *d_cand_offsets, const int16_t *d_pmv,
