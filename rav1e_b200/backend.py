@@ -119,6 +119,7 @@ def lib():
             f.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t] + extra
             f.restype = u32
     L.b200_me_candidates_dev.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
+    L.b200_encode_tx_blocks_dev.argtypes = [vp, pp, pp, pp, vp, sz, vp, i32, i32, i32, u32, u32, i32, i32, vp, vp, vp, vp, vp]
     L.b200_inverse_transform_add_dev.argtypes = [vp, vp, pp, vp, sz, i32, i32, i32]
     L.b200_quantize_dev.argtypes = [vp, vp, sz, i32, i32, u32, u32, i32, i32, vp, vp, vp, vp]
     L.b200_weighted_sse.restype = C.c_uint64
@@ -280,6 +281,13 @@ class Context:
         self.check(self.L.b200_quantize_dev(self.h, _dev_ptr(d_coeffs), n, tx_size, tx_type, dc_quant, ac_quant,
                                             int(is_intra), int(coeff_i32), _dev_ptr(d_q), _dev_ptr(d_r),
                                             _dev_ptr(d_eob), _dev_ptr(d_dist)))
+
+    def encode_tx_blocks_dev(self, cur, ref, rec, d_blocks, n, d_mv_src, tx_size, tx_type, bd, dc_quant, ac_quant,
+                             is_intra, need_recon, d_coeffs, d_q, d_r, d_eob=None, d_dist=None):
+        self.check(self.L.b200_encode_tx_blocks_dev(
+            self.h, C.byref(cur), C.byref(ref), C.byref(rec) if rec is not None else None, _dev_ptr(d_blocks), n,
+            _dev_ptr(d_mv_src), tx_size, tx_type, bd, dc_quant, ac_quant, int(is_intra), int(need_recon),
+            _dev_ptr(d_coeffs), _dev_ptr(d_q), _dev_ptr(d_r), _dev_ptr(d_eob), _dev_ptr(d_dist)))
 
     def inverse_transform_add_dev(self, d_coeffs, dst, d_blocks, n, tx_size, tx_type, bd):
         self.check(self.L.b200_inverse_transform_add_dev(self.h, _dev_ptr(d_coeffs), C.byref(dst), _dev_ptr(d_blocks),

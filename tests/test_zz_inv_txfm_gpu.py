@@ -101,3 +101,32 @@ def test_encode_tx_block_chain_on_device():
     assert np.abs(got.astype(np.int32) - cur.astype(np.int32)).mean() < 12
     for pl in (dcur, dref, drec):
         c.plane_free(pl)
+
+
+def test_encode_tx_blocks_one_call_equals_the_three_steps():
+    """b200_encode_tx_blocks_dev == b200_fwd_txfm_residual_dev + b200_quantize_dev +
+    b200_inverse_transform_add_dev called one after the other."""
+    import torch
+    c = G.ctx()
+    W, H, PAD = 192, 128, 64
+    cur, ref = G.make_planes(W, H, PAD, np.uint8, seed=44)
+    _, dcur = G.both_planes(cur, PAD)
+    _, dref = G.both_planes(ref, PAD)
+    blocks = G.grid_blocks(W, H, 16, 16)
+    n = len(blocks)
+    d_blocks = G.to_dev(blocks)
+    mk = lambda: torch.empty((n, 256), dtype=torch.int16, device="cuda")
+    co1, q1, r1, co2, q2, r2 = mk(), mk(), mk(), mk(), mk(), mk()
+    e1, e2 = (torch.zeros(n, dtype=torch.int16, device="cuda") for _ in range(2))
+    d1, d2 = (torch.zeros(n, dtype=torch.int64, device="cuda") for _ in range(2))
+    rec1, rec2 = c.plane_from_host(ref, 0), c.plane_from_host(ref, 0)
+    c.fwd_txfm_residual_dev(dcur, dref, d_blocks, n, None, co1, 2, 0, 8)
+    c.quantize_dev(co1, n, 2, 0, 70, 60, False, False, q1, r1, e1, d1)
+    c.inverse_transform_add_dev(r1, rec1, d_blocks, n, 2, 0, 8)
+    c.encode_tx_blocks_dev(dcur, dref, rec2, d_blocks, n, None, 2, 0, 8, 70, 60, False, True, co2, q2, r2, e2, d2)
+    c.synchronize()
+    for a, b in ((co1, co2), (q1, q2), (r1, r2), (e1, e2), (d1, d2)):
+        assert torch.equal(a, b)
+    np.testing.assert_array_equal(download(c, rec1, ref), download(c, rec2, ref))
+    for pl in (dcur, dref, rec1, rec2):
+        c.plane_free(pl)
