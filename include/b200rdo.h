@@ -51,7 +51,13 @@ int b200_ctx_create(int device, b200_ctx **out);
 void b200_ctx_destroy(b200_ctx *ctx);
 const char *b200_last_error(const b200_ctx *ctx); /* ctx may be NULL: global last error */
 /* Enqueue on an externally owned cudaStream_t (e.g. the host framework's current stream;
- * NULL = the CUDA default stream).  b200_ctx_reset_stream returns to the ctx's own stream. */
+ * NULL = the CUDA default stream).  b200_ctx_reset_stream returns to the ctx's own stream.
+ * ORDERING CONTRACT: every `*_dev` entry point only enqueues work on the ctx's stream.  The ctx's
+ * own stream is created cudaStreamNonBlocking, i.e. it does NOT synchronise with the legacy default
+ * stream: device buffers a caller fills on another stream (a framework's zero-fill, an upload) must
+ * be complete - or that stream must be the one given to b200_ctx_set_stream - before they are
+ * handed to a `*_dev` call, and results must be read after b200_ctx_synchronize() or on the same
+ * stream. */
 int b200_ctx_set_stream(b200_ctx *ctx, void *cuda_stream);
 int b200_ctx_reset_stream(b200_ctx *ctx);
 void *b200_ctx_get_stream(b200_ctx *ctx);
@@ -301,6 +307,19 @@ int b200_weighted_sse_dev(b200_ctx *ctx, const b200_plane *src1, const b200_plan
 int b200_cdef_dist_dev(b200_ctx *ctx, const b200_plane *src, const b200_plane *dst,
                        const b200_block *d_blocks, size_t nblocks, int w, int h, int bit_depth,
                        uint32_t *d_out, uint32_t *d_raw);
+
+/* ---------------------------------------------------------------- RDO cost (rdo.rs)
+ * compute_rd_cost (rdo.rs:718-723): fi.lambda.mul_add(rate as f64 / 8.0, distortion.0 as f64) - the
+ * only floating-point value on the path.  Device DFMA + round-to-nearest conversions: bit-identical
+ * to f64::mul_add (0 ULP; the north star allows 1).
+ * Batched: d_cost[i] (may be NULL when d_best is asked for) for n (rate, distortion) pairs; with
+ * d_group_offsets (ngroups + 1 CSR offsets) d_best[g] = index inside group g of its first minimum
+ * (the RDO loops' strict `rd < best.rd_cost`, e.g. rdo.rs:1003-1009), 0xffffffff for an empty group. */
+int b200_compute_rd_cost_dev(b200_ctx *ctx, double lambda, const uint32_t *d_rate,
+                             const uint64_t *d_distortion, size_t n, const uint32_t *d_group_offsets,
+                             size_t ngroups, double *d_cost, uint32_t *d_best);
+/* Per-call form (host scalars in, cost out; one launch on the calling thread's context). */
+double b200_compute_rd_cost(double lambda, uint32_t rate, uint64_t distortion);
 
 /* ------------------------------------------------ forward transform (transform/forward.rs)
  * The reference has no extern-C symbol here: the boundary is the generic Rust fn

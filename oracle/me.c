@@ -4,7 +4,7 @@
  * :1445-1461, full_search :1464-1509, get_mv_rate :1512-1523).
  * TEST INFRASTRUCTURE ONLY (see oracle.h).
  *
- * `ILog::ilog` comes from v_frame 0.3.9 (off disk): bits - leading_zeros, 0 for x <= 0.
+ * `ILog::ilog` comes from v_frame 0.3.9 (off disk): bits - leading_zeros of the value's own width (0 for x == 0).
  * No reference test pins it ("parity unpinned" for the rate term); SAD itself is pinned.
  */
 #include "oracle.h"
@@ -26,9 +26,11 @@ int orc_num_threads(void) {
 #endif
 }
 
-static inline uint32_t ilog_i16(int16_t v) { /* v_frame ILog::ilog for i16 */
-  if (v <= 0) return 0;
-  return 32 - (uint32_t)__builtin_clz((uint32_t)v);
+static inline uint32_t ilog_i16(int16_t v) { /* v_frame ILog::ilog for i16: 16 - leading_zeros */
+  if (v == 0) return 0;
+  /* bits of the i16 pattern: a negative value (only i16::MIN survives the wrapping abs) has no
+   * leading zeros -> 16 */
+  return 32 - (uint32_t)__builtin_clz((uint32_t)(uint16_t)v);
 }
 
 /* me.rs:1516-1519 diff_to_rate */

@@ -217,6 +217,12 @@ void orc_cdef_filter_plane(const void *in, ptrdiff_t in_stride, void *out, ptrdi
 
 int orc_num_threads(void);
 
+/* -------------------------------------------------------------------- rdo.rs
+ * compute_rd_cost (rdo.rs:718-723): lambda.mul_add(rate / 8.0, distortion as f64). */
+double orc_compute_rd_cost(double lambda, uint32_t rate, uint64_t distortion);
+void orc_compute_rd_cost_batch(double lambda, const uint32_t *rate, const uint64_t *distortion,
+                               size_t n, double *out);
+
 #ifdef __cplusplus
 }
 #endif

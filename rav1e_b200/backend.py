@@ -126,6 +126,9 @@ def lib():
     L.b200_weighted_sse.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t, vp, C.c_ssize_t, i32, i32, i32]
     L.b200_cdef_dist_kernel.restype = u32
     L.b200_cdef_dist_kernel.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t, i32, i32, i32, vp]
+    L.b200_compute_rd_cost_dev.argtypes = [vp, C.c_double, vp, vp, sz, vp, sz, vp, vp]
+    L.b200_compute_rd_cost.argtypes = [C.c_double, u32, C.c_uint64]
+    L.b200_compute_rd_cost.restype = C.c_double
     L.b200_activity_mask_dev.argtypes = [vp, pp, i32, vp, vp]
     L.b200_weighted_sse_dev.argtypes = [vp, pp, pp, vp, sz, i32, i32, vp, sz, vp]
     L.b200_cdef_dist_dev.argtypes = [vp, pp, pp, vp, sz, i32, i32, i32, vp, vp]
@@ -292,6 +295,11 @@ class Context:
     def inverse_transform_add_dev(self, d_coeffs, dst, d_blocks, n, tx_size, tx_type, bd):
         self.check(self.L.b200_inverse_transform_add_dev(self.h, _dev_ptr(d_coeffs), C.byref(dst), _dev_ptr(d_blocks),
                                                          n, tx_size, tx_type, bd))
+
+    # ---- RDO cost
+    def compute_rd_cost_dev(self, lam, d_rate, d_dist, n, d_cost=None, d_offsets=None, ngroups=0, d_best=None):
+        self.check(self.L.b200_compute_rd_cost_dev(self.h, float(lam), _dev_ptr(d_rate), _dev_ptr(d_dist), n,
+                                                   _dev_ptr(d_offsets), ngroups, _dev_ptr(d_cost), _dev_ptr(d_best)))
 
     # ---- RDO distortion
     def weighted_sse_dev(self, src1, src2, d_blocks, n, w, h, d_scale, scale_stride, d_out):

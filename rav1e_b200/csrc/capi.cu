@@ -59,6 +59,7 @@ extern "C" void b200_ctx_destroy(b200_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->dwork) cudaFree(ctx->dwork);
+  for (auto &kv : ctx->scan_dev) cudaFree(kv.second);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -132,18 +133,30 @@ int b200_reserve_dwork(b200_ctx *ctx, size_t bytes) {
   return B200_OK;
 }
 
+// The context behind the per-call (reference-signature) entry points: ONE PER HOST THREAD, created
+// on first use and destroyed with the thread.  rav1e calls its kernels concurrently from one rayon
+// worker per tile (encoder.rs:3253) and the asm functions are re-entrant; a thread-local context
+// (own stream, own scratch) keeps the per-call forms re-entrant too, with no lock anywhere.
+namespace {
+struct TlsCtx {
+  b200_ctx *ctx = nullptr;
+  ~TlsCtx() {
+    if (ctx) b200_ctx_destroy(ctx);
+  }
+};
+}  // namespace
+
 b200_ctx *b200_default_ctx() {
-  static b200_ctx *ctx = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
+  static thread_local TlsCtx t;
+  if (!t.ctx) {
     int dev = 0;
     if (const char *e = getenv("B200RDO_DEVICE")) dev = atoi(e);
-    if (b200_ctx_create(dev, &ctx) != B200_OK) {
+    if (b200_ctx_create(dev, &t.ctx) != B200_OK) {
       fprintf(stderr, "b200rdo: FATAL: %s\n", g_b200_last_error);
       abort();  // no CPU fallback, by design
     }
-  });
-  return ctx;
+  }
+  return t.ctx;
 }
 
 // ------------------------------------------------------------------ planes

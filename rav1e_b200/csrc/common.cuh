@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
+#include <vector>
 
 #include "../../include/b200rdo.h"
 
@@ -24,6 +26,11 @@ struct b200_ctx {
   void *dwork = nullptr;
   size_t dwork_bytes = 0;
   int async_batch = 0;  // host-buffer forms skip their final synchronize (b200_ctx_set_async)
+  // device copies of the coefficient scan tables, key = tx_size * 4 + kind (quantize.cu); owned
+  // by the context and freed with it.  The host images stay alive with them (the upload is
+  // stream-ordered on `stream`).
+  std::map<int, uint16_t *> scan_dev;
+  std::map<int, std::vector<uint16_t>> scan_host;
   char err[512] = {0};
 };
 
@@ -43,9 +50,11 @@ inline int b200_fail(b200_ctx *ctx, int status, const char *fmt, ...) {
 #define B200_CUDA(ctx, expr)                                                              \
   do {                                                                                    \
     cudaError_t _e = (expr);                                                              \
-    if (_e != cudaSuccess)                                                                \
+    if (_e != cudaSuccess) {                                                              \
+      (void)cudaGetLastError(); /* reported here: do not leave it for a later launch check */ \
       return b200_fail((ctx), _e == cudaErrorMemoryAllocation ? B200_ERR_OOM : B200_ERR_CUDA, \
                        "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+    }                                                                                     \
   } while (0)
 
 #define B200_REQUIRE(ctx, cond, ...)                              \
@@ -105,8 +114,10 @@ __host__ __device__ inline MvRange b200_mv_range(int w_in_b, int h_in_b, int bo_
 __device__ __forceinline__ uint32_t b200_diff_to_rate(int diff16, int allow_hp) {
   int d = (int)(short)diff16;          // i16 subtraction wraps like Rust release builds
   d = allow_hp ? d : (d >> 1);         // arithmetic shift
-  int a = (int)(short)(d < 0 ? -d : d);
-  return a > 0 ? 2u * (32u - (uint32_t)__clz(a)) : 0u;
+  // i16::abs wraps for i16::MIN in release builds and ILog::ilog counts the bits of the i16
+  // pattern: |-32768| -> 0x8000 -> ilog 16 (v_frame 0.3.9 math.rs)
+  const uint32_t a = (uint32_t)(uint16_t)(d < 0 ? -d : d);
+  return a ? 2u * (32u - (uint32_t)__clz(a)) : 0u;
 }
 
 __device__ __forceinline__ uint32_t b200_mv_rate(int a_row, int a_col, int b_row, int b_col,

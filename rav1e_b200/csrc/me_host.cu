@@ -1,8 +1,6 @@
 // me_host.cu — host-buffer (`*_batch`) and per-call reference-signature entry points of the
 // SAD/SATD/ME path.  They copy the caller's host buffers (pinned or pageable) to a stream-
 // ordered device allocation, run the same device kernels as the `_dev` forms (me_kernels.cu) and copy results back before returning.
-#include <mutex>
-
 #include "common.cuh"
 
 namespace {
@@ -244,12 +242,9 @@ extern "C" int b200_me_full_search_batch(b200_ctx *ctx, const b200_host_plane *c
 // (two tiny H2D copies + one launch + one D2H); the batched forms are the product path.
 namespace {
 
-std::mutex g_percall_mu;
-
 uint32_t percall_dist(const void *org, ptrdiff_t org_stride, const void *ref, ptrdiff_t ref_stride,
                       int w, int h, int bpp, int use_satd) {
   b200_ctx *ctx = b200_default_ctx();
-  std::lock_guard<std::mutex> lock(g_percall_mu);
   b200_host_plane hc{org, org_stride, w, h, 0, bpp};
   b200_host_plane hr{ref, ref_stride, w, h, 0, bpp};
   b200_block blk{0, 0};

@@ -148,13 +148,17 @@ __device__ __forceinline__ uint32_t partial_sad(const BlockCtx &c, int dx, int d
       if (8 * (j + 1) >= c.total) break;  // uniform
     }
   } else {
-    for (int i = sub; i < c.total; i += 8) {  // total is a multiple of 8 here
+    // same row-end rule as the cached path (a 16x64 8-bit block has 4 words per row: two rows per
+    // step); uniform trip count so every full-mask shuffle is executed by all 32 lanes
+    for (int i0 = 0; i0 < c.total; i0 += 8) {
+      const int i = i0 + sub;
+      const bool on = i < c.total;
       const int y = i >> c.log_nw, k = i & (nw - 1);
-      const uint32_t *q = rw + (long long)y * rpw + k;
+      const uint32_t *q = rw + (on ? (long long)y * rpw + k : 0);
       const uint32_t w0 = __ldg(q);
       uint32_t w1 = __shfl_down_sync(0xffffffffu, w0, 1);
-      if (rsh && (k & 7) == 7) w1 = __ldg(q + 1);
-      acc = word_sad<T>(__funnelshift_r(w0, w1, rsh * 8), load_word(c.org, c.org_pitch, y, k), acc);
+      if (rsh && ((k & (seg - 1)) == seg - 1 || !on)) w1 = __ldg(q + 1);
+      if (on) acc = word_sad<T>(__funnelshift_r(w0, w1, rsh * 8), load_word(c.org, c.org_pitch, y, k), acc);
     }
   }
   return acc;

@@ -16,9 +16,6 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
-#include <map>
-#include <mutex>
-#include <tuple>
 #include <vector>
 
 #include "common.cuh"
@@ -197,24 +194,29 @@ void make_scan(int tx_size, int kind, std::vector<uint16_t> *scan, std::vector<u
   for (size_t i = 0; i < scan->size(); i++) (*iscan)[(*scan)[i]] = (uint16_t)i;
 }
 
-// device copies of the scan tables, one per (device, tx_size, kind), created on first use
+// device copies of the scan tables, one per (ctx, tx_size, kind), created on first use and owned by
+// the context (b200_ctx_destroy frees them); uploaded on the ctx's stream, so the kernel that
+// follows on the same stream is ordered behind the copy
 int scan_tables(b200_ctx *ctx, int tx_size, int kind, const uint16_t **d_scan, const uint16_t **d_iscan) {
-  static std::mutex mu;
-  static std::map<std::tuple<int, int, int>, uint16_t *> cache;
-  std::lock_guard<std::mutex> lock(mu);
-  const auto key = std::make_tuple(ctx->device, tx_size, kind);
-  auto it = cache.find(key);
-  if (it == cache.end()) {
+  const int key = tx_size * 4 + kind;
+  const size_t n = (size_t)std::min(kTxW[tx_size], 32) * std::min(kTxH[tx_size], 32);
+  auto it = ctx->scan_dev.find(key);
+  if (it == ctx->scan_dev.end()) {
     std::vector<uint16_t> scan, iscan;
     make_scan(tx_size, kind, &scan, &iscan);
+    std::vector<uint16_t> &img = ctx->scan_host[key];
+    img = scan;
+    img.insert(img.end(), iscan.begin(), iscan.end());
     uint16_t *d = nullptr;
-    const size_t n = scan.size();
     B200_CUDA(ctx, cudaMalloc(&d, 2 * n * sizeof(uint16_t)));
-    B200_CUDA(ctx, cudaMemcpy(d, scan.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    B200_CUDA(ctx, cudaMemcpy(d + n, iscan.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    it = cache.emplace(key, d).first;
+    const cudaError_t e = cudaMemcpyAsync(d, img.data(), 2 * n * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+      cudaFree(d);
+      ctx->scan_host.erase(key);
+      B200_CUDA(ctx, e);
+    }
+    it = ctx->scan_dev.emplace(key, d).first;
   }
-  const size_t n = (size_t)std::min(kTxW[tx_size], 32) * std::min(kTxH[tx_size], 32);
   *d_scan = it->second;
   *d_iscan = it->second + n;
   return B200_OK;

@@ -138,7 +138,6 @@ int check_pair(b200_ctx *ctx, const b200_plane *a, const b200_plane *b) {
   return B200_OK;
 }
 
-std::mutex g_percall_mu;
 
 // stage two host blocks (w x h, byte strides) into a scratch device plane pair
 struct HostPair {
@@ -220,7 +219,6 @@ extern "C" uint64_t b200_weighted_sse(const void *src, ptrdiff_t src_stride, con
                                       ptrdiff_t dst_stride, const uint32_t *scale,
                                       ptrdiff_t scale_stride_bytes, int w, int h, int bpp) {
   b200_ctx *ctx = b200_default_ctx();
-  std::lock_guard<std::mutex> lock(g_percall_mu);
   auto die = [&](const char *what) {
     fprintf(stderr, "b200rdo: FATAL: per-call weighted_sse failed (%s): %s\n", what, b200_last_error(ctx));
     abort();  // the reference has no error return here either; never silently wrong
@@ -249,7 +247,6 @@ extern "C" uint64_t b200_weighted_sse(const void *src, ptrdiff_t src_stride, con
 extern "C" uint32_t b200_cdef_dist_kernel(const void *src, ptrdiff_t src_stride, const void *dst,
                                           ptrdiff_t dst_stride, int w, int h, int bit_depth, uint32_t ret[3]) {
   b200_ctx *ctx = b200_default_ctx();
-  std::lock_guard<std::mutex> lock(g_percall_mu);
   auto die = [&](const char *what) {
     fprintf(stderr, "b200rdo: FATAL: per-call cdef_dist_kernel failed (%s): %s\n", what, b200_last_error(ctx));
     abort();

@@ -11,7 +11,10 @@ _CTX = None
 def ctx():
     global _CTX
     if _CTX is None:
-        _CTX = B.Context(0)
+        # kernels go to torch's current stream: the tests fill torch tensors (torch.zeros, .cuda())
+        # on that stream and the ctx's own stream is non-blocking, so sharing one stream is what
+        # orders "fill, then launch" (the ordering contract stated in include/b200rdo.h)
+        _CTX = B.Context(0, use_torch_stream=True)
     return _CTX
 
 
@@ -44,8 +47,9 @@ def make_planes(width, height, pad, dtype=np.uint8, seed=0, bit_depth=8, smooth=
     dx, dy = shift if shift is not None else (3, -2)
     ref = base[32:32 + height, 32:32 + width]
     cur = base[32 + dy:32 + dy + height, 32 + dx:32 + dx + width] + rng.normal(0, 2, (height, width))
-    ref = np.clip(np.rint(ref), 0, maxv).astype(dtype)
-    cur = np.clip(np.rint(cur), 0, maxv).astype(dtype)
+    # C-contiguous: callers hand .ctypes.data / .strides[0] to the C ABI
+    ref = np.ascontiguousarray(np.clip(np.rint(ref), 0, maxv).astype(dtype))
+    cur = np.ascontiguousarray(np.clip(np.rint(cur), 0, maxv).astype(dtype))
     return cur, ref
 
 

@@ -50,6 +50,12 @@ SEARCH_CASES = [
     (4, 4, np.uint8, 8, 3, 24, 100, True),
     (16, 16, np.uint16, 10, 3, 24, 2400, True),
     (32, 16, np.uint16, 12, 1, 0, 9000, True),
+    # blocks beyond the lanes' org-word cache with fewer than 8 words per row (the uncached path
+    # covers two rows per step) and its 16-bit counterpart
+    (16, 64, np.uint8, 8, 3, 24, 900, True),
+    (16, 64, np.uint8, 8, 1, 0, 0, False),
+    (8, 32, np.uint16, 10, 3, 16, 900, True),
+    (64, 16, np.uint16, 10, 1, 0, 2400, True),
 ]
 
 

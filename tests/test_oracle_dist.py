@@ -91,6 +91,10 @@ def test_mv_rate_and_range():
     assert L.orc_get_mv_rate(mv(-1, 0), mv(0, 0), 0) == 2
     assert L.orc_get_mv_rate(mv(1, 0), mv(0, 0), 0) == 0
     assert L.orc_get_mv_rate(mv(1, 0), mv(0, 0), 1) == 2
+    # i16 wrap: -16384 - 16384 = -32768; with hp the wrapping abs keeps i16::MIN, whose 16-bit
+    # pattern has no leading zeros -> ilog 16 -> rate 32; without hp: -32768 >> 1 = -16384 -> ilog 15
+    assert L.orc_get_mv_rate(mv(-16384, 0), mv(16384, 0), 1) == 32
+    assert L.orc_get_mv_rate(mv(-16384, 0), mv(16384, 0), 0) == 30
     # cost = 256*sad + min(r1, r2+1)*lambda
     assert L.orc_mv_cost(10, mv(8, 0), mv(0, 0), mv(8, 0), 100, 0) == 2560 + 1 * 100
     import ctypes as C

@@ -1,14 +1,12 @@
 """GPU parity for b200_activity_mask_dev == oracle (ActivityMask::from_plane + fill_scales).
-Written after the round's GPU budget was spent: xfail(strict=False) until it has run on hardware
-(the per-thread variance function is already checked on the CPU by tests/test_activity.py)."""
+(The per-thread variance function is also checked on the CPU by tests/test_activity.py.)"""
 import numpy as np
 import pytest
 
 from tests import gpu_util as G
 from tests.test_activity import oracle_mask
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="activity-mask kernel not yet verified on hardware")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("dtype,bd", [(np.uint8, 8), (np.uint16, 10), (np.uint16, 12)])
