@@ -493,6 +493,31 @@ typedef struct {
   uint8_t pad_;
 } b200_intra_item;
 
+/* get_intra_edges (partition.rs:639-898) for a batch of transform blocks of one PlaneRegion: builds
+ * the IntraEdge buffers b200_predict_intra_dev consumes, with the reference's availability rules
+ * (has_top_right / has_bottom_left, recon_intra.rs:174-452), border constants and replication.
+ * `plane` with (rect_x, rect_y, rect_w, rect_h) is the `dst` region (tile) the offsets are relative
+ * to; plane->width / height are plane_cfg.width / height; xdec / ydec the plane's decimation.
+ * d_edges: nitems x 257 pixels (top-left at [128]); entries outside
+ * [128 - init_left, 129 + init_above) are zero (uninitialised upstream); d_lens (may be NULL):
+ * {init_left, init_above} per item = the slice lengths IntraEdge::new records.  What may share a
+ * batch is the caller's business: blocks whose neighbours are final (all of a frame in the lookahead,
+ * one wavefront of the encode loop). */
+typedef struct {
+  int16_t po_x, po_y;     /* PlaneOffset of the transform block inside the region, pixels */
+  int16_t part_x, part_y; /* partition_bo (TileBlockOffset), 4x4 luma units */
+  uint8_t bx, by;         /* transform-block index inside the partition */
+  uint8_t bsize;          /* partition BlockSize discriminant 0..21 (partition.rs:130-153) */
+  uint8_t tx_size;        /* TxSize discriminant 0..18 */
+  uint8_t mode;           /* PredictionMode 0..13, 255 = None (every edge wanted) */
+  int8_t angle_delta;     /* IntraParam::AngleDelta, else 0 */
+  uint8_t enable_ief;     /* enable_intra_edge_filter */
+  uint8_t pad_;
+} b200_edge_item;
+int b200_get_intra_edges_dev(b200_ctx *ctx, const b200_plane *plane, int rect_x, int rect_y, int rect_w,
+                             int rect_h, int xdec, int ydec, int bit_depth, const b200_edge_item *d_items,
+                             size_t nitems, void *d_edges, uint8_t *d_lens);
+
 /* Batched: one prediction per item (typically blocks x candidate modes sharing edge buffers);
  * d_out receives nitems packed w x h blocks (pixels). */
 int b200_predict_intra_dev(b200_ctx *ctx, const void *d_edges, const b200_intra_item *d_items,
@@ -503,6 +528,97 @@ int b200_predict_intra_dev(b200_ctx *ctx, const void *d_edges, const b200_intra_
 int b200_pred_cfl_ac_dev(b200_ctx *ctx, const b200_plane *luma, const b200_block *d_blocks,
                          size_t nblocks, int bw, int bh, int w_pad, int h_pad, int xdec, int ydec,
                          int16_t *d_ac);
+
+/* ------------------------------------------------ reference-signature symbols (MC / intra / CDEF)
+ * The reference's own extern "C" prototypes, symbol for symbol, with the ISA suffix replaced by
+ * `_cuda`: they slot into PUT_FNS / PUT_HBD_FNS / PREP_FNS / PREP_HBD_FNS / AVG_FNS / AVG_HBD_FNS
+ * (asm/x86/mc.rs:322-620), the per-mode calls of asm::x86::predict::dispatch_predict_intra and
+ * pred_cfl_ac (asm/x86/predict.rs:239-960), CDEF_FILTER_FNS and CDEF_DIR_{LBD,HBD}_FNS
+ * (asm/x86/cdef.rs:161-176, :236-260) unchanged.  Host pointers, BYTE strides, exactly the
+ * reference's argument lists (defined in rav1e_b200/csrc/ref_abi.cu over the per-call forms above).
+ * Re-entrant: each host thread runs on its own context (one rayon worker per tile, encoder.rs:3253). */
+/* X(name, FilterMode x, FilterMode y): table slot (x + 4 y) & 15, asm/x86/mc.rs:80-82, :394-405 */
+#define B200_FOR_EACH_MC_FILTER(X)                                                              \
+  X(8tap_regular, 0, 0) X(8tap_regular_smooth, 0, 1) X(8tap_regular_sharp, 0, 2)                \
+  X(8tap_smooth_regular, 1, 0) X(8tap_smooth, 1, 1) X(8tap_smooth_sharp, 1, 2)                  \
+  X(8tap_sharp_regular, 2, 0) X(8tap_sharp_smooth, 2, 1) X(8tap_sharp, 2, 2) X(bilin, 3, 3)
+#define B200_DECL_MC(NAME, MX, MY)                                                                            \
+  void rav1e_put_##NAME##_8bpc_cuda(uint8_t *dst, ptrdiff_t dst_stride, const uint8_t *src,                   \
+                                    ptrdiff_t src_stride, int w, int h, int mx, int my);                      \
+  void rav1e_put_##NAME##_16bpc_cuda(uint16_t *dst, ptrdiff_t dst_stride, const uint16_t *src,                \
+                                     ptrdiff_t src_stride, int w, int h, int mx, int my, int bitdepth_max);   \
+  void rav1e_prep_##NAME##_8bpc_cuda(int16_t *tmp, const uint8_t *src, ptrdiff_t src_stride, int w, int h,    \
+                                     int mx, int my);                                                         \
+  void rav1e_prep_##NAME##_16bpc_cuda(int16_t *tmp, const uint16_t *src, ptrdiff_t src_stride, int w, int h,  \
+                                      int mx, int my, int bitdepth_max);
+B200_FOR_EACH_MC_FILTER(B200_DECL_MC)
+#undef B200_DECL_MC
+void rav1e_avg_8bpc_cuda(uint8_t *dst, ptrdiff_t dst_stride, const int16_t *tmp1, const int16_t *tmp2, int w,
+                         int h);
+void rav1e_avg_16bpc_cuda(uint16_t *dst, ptrdiff_t dst_stride, const int16_t *tmp1, const int16_t *tmp2, int w,
+                          int h, int bitdepth_max);
+
+/* X(name, PredictionMode, PredictionVariant): asm/x86/predict.rs:21-120.  `topleft` = IntraEdge::
+ * top_left_ptr() (element 128 of the 257-pixel buffer, partition.rs:600-627). */
+#define B200_FOR_EACH_IPRED(X)                                                              \
+  X(dc, 0, 3) X(dc_128, 0, 0) X(dc_left, 0, 1) X(dc_top, 0, 2) X(v, 1, 3) X(h, 2, 3)        \
+  X(smooth, 9, 3) X(smooth_v, 10, 3) X(smooth_h, 11, 3) X(paeth, 12, 3)
+#define B200_DECL_IPRED(NAME, MODE, VAR)                                                                      \
+  void rav1e_ipred_##NAME##_8bpc_cuda(uint8_t *dst, ptrdiff_t stride, const uint8_t *topleft, int width,      \
+                                      int height, int angle);                                                 \
+  void rav1e_ipred_##NAME##_16bpc_cuda(uint16_t *dst, ptrdiff_t stride, const uint16_t *topleft, int width,   \
+                                       int height, int angle, int max_width, int max_height,                  \
+                                       int bitdepth_max);
+B200_FOR_EACH_IPRED(B200_DECL_IPRED)
+#undef B200_DECL_IPRED
+/* directional zones; `angle` = degrees | enable_ief << 10 | smooth << 9 (asm/x86/predict.rs:287-322);
+ * z2: dx, dy = distance from the block to the frame edge rounded up to 8 (:304-313) */
+void rav1e_ipred_z1_8bpc_cuda(uint8_t *dst, ptrdiff_t stride, const uint8_t *topleft, int width, int height,
+                              int angle);
+void rav1e_ipred_z2_8bpc_cuda(uint8_t *dst, ptrdiff_t stride, const uint8_t *topleft, int width, int height,
+                              int angle, int dx, int dy);
+void rav1e_ipred_z3_8bpc_cuda(uint8_t *dst, ptrdiff_t stride, const uint8_t *topleft, int width, int height,
+                              int angle);
+void rav1e_ipred_z1_16bpc_cuda(uint16_t *dst, ptrdiff_t stride, const uint16_t *topleft, int width, int height,
+                               int angle, int max_width, int max_height, int bitdepth_max);
+void rav1e_ipred_z2_16bpc_cuda(uint16_t *dst, ptrdiff_t stride, const uint16_t *topleft, int width, int height,
+                               int angle, int dx, int dy, int bitdepth_max);
+void rav1e_ipred_z3_16bpc_cuda(uint16_t *dst, ptrdiff_t stride, const uint16_t *topleft, int width, int height,
+                               int angle, int max_width, int max_height, int bitdepth_max);
+/* X(name, PredictionVariant): asm/x86/predict.rs:188-234 */
+#define B200_FOR_EACH_CFL(X) X(cfl, 3) X(cfl_128, 0) X(cfl_left, 1) X(cfl_top, 2)
+#define B200_DECL_CFL(NAME, VAR)                                                                              \
+  void rav1e_ipred_##NAME##_8bpc_cuda(uint8_t *dst, ptrdiff_t stride, const uint8_t *topleft, int width,      \
+                                      int height, const int16_t *ac, int alpha);                              \
+  void rav1e_ipred_##NAME##_16bpc_cuda(uint16_t *dst, ptrdiff_t stride, const uint16_t *topleft, int width,   \
+                                       int height, const int16_t *ac, int alpha, int bitdepth_max);
+B200_FOR_EACH_CFL(B200_DECL_CFL)
+#undef B200_DECL_CFL
+/* X(layout, xdec, ydec): asm/x86/predict.rs:142-186 */
+#define B200_FOR_EACH_CFL_AC(X) X(420, 1, 1) X(422, 1, 0) X(444, 0, 0)
+#define B200_DECL_CFL_AC(NAME, XDEC, YDEC)                                                                    \
+  void rav1e_ipred_cfl_ac_##NAME##_8bpc_cuda(int16_t *ac, const uint8_t *src, ptrdiff_t stride, int w_pad,    \
+                                             int h_pad, int width, int height);                               \
+  void rav1e_ipred_cfl_ac_##NAME##_16bpc_cuda(int16_t *ac, const uint16_t *src, ptrdiff_t stride, int w_pad,  \
+                                              int h_pad, int width, int height);
+B200_FOR_EACH_CFL_AC(B200_DECL_CFL_AC)
+#undef B200_DECL_CFL_AC
+
+/* X(size, xdec, ydec): CdefFilterFn, slot decimate_index(xdec, ydec) (asm/x86/cdef.rs:16-42, :146-167).
+ * The reference has no HBD filter asm (its CDEF_FILTER_HBD_FNS table is empty, :174-178): the
+ * `_16bpc` forms take CdefFilterHBDFn's argument list (:27-37) over the same padded u16 tile. */
+#define B200_FOR_EACH_CDEF_SIZE(X) X(4x4, 1, 1) X(4x8, 1, 0) X(8x8, 0, 0)
+#define B200_DECL_CDEF(NAME, XDEC, YDEC)                                                                      \
+  void rav1e_cdef_filter_##NAME##_cuda(uint8_t *dst, ptrdiff_t dst_stride, const uint16_t *tmp,               \
+                                       ptrdiff_t tmp_stride, int pri_strength, int sec_strength, int dir,     \
+                                       int damping);                                                          \
+  void rav1e_cdef_filter_##NAME##_16bpc_cuda(uint16_t *dst, ptrdiff_t dst_stride, const uint16_t *tmp,        \
+                                             ptrdiff_t tmp_stride, int pri_strength, int sec_strength,        \
+                                             int dir, int damping, int bitdepth_max);
+B200_FOR_EACH_CDEF_SIZE(B200_DECL_CDEF)
+#undef B200_DECL_CDEF
+int32_t rav1e_cdef_dir_8bpc_cuda(const uint8_t *img, ptrdiff_t stride, uint32_t *var);
+int32_t rav1e_cdef_dir_16bpc_cuda(const uint16_t *img, ptrdiff_t stride, uint32_t *var, int bitdepth_max);
 
 #ifdef __cplusplus
 }

@@ -217,6 +217,19 @@ void orc_cdef_filter_plane(const void *in, ptrdiff_t in_stride, void *out, ptrdi
 
 int orc_num_threads(void);
 
+/* ------------------------------------------- partition.rs / recon_intra.rs: intra edges */
+int orc_block_size_index(int w, int h);
+int orc_intra_avail_table(int kind, int bsize, uint8_t *out);
+int orc_has_top_right(int bsize, int mi_col, int mi_row, int top_available, int right_available, int tx_w,
+                      int row_off, int col_off, int ss_x, int ss_y);
+int orc_has_bottom_left(int bsize, int mi_col, int mi_row, int bottom_available, int left_available, int tx_h,
+                        int row_off, int col_off, int ss_x, int ss_y);
+void orc_get_intra_edges(void *edge, const void *region, ptrdiff_t stride, int bpp, int plane_w, int plane_h,
+                         int rect_x, int rect_y, int rect_w, int rect_h, int xdec, int ydec, int part_bo_x,
+                         int part_bo_y, int bx, int by, int partition_bsize, int po_x, int po_y, int tx_w,
+                         int tx_h, int bit_depth, int mode, int enable_intra_edge_filter, int angle_delta,
+                         int *out_init_left, int *out_init_above);
+
 /* -------------------------------------------------------------------- rdo.rs
  * compute_rd_cost (rdo.rs:718-723): lambda.mul_add(rate / 8.0, distortion as f64). */
 double orc_compute_rd_cost(double lambda, uint32_t rate, uint64_t distortion);

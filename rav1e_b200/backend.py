@@ -45,6 +45,9 @@ CAND_DTYPE = np.dtype([("block", "<u4"), ("mv_row", "<i2"), ("mv_col", "<i2")])
 INTRA_ITEM_DTYPE = np.dtype([("edge", "<u4"), ("ac", "<u4"), ("x", "<i2"), ("y", "<i2"),
                              ("angle", "<i2"), ("mode", "u1"), ("variant", "u1"), ("ief", "i1"),
                              ("left_len", "u1"), ("above_len", "u1"), ("pad_", "u1")])
+EDGE_ITEM_DTYPE = np.dtype([("po_x", "<i2"), ("po_y", "<i2"), ("part_x", "<i2"), ("part_y", "<i2"), ("bx", "u1"),
+                            ("by", "u1"), ("bsize", "u1"), ("tx_size", "u1"), ("mode", "u1"), ("angle_delta", "i1"),
+                            ("enable_ief", "u1"), ("pad_", "u1")])
 ME_RESULT_DTYPE = np.dtype(
     {"names": ["cost", "sad", "mv_row", "mv_col"],
      "formats": ["<u8", "<u4", "<i2", "<i2"], "offsets": [0, 8, 12, 14], "itemsize": 16})
@@ -170,6 +173,7 @@ def lib():
     L.b200_predict_intra.argtypes = [i32, i32, vp, C.c_ssize_t, i32, i32, i32, vp, i32, i32, vp] + [i32] * 6
     L.b200_predict_intra.restype = None
     L.b200_predict_intra_dev.argtypes = [vp, vp, vp, sz, vp, i32, i32, i32, i32, i32, vp]
+    L.b200_get_intra_edges_dev.argtypes = [vp, pp] + [i32] * 7 + [vp, sz, vp, vp]
     L.b200_pred_cfl_ac_dev.argtypes = [vp, pp, vp, sz] + [i32] * 6 + [vp]
     _LIB = L
     return L
@@ -341,6 +345,11 @@ class Context:
         self.check(self.L.b200_predict_intra_dev(self.h, _dev_ptr(d_edges), _dev_ptr(d_items), n,
                                                  _dev_ptr(d_ac), w, h, bit_depth, plane_w, plane_h,
                                                  _dev_ptr(d_out)))
+
+    def get_intra_edges_dev(self, plane, rect, xdec, ydec, bit_depth, d_items, n, d_edges, d_lens=None):
+        self.check(self.L.b200_get_intra_edges_dev(self.h, C.byref(plane), rect[0], rect[1], rect[2], rect[3], xdec,
+                                                   ydec, bit_depth, _dev_ptr(d_items), n, _dev_ptr(d_edges),
+                                                   _dev_ptr(d_lens)))
 
     def pred_cfl_ac_dev(self, luma, d_blocks, n, bw, bh, w_pad, h_pad, xdec, ydec, d_ac):
         self.check(self.L.b200_pred_cfl_ac_dev(self.h, C.byref(luma), _dev_ptr(d_blocks), n, bw, bh,

@@ -1118,6 +1118,283 @@ __global__ void __launch_bounds__(256, SATD ? B200_WARP_SATD_MINBLOCKS : 1) me_c
   }
 }
 
+// ---------------------------------------------------------------- sparse SATD lists, 8x8 chunks
+// The warp-per-block kernel above gives every thread one 8x8 chunk of one candidate and lets it
+// fetch its own 8 rows: 32 threads read 32 different places per load (32 cache lines per
+// instruction, L1 tag bound: 0.45 ms per 32-pair launch, 120 registers).  This kernel keeps the
+// thread-per-chunk arithmetic (no shuffles inside the transform) but separates fetching from
+// evaluating and pipelines the two across blocks.  Per warp, for the blocks b0, b1, ... it owns:
+//   header   (block position, candidate range)        loaded three blocks ahead        -> registers
+//   record   (this lane's candidate)                  loaded two blocks ahead          -> registers
+//   stage    the candidates' footprints, whole 16-byte aligned segments with lanes walking
+//            (row, segment) so one instruction touches H cache lines instead of 32, and the block's
+//            org rows, copied global -> shared with cp.async (LDGSTS: no registers, asynchronous)
+//            one block ahead into the other half of a double buffer;
+//   evaluate thread (candidate, chunk) reads its 8 rows from shared memory (3 words + funnel shift
+//            per row), runs the horizontal pass as IDP.4A chains (t = H.org - H.ref, 4 dp4a per
+//            output, nothing on the ALU pipe), the vertical pass as register butterflies whose last
+//            stage is folded into the sum (|a+b| + |a-b| = 2 max(|a|,|b|)); the chunk sums of a
+//            candidate meet by shuffle.
+// No dependent global load is waited for inside a block: every wait is for data requested at least
+// one block earlier.  Blocks with more than CPP = 32 / NCH candidates take their further batches
+// in place (not pipelined).  Same results as get_satd (dist.rs:156-221): exact integer arithmetic,
+// one final rounding.
+#ifndef B200_SATD_SPARSE_MINBLOCKS
+#define B200_SATD_SPARSE_MINBLOCKS 2
+#endif
+template <int W, int H>
+struct SatdSparseCfg {
+  static constexpr int CW = W / 8, CH = H / 8, NCH = CW * CH;
+  static constexpr int CPP = 32 / NCH;              // candidates per batch
+  static constexpr int NSEG = (W + 30) / 16;        // 16-byte segments covering W + 15 bytes
+  static constexpr int ROWW = NSEG * 4;             // words per staged row
+  static constexpr int CANDW0 = H * ROWW + 4 * CH;  // + one 16-byte pad per chunk row (bank spread)
+  static constexpr int CANDW = CANDW0 + ((8 - CANDW0 % 32 + 32) % 32);  // == 8 (mod 32), 16-byte multiple
+  static constexpr int ORGW = NCH * 16;             // org words: [chunk][row][2]
+  static constexpr int BUFW = CPP * CANDW + ORGW;   // one half of the double buffer
+  static constexpr int WARP_WORDS = 2 * BUFW;
+  static constexpr int WARPS = 8;
+  static constexpr size_t SMEM = (size_t)WARPS * WARP_WORDS * 4;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+struct SatdHdr {   // what a stage needs to know about a block
+  uint32_t lo, hi;  // candidate range
+  b200_block b;
+};
+struct SatdLane {  // this lane's candidate of a batch and what staging derived from it
+  b200_cand c;
+  int mis;   // (reference address of the candidate's first pixel) & 15
+  bool inr;  // in the block's mv range (evaluated and reported)
+};
+
+template <int W, int H>
+__global__ void __launch_bounds__(256, B200_SATD_SPARSE_MINBLOCKS)
+    me_satd_sparse_u8(const __grid_constant__ MeArgs a) {
+  using C = SatdSparseCfg<W, H>;
+  constexpr int CW = C::CW, NCH = C::NCH, CPP = C::CPP, NSEG = C::NSEG, ROWW = C::ROWW, CANDW = C::CANDW,
+                BUFW = C::BUFW;
+  extern __shared__ __align__(128) uint32_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t *const wbuf = smem + warp * C::WARP_WORDS;
+  const uint32_t wbuf_s = smem_u32(wbuf);
+  const int myc = lane / NCH, chunk = lane - myc * NCH;  // evaluation role: (candidate, chunk)
+  const int cy = chunk / CW, cx = chunk - cy * CW;
+  const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+  const size_t blk_end = a.pr.block_end[a.pr.n - 1];
+  const size_t blk0 = a.pr.block_begin + (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
+
+  auto fetch_hdr = [&](size_t blk) {
+    SatdHdr h;
+    h.lo = h.hi = 0;
+    h.b.x = h.b.y = 0;
+    if (blk < blk_end) {
+      h.lo = __ldg(a.cand_offsets + blk);
+      h.hi = __ldg(a.cand_offsets + blk + 1);
+      h.b = a.blocks[blk];
+    }
+    return h;
+  };
+  auto fetch_cand = [&](const SatdHdr &h, uint32_t base) {
+    b200_cand c;
+    c.block = 0;
+    c.mv_row = 0;
+    c.mv_col = 0;
+    if (base + myc < h.hi) c = a.cands[base + myc];
+    return c;
+  };
+  // stage one batch (and, with_org, the block's org rows) into half `half` of the double buffer
+  auto stage = [&](size_t blk, int pi, const SatdHdr &h, uint32_t base, const b200_cand &c, int half,
+                   bool with_org) {
+    SatdLane L;
+    L.c = c;
+    L.mis = 0;
+    L.inr = false;
+    if (blk < blk_end) {
+      const PlaneView cur = a.pr.cur[pi], ref = a.pr.ref[pi];
+      const MvRange r = b200_mv_range(a.w_in_b, a.h_in_b, h.b.x / MI_SIZE, h.b.y / MI_SIZE, W, H);
+      L.inr = base + myc < h.hi && !(c.mv_col < r.x_min || c.mv_col > r.x_max || c.mv_row < r.y_min ||
+                                     c.mv_row > r.y_max);
+      const uint8_t *rp = px<uint8_t>(ref, h.b.x + c.mv_col / 8, h.b.y + c.mv_row / 8);
+      L.mis = (int)((uintptr_t)rp & 15);
+      const unsigned long long segbase = L.inr ? (unsigned long long)(uintptr_t)(rp - L.mis) : 0ull;
+      const uint32_t dst0 = wbuf_s + (uint32_t)(half * BUFW) * 4u;
+      // unit u = (candidate, row, segment); lanes walk consecutive units
+#pragma unroll
+      for (int u0 = 0; u0 < CPP * H * NSEG; u0 += 32) {
+        const int u = u0 + lane;
+        const int uc = u / (H * NSEG), rem = u - uc * (H * NSEG);
+        const int R = rem / NSEG, seg = rem - R * NSEG;
+        const unsigned long long sb = __shfl_sync(0xffffffffu, segbase, (uc * NCH) & 31);
+        if (sb)
+          cp_async16(dst0 + (uint32_t)(uc * CANDW + R * ROWW + 4 * (R >> 3) + seg * 4) * 4u,
+                     (const uint8_t *)(uintptr_t)sb + (long long)R * ref.stride + seg * 16);
+      }
+      if (with_org) {  // org rows as [chunk][row][2 words]; word aligned when the block sits on x % 4 == 0
+        const uint8_t *op = px<uint8_t>(cur, h.b.x, h.b.y);
+        const uint32_t odst = dst0 + (uint32_t)(CPP * CANDW) * 4u;
+        const bool aligned = ((uintptr_t)op & 3) == 0;
+#pragma unroll
+        for (int t0 = 0; t0 < NCH * 16; t0 += 32) {
+          const int t = t0 + lane;  // word t = (chunk, row, half)
+          const int ch = t >> 4, row = (t >> 1) & 7, hw = t & 1;
+          const int ocy = ch / CW, ocx = ch - ocy * CW;
+          const uint8_t *q = op + (long long)(ocy * 8 + row) * cur.stride + ocx * 8 + hw * 4;
+          if (aligned) {
+            cp_async4(odst + (uint32_t)t * 4u, q);
+          } else {  // rare: byte-aligned blocks take the synchronous way
+            const int osh = (int)((uintptr_t)q & 3);
+            const uint32_t *qw = (const uint32_t *)(q - osh);
+            wbuf[half * BUFW + CPP * CANDW + t] = __funnelshift_r(__ldg(qw), __ldg(qw + 1), osh * 8);
+          }
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    return L;
+  };
+  // evaluate this thread's chunk of its candidate from half `half`; every lane of a candidate
+  // returns the candidate's SATD
+  auto evaluate = [&](int half, int mis) -> uint32_t {
+    const int off = mis + cx * 8;
+    const uint32_t *rowp = wbuf + half * BUFW + myc * CANDW + (cy * 8) * ROWW + 4 * cy + (off >> 2);
+    const uint2 *orgp = (const uint2 *)(wbuf + half * BUFW + CPP * CANDW + chunk * 16);
+    const int sh = (off & 3) * 8;
+    int t[8][8];
+#pragma unroll
+    for (int y = 0; y < 8; y++) {
+      const uint32_t w0 = rowp[y * ROWW], w1 = rowp[y * ROWW + 1], w2 = rowp[y * ROWW + 2];
+      const uint32_t q0 = __funnelshift_r(w0, w1, sh), q1 = __funnelshift_r(w1, w2, sh);
+      const uint2 o = orgp[y];
+      // t = H.org - H.ref for the row: Hadamard rows on the org bytes, negated ones on the
+      // reference bytes; outputs 4..7 take the second word of each with the opposite sign
+      t[y][0] = dp4a_us(q1, 0xFFFFFFFFu, dp4a_us(q0, 0xFFFFFFFFu, dp4a_us(o.y, 0x01010101u, dp4a_us(o.x, 0x01010101u, 0))));
+      t[y][1] = dp4a_us(q1, 0x01FF01FFu, dp4a_us(q0, 0x01FF01FFu, dp4a_us(o.y, 0xFF01FF01u, dp4a_us(o.x, 0xFF01FF01u, 0))));
+      t[y][2] = dp4a_us(q1, 0x0101FFFFu, dp4a_us(q0, 0x0101FFFFu, dp4a_us(o.y, 0xFFFF0101u, dp4a_us(o.x, 0xFFFF0101u, 0))));
+      t[y][3] = dp4a_us(q1, 0xFF0101FFu, dp4a_us(q0, 0xFF0101FFu, dp4a_us(o.y, 0x01FFFF01u, dp4a_us(o.x, 0x01FFFF01u, 0))));
+      t[y][4] = dp4a_us(q1, 0x01010101u, dp4a_us(q0, 0xFFFFFFFFu, dp4a_us(o.y, 0xFFFFFFFFu, dp4a_us(o.x, 0x01010101u, 0))));
+      t[y][5] = dp4a_us(q1, 0xFF01FF01u, dp4a_us(q0, 0x01FF01FFu, dp4a_us(o.y, 0x01FF01FFu, dp4a_us(o.x, 0xFF01FF01u, 0))));
+      t[y][6] = dp4a_us(q1, 0xFFFF0101u, dp4a_us(q0, 0x0101FFFFu, dp4a_us(o.y, 0x0101FFFFu, dp4a_us(o.x, 0xFFFF0101u, 0))));
+      t[y][7] = dp4a_us(q1, 0x01FFFF01u, dp4a_us(q0, 0xFF0101FFu, dp4a_us(o.y, 0xFF0101FFu, dp4a_us(o.x, 0x01FFFF01u, 0))));
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int col = 0; col < 8; col++) {
+      int v[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) v[k] = t[k][col];
+      bfly(v[0], v[1]);
+      bfly(v[2], v[3]);
+      bfly(v[4], v[5]);
+      bfly(v[6], v[7]);
+      bfly(v[0], v[2]);
+      bfly(v[1], v[3]);
+      bfly(v[4], v[6]);
+      bfly(v[5], v[7]);
+      // last stage pairs (k, k + 4): |x + y| + |x - y| = 2 max(|x|, |y|)
+#pragma unroll
+      for (int k = 0; k < 4; k++) s += (uint32_t)max(abs(v[k]), abs(v[k + 4]));
+    }
+    uint32_t acc = 2u * s;
+#pragma unroll
+    for (int o = NCH >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return (acc + 4u) >> 3;  // dist.rs:219-220, single final rounding (8x8: ln = 3)
+  };
+
+  // ---- prologue: headers of blocks 0..2, records of 0..1, block 0 staged
+  size_t blk = blk0;
+  SatdHdr h0 = fetch_hdr(blk), h1 = fetch_hdr(blk + nwarps), h2 = fetch_hdr(blk + 2 * nwarps);
+  b200_cand c0 = fetch_cand(h0, h0.lo), c1 = fetch_cand(h1, h1.lo);
+  // plane pair of a block: the warp's blocks come in ascending order, the pair index only grows
+  auto advance_pair = [&](int pi, size_t b) {
+    while (pi + 1 < a.pr.n && (uint32_t)b >= a.pr.block_end[pi]) pi++;
+    return pi;
+  };
+  int pi0 = advance_pair(0, blk);
+  SatdLane L0 = stage(blk, pi0, h0, h0.lo, c0, 0, true);
+  int half = 0;
+  for (; blk < blk_end; blk += nwarps) {
+    // ---- look ahead: stage block k+1, request block k+2's records and block k+3's header
+    const int pi1 = advance_pair(pi0, blk + nwarps);
+    const SatdLane L1 = stage(blk + nwarps, pi1, h1, h1.lo, c1, half ^ 1, true);
+    const b200_cand c2 = fetch_cand(h2, h2.lo);
+    const SatdHdr h3 = fetch_hdr(blk + 3 * nwarps);
+    int p0r = 0, p0c = 0, p1r = 0, p1c = 0;
+    if (a.pmv) {
+      const short *p = a.pmv + 4 * blk;
+      p0r = p[0], p0c = p[1], p1r = p[2], p1c = p[3];
+    }
+    // ---- block k: its footprints were requested one block ago
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+    unsigned long long best = ~0ull;
+    SatdLane L = L0;
+    for (uint32_t base = h0.lo;;) {
+      const uint32_t i = base + myc;
+      const uint32_t acc = evaluate(half, L.mis);
+      uint32_t sad = kEmptySad;
+      unsigned long long cost = kEmptyCost, key = ~0ull;
+      if (L.inr && chunk == 0) {
+        sad = acc;
+        cost = b200_mv_cost(sad, L.c.mv_row, L.c.mv_col, p0r, p0c, p1r, p1c, a.lambda, a.allow_hp);
+        key = pack_key(cost, i - h0.lo);
+      }
+      if (i < h0.hi && chunk == 0) {
+        if (a.out_sad) a.out_sad[i] = sad;
+        if (a.out_cost) a.out_cost[i] = cost;
+      }
+      best = key < best ? key : best;
+      base += CPP;
+      if (base >= h0.hi) break;
+      // further batches of a long list, in place: this half is free once every lane has evaluated
+      __syncwarp();
+      L = stage(blk, pi0, h0, base, fetch_cand(h0, base), half, false);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+    }
+    if (a.out_best) {
+      const uint32_t khi = (uint32_t)(best >> 32);
+      const uint32_t mh = __reduce_min_sync(0xffffffffu, khi);
+      const uint32_t klo = khi == mh ? (uint32_t)best : 0xffffffffu;
+      const uint32_t ml = __reduce_min_sync(0xffffffffu, klo);
+      if (lane == 0) {
+        const unsigned long long key = ((unsigned long long)mh << 32) | ml;
+        b200_me_result res;
+        res.cost = kEmptyCost;
+        res.sad = kEmptySad;
+        res.mv_row = 0;
+        res.mv_col = 0;
+        if (key != ~0ull) {
+          const uint32_t idx = (uint32_t)(key & ((1u << kKeyIdxBits) - 1));
+          const unsigned long long cost = key >> kKeyIdxBits;
+          const b200_cand c = a.cands[h0.lo + idx];
+          const uint32_t r1 = b200_mv_rate(c.mv_row, c.mv_col, p0r, p0c, a.allow_hp);
+          const uint32_t r2 = b200_mv_rate(c.mv_row, c.mv_col, p1r, p1c, a.allow_hp) + 1;
+          const uint32_t rate = r1 < r2 ? r1 : r2;
+          res.cost = cost;
+          res.sad = (uint32_t)((cost - (unsigned long long)rate * a.lambda) >> 8);
+          res.mv_row = c.mv_row;
+          res.mv_col = c.mv_col;
+        }
+        a.out_best[blk] = res;
+      }
+    }
+    __syncwarp();  // every lane is done with this half before block k+2 is staged into it
+    h0 = h1, h1 = h2, h2 = h3;
+    c0 = c1, c1 = c2;
+    L0 = L1;
+    pi0 = pi1;
+    half ^= 1;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- full search
 struct FsArgs {
   PlaneView cur, ref;
@@ -1405,6 +1682,26 @@ int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px, const b200_pl
     const double avg0 = a.nblocks ? (double)a.ncands / (double)a.nblocks : 0.0;
     if (avg0 * W * H * 4 < win_bytes && cur_word_pitch) {
       const int wpc = 8;
+      if constexpr (SATD && W >= 8 && H >= 8 && (W / 8) * (H / 8) <= 32) {
+        // 8x8-chunk SATD: footprints staged per warp with cp.async, thread per (candidate, chunk)
+        bool ref16 = true;  // 16-byte segments need 16-byte aligned rows
+        for (int k = 0; k < a.pr.n; k++)
+          ref16 = ref16 && (a.pr.ref[k].stride & 15) == 0 && ((uintptr_t)a.pr.ref[k].data & 15) == 0;
+        if (ref16 && !getenv("B200_OLD_SATD")) {
+          using C = SatdSparseCfg<W, H>;
+          static std::once_flag once;
+          static cudaError_t err = cudaSuccess;
+          std::call_once(once, [] {
+            err = cudaFuncSetAttribute(me_satd_sparse_u8<W, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)C::SMEM);
+          });
+          B200_CUDA(ctx, err);
+          const int grid = (int)std::min<size_t>((a.nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms * 16);
+          me_satd_sparse_u8<W, H><<<grid, wpc * 32, C::SMEM, ctx->stream>>>(a);
+          B200_LAUNCH_CHECK(ctx);
+          return B200_OK;
+        }
+      }
       const int grid = (int)std::min<size_t>((a.nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms * 16);
       me_cand_warp_u8<W, H, SATD><<<grid, wpc * 32, 0, ctx->stream>>>(a);
       B200_LAUNCH_CHECK(ctx);

@@ -13,6 +13,10 @@ Sources (xiph/rav1e @ 564ae3b):
                                (TxSize, TxType) -> table map of av1_scan_orders :949-1321
   src/transform/mod.rs:519-552  log_tx_ratios (TxSize, rect_ratio_log2) pairs
   src/transform/mod.rs:555-603  roundtrips: (TxSize, TxType, tolerance) of forward -> inverse_transform_add
+  src/recon_intra.rs:30-136, :258-354  the 22 has_tr_* and 22 has_bl_* availability bitmaps of
+                               get_intra_edges' has_top_right / has_bottom_left (length, first 4
+                               bytes and sha256 of each; the oracle and the CUDA side regenerate
+                               them from their rule)
   tests/small_input.y4m   BASELINE config 0's input: the luma planes of its 5 frames (64x64, 8 bit)
                           -> tests/golden/small_input_luma.npy
 The Rust test code is parsed textually; nothing is executed (no rustc in this image).
@@ -74,8 +78,15 @@ def main():
     rt = "\n".join(l for l in rt.splitlines() if not l.strip().startswith("//"))
     roundtrips = [[a, b, int(t)] for a, b, t in re.findall(r"\((TX_\w+),\s*(\w+),\s*(\d+)\)", rt)]
     assert len(log_tx_ratios) == 19 and len(roundtrips) == 44, (len(log_tx_ratios), len(roundtrips))
+    ri = open(os.path.join(REF, "recon_intra.rs")).read()
+    avail = {}
+    for m in re.finditer(r"static (has_(?:tr|bl)_\d+x\d+): &\[u8\] =\s*&\[(.*?)\];", ri, re.S):
+        vals = [int(x) for x in re.findall(r"\d+", m.group(2))]
+        avail[m.group(1)] = {"n": len(vals), "first4": vals[:4], "sha256": hashlib.sha256(bytes(vals)).hexdigest()}
+    assert len(avail) == 44, sorted(avail)
     out = {
         "source": "xiph/rav1e @ 564ae3b, extracted by tests/golden/make_golden.py",
+        "intra_avail_tables": avail,
         "log_tx_ratios": log_tx_ratios, "roundtrips": roundtrips,
         "log_tx_scale": log_tx_scale, "scan_tables": tables, "scan_map": scan_map,
         "dist_pattern": {"org": "(x + y + 24) & 255", "ref": "(x - y + 8) & 255", "block_at": [32, 40],

@@ -76,6 +76,17 @@ CAND_CASES = [
     (4, 8, np.uint8, 8, True, 3, 20),
     (64, 64, np.uint8, 8, True, 2, 60),
     (32, 16, np.uint8, 8, False, 1, 50),
+    # sparse SATD lists through the staged 8x8-chunk kernel: every block size it serves, more
+    # candidates per block than one batch holds, blocks without candidates (jitter)
+    (16, 16, np.uint8, 8, True, 8, 64),
+    (16, 16, np.uint8, 8, True, 13, 90),
+    (8, 16, np.uint8, 8, True, 5, 40),
+    (16, 8, np.uint8, 8, True, 9, 60),
+    (16, 32, np.uint8, 8, True, 5, 60),
+    (32, 16, np.uint8, 8, True, 6, 60),
+    (32, 64, np.uint8, 8, True, 2, 60),
+    (64, 32, np.uint8, 8, True, 3, 70),
+    (8, 8, np.uint8, 8, True, 1, 70),
 ]
 
 
