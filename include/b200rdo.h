@@ -362,6 +362,65 @@ int b200_fwd_txfm_residual_multi_dev(b200_ctx *ctx, size_t npairs, const b200_pl
 int b200_activity_mask_dev(b200_ctx *ctx, const b200_plane *luma, int bit_depth, uint32_t *d_variances,
                            uint32_t *d_scales);
 
+/* ---------------------------------------------------------------- frame pipe (host buffers, per frame)
+ * One call per frame runs the ME and transform legs of the RDO inner loop for every block of the frame
+ * with the state an encoder thread keeps per tile: pushing a frame uploads it ONCE (the previously
+ * pushed frame is the reference, like the reference slots rav1e searches, me.rs:178-212), the block
+ * grid and every intermediate stay on the device, candidate lists travel as 2 bytes per candidate
+ * ((row, col) full-pel offsets around a per-block centre MotionVector: a search stage's pattern around
+ * its predictor, me.rs:884-1303; candidate = centre + 8 * offset with i16 wrapping), the SAD winners
+ * feed the fused residual + forward transform (+ quantize chain, when ac_quant != 0) on the device and
+ * only results cross PCIe.  Asynchronous like the other host-buffer forms under b200_ctx_set_async:
+ * host buffers (pinned for speed) are valid after b200_ctx_synchronize. */
+typedef struct b200_frame_pipe b200_frame_pipe;
+typedef struct {
+  int32_t width, height, pad, bpp, bit_depth;
+  int32_t block_w, block_h; /* the blocks tile the frame (full blocks only), row-major */
+  uint32_t lambda;
+  int32_t sad_per_block, satd_per_block; /* list lengths (uniform over the blocks; 0 = leg off) */
+  int32_t window_hint_px;                /* bound on the offsets' reach, as in b200_me_params */
+  int32_t tx_size, tx_type; /* transform of the SAD winner's residual (block size = transform size); tx_size < 0: off */
+  uint32_t dc_quant, ac_quant; /* ac_quant 0: raw coefficients out; else qcoeffs + eob + tx-domain distortion */
+} b200_frame_pipe_cfg;
+int b200_frame_pipe_create(b200_ctx *ctx, const b200_frame_pipe_cfg *cfg, b200_frame_pipe **out);
+void b200_frame_pipe_destroy(b200_frame_pipe *pipe);
+size_t b200_frame_pipe_nblocks(const b200_frame_pipe *pipe);
+/* frame: HOST pointer to the visible width x height area.  sad_offsets / satd_offsets: nblocks x
+ * per_block (row, col) int8 pairs; centers: nblocks (row, col) int16 MotionVectors in 1/8 pel or NULL
+ * (zero).  Outputs (each may be NULL): best_sad / best_satd [nblocks]; coeffs: nblocks x w*h raw
+ * coefficients, or nblocks x b200_coded_tx_area() quantized ones with eob [nblocks] and tx_dist
+ * [nblocks] (i16 for 8-bit frames, i32 for HBD).  The first push only uploads (there is no reference
+ * yet) and leaves the outputs untouched. */
+int b200_frame_pipe_push(b200_frame_pipe *pipe, const void *frame, ptrdiff_t frame_stride_bytes,
+                         const int8_t *sad_offsets, const int8_t *satd_offsets, const int16_t *centers,
+                         b200_me_result *best_sad, b200_me_result *best_satd, void *coeffs, uint16_t *eob,
+                         uint64_t *tx_dist);
+
+/* ---------------------------------------------------------------- lookahead (api/lookahead.rs)
+ * Plane::downsampled (v_frame 0.3.9; encoder.rs:476-477 builds the half / quarter resolution planes of
+ * the ME pyramid): dst(c, r) = (src(2c, 2r) + src(2c+1, 2r) + src(2c, 2r+1) + src(2c+1, 2r+1) + 2) >> 2,
+ * dst is ((src.width + 1) / 2) x ((src.height + 1) / 2), followed by Plane::pad(frame_w, frame_h):
+ * everything outside [0, pad_w) x [0, pad_h) is a replica of the nearest pixel inside, with
+ * pad_w = (frame_w + xdec) >> xdec, pad_h = (frame_h + ydec) >> ydec of the NEW plane (xdec = 1 for
+ * the half, 2 for the quarter resolution plane).  The whole padded area of dst is written. */
+int b200_plane_downsample_dev(b200_ctx *ctx, const b200_plane *src, const b200_plane *dst, int pad_w, int pad_h);
+/* estimate_intra_costs (lookahead.rs:30-128): for every 8x8 importance block of the source luma,
+ * get_intra_edges(DC_PRED, TX_8X8) -> DC prediction -> get_satd against the source, fused;
+ * d_costs[(y / 8) * (width / 8) + x / 8]. */
+int b200_estimate_intra_costs_dev(b200_ctx *ctx, const b200_plane *luma, int bit_depth, uint32_t *d_costs);
+/* The cost part of estimate_inter_costs (lookahead.rs:238-270): SATD between every importance block and
+ * the reference block displaced by its motion vector (d_mvs: (row, col) int16 per importance block =
+ * stats[y * 2][x * 2].mv of the reference, e.g. the winners of b200_me_search_dev) -> d_costs (may be
+ * NULL) and *d_mean = sum / count as f64 (one correctly rounded division, bit-identical to the
+ * reference's).  d_scratch: 8 bytes of device memory.  The reference plane must be readable wherever
+ * the vectors point (padding). */
+int b200_estimate_inter_costs_dev(b200_ctx *ctx, const b200_plane *org, const b200_plane *ref, const int16_t *d_mvs,
+                                  uint32_t *d_costs, uint64_t *d_scratch, double *d_mean);
+/* estimate_importance_block_difference (lookahead.rs:131-180): mean over the importance blocks of
+ * |round(mean(org block)) - round(mean(ref block))| as f64. */
+int b200_importance_block_difference_dev(b200_ctx *ctx, const b200_plane *org, const b200_plane *ref,
+                                         uint64_t *d_scratch, double *d_mean);
+
 /* ---------------------------------------------------------------- quantize chain
  * The steps of encode_tx_block after the forward transform (encoder.rs:1556-1655) for nblocks
  * transform blocks of one (tx_size, tx_type), device-resident:

@@ -230,6 +230,16 @@ void orc_get_intra_edges(void *edge, const void *region, ptrdiff_t stride, int b
                          int tx_h, int bit_depth, int mode, int enable_intra_edge_filter, int angle_delta,
                          int *out_init_left, int *out_init_above);
 
+/* ------------------------------------------------ api/lookahead.rs + v_frame Plane::downsampled */
+void orc_plane_downsample(const void *src, ptrdiff_t src_stride, int src_w, int src_h, void *dst,
+                          ptrdiff_t dst_stride, int dst_pad, int bpp, int pad_w, int pad_h);
+void orc_estimate_intra_costs(const void *luma, ptrdiff_t stride, int width, int height, int bpp, int bit_depth,
+                              uint32_t *costs);
+double orc_importance_block_difference(const void *org, ptrdiff_t org_stride, const void *ref, ptrdiff_t ref_stride,
+                                       int width, int height, int bpp);
+double orc_estimate_inter_costs(const void *org, ptrdiff_t org_stride, const void *ref, ptrdiff_t ref_stride,
+                                int width, int height, int bpp, const int16_t *mvs, uint32_t *costs);
+
 /* -------------------------------------------------------------------- rdo.rs
  * compute_rd_cost (rdo.rs:718-723): lambda.mul_add(rate / 8.0, distortion as f64). */
 double orc_compute_rd_cost(double lambda, uint32_t rate, uint64_t distortion);

@@ -40,6 +40,13 @@ class MeParams(C.Structure):
                 ("bit_depth", C.c_int32), ("window_hint_px", C.c_int32)]
 
 
+class FramePipeCfg(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("pad", C.c_int32), ("bpp", C.c_int32),
+                ("bit_depth", C.c_int32), ("block_w", C.c_int32), ("block_h", C.c_int32), ("lambda_", C.c_uint32),
+                ("sad_per_block", C.c_int32), ("satd_per_block", C.c_int32), ("window_hint_px", C.c_int32),
+                ("tx_size", C.c_int32), ("tx_type", C.c_int32), ("dc_quant", C.c_uint32), ("ac_quant", C.c_uint32)]
+
+
 BLOCK_DTYPE = np.dtype([("x", "<i2"), ("y", "<i2")])
 CAND_DTYPE = np.dtype([("block", "<u4"), ("mv_row", "<i2"), ("mv_col", "<i2")])
 INTRA_ITEM_DTYPE = np.dtype([("edge", "<u4"), ("ac", "<u4"), ("x", "<i2"), ("y", "<i2"),
@@ -173,6 +180,16 @@ def lib():
     L.b200_predict_intra.argtypes = [i32, i32, vp, C.c_ssize_t, i32, i32, i32, vp, i32, i32, vp] + [i32] * 6
     L.b200_predict_intra.restype = None
     L.b200_predict_intra_dev.argtypes = [vp, vp, vp, sz, vp, i32, i32, i32, i32, i32, vp]
+    L.b200_frame_pipe_create.argtypes = [vp, C.POINTER(FramePipeCfg), C.POINTER(vp)]
+    L.b200_frame_pipe_destroy.argtypes = [vp]
+    L.b200_frame_pipe_destroy.restype = None
+    L.b200_frame_pipe_nblocks.argtypes = [vp]
+    L.b200_frame_pipe_nblocks.restype = sz
+    L.b200_frame_pipe_push.argtypes = [vp, vp, C.c_ssize_t] + [vp] * 8
+    L.b200_plane_downsample_dev.argtypes = [vp, pp, pp, i32, i32]
+    L.b200_estimate_intra_costs_dev.argtypes = [vp, pp, i32, vp]
+    L.b200_estimate_inter_costs_dev.argtypes = [vp, pp, pp, vp, vp, vp, vp]
+    L.b200_importance_block_difference_dev.argtypes = [vp, pp, pp, vp, vp]
     L.b200_get_intra_edges_dev.argtypes = [vp, pp] + [i32] * 7 + [vp, sz, vp, vp]
     L.b200_pred_cfl_ac_dev.argtypes = [vp, pp, vp, sz] + [i32] * 6 + [vp]
     _LIB = L
@@ -299,6 +316,26 @@ class Context:
     def inverse_transform_add_dev(self, d_coeffs, dst, d_blocks, n, tx_size, tx_type, bd):
         self.check(self.L.b200_inverse_transform_add_dev(self.h, _dev_ptr(d_coeffs), C.byref(dst), _dev_ptr(d_blocks),
                                                          n, tx_size, tx_type, bd))
+
+    # ---- lookahead
+    def plane_alloc(self, width, height, pad, bpp):
+        p = Plane()
+        self.check(self.L.b200_plane_alloc(self.h, width, height, pad, bpp, C.byref(p)))
+        return p
+
+    def plane_downsample_dev(self, src, dst, pad_w, pad_h):
+        self.check(self.L.b200_plane_downsample_dev(self.h, C.byref(src), C.byref(dst), pad_w, pad_h))
+
+    def estimate_intra_costs_dev(self, luma, bit_depth, d_costs):
+        self.check(self.L.b200_estimate_intra_costs_dev(self.h, C.byref(luma), bit_depth, _dev_ptr(d_costs)))
+
+    def estimate_inter_costs_dev(self, org, ref, d_mvs, d_costs, d_scratch, d_mean):
+        self.check(self.L.b200_estimate_inter_costs_dev(self.h, C.byref(org), C.byref(ref), _dev_ptr(d_mvs),
+                                                        _dev_ptr(d_costs), _dev_ptr(d_scratch), _dev_ptr(d_mean)))
+
+    def importance_block_difference_dev(self, org, ref, d_scratch, d_mean):
+        self.check(self.L.b200_importance_block_difference_dev(self.h, C.byref(org), C.byref(ref),
+                                                               _dev_ptr(d_scratch), _dev_ptr(d_mean)))
 
     # ---- RDO cost
     def compute_rd_cost_dev(self, lam, d_rate, d_dist, n, d_cost=None, d_offsets=None, ngroups=0, d_best=None):
@@ -439,6 +476,33 @@ class Context:
             self.h, C.byref(cur_hp), C.byref(ref_hp), _np_ptr(blocks), len(blocks),
             C.byref(params), range_x, range_y, step, _np_ptr(best)))
         return best
+
+
+class FramePipe:
+    """b200_frame_pipe: one per context; push() one frame per call (include/b200rdo.h)."""
+
+    def __init__(self, ctx, width, height, pad, block=(16, 16), lambda_=0, sad_per_block=0, satd_per_block=0,
+                 window_hint_px=0, tx_size=-1, tx_type=0, dc_quant=0, ac_quant=0, bit_depth=8):
+        self.ctx = ctx
+        cfg = FramePipeCfg(width, height, pad, 1 if bit_depth == 8 else 2, bit_depth, block[0], block[1], lambda_,
+                           sad_per_block, satd_per_block, window_hint_px, tx_size, tx_type, dc_quant, ac_quant)
+        h = C.c_void_p()
+        ctx.check(ctx.L.b200_frame_pipe_create(ctx.h, C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.cfg = cfg
+        self.nblocks = int(ctx.L.b200_frame_pipe_nblocks(h))
+
+    def push(self, frame, sad_offsets=None, satd_offsets=None, centers=None, best_sad=None, best_satd=None,
+             coeffs=None, eob=None, tx_dist=None):
+        """frame: 2-D numpy array (visible area); lists / outputs: numpy arrays (pinned for speed)."""
+        self.ctx.check(self.ctx.L.b200_frame_pipe_push(
+            self.h, frame.ctypes.data, frame.strides[0], _np_ptr(sad_offsets), _np_ptr(satd_offsets), _np_ptr(centers),
+            _np_ptr(best_sad), _np_ptr(best_satd), _np_ptr(coeffs), _np_ptr(eob), _np_ptr(tx_dist)))
+
+    def close(self):
+        if self.h:
+            self.ctx.L.b200_frame_pipe_destroy(self.h)
+            self.h = None
 
 
 def host_plane(arr2d_full, pad):

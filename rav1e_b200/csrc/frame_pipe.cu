@@ -1,0 +1,238 @@
+// frame_pipe.cu — the frame-level host-buffer entry point: what an encoder thread calls once per frame
+// to run the ME / transform legs of the RDO inner loop for every block of that frame.
+//
+// Why it exists: the per-list host-buffer forms (b200_me_mvs_resident, b200_fwd_txfm_residual_resident)
+// re-send what does not change (block grid, CSR offsets), send every frame twice (once as `cur`, once as
+// the next pair's `ref`), allocate per call and bounce the winners through the host between the ME and
+// the transform leg.  A pipe keeps the state an encoder keeps per tile thread:
+//   * two resident planes: pushing a frame uploads it ONCE (one linear copy + on-device unpack / border
+//     replication, v_frame Plane::pad semantics) and the previously pushed frame becomes the reference
+//     (rav1e: the reconstructed / source frame stays in the reference slots, src/encoder.rs:476-477);
+//   * the block grid, the CSR offsets of the (uniform) candidate lists and every intermediate on the
+//     device, allocated once;
+//   * candidate lists travel as 2 bytes per candidate: (row, col) full-pel offsets relative to a
+//     per-block centre MotionVector - the shape of rav1e's search stages, which evaluate a predictor plus
+//     a pattern around it (me.rs:884-1303); the device expands them to MotionVectors
+//     (centre + 8 * offset, i16 wrapping like the reference's MotionVector arithmetic);
+//   * the winners of the SAD list feed the fused residual + forward transform (+ quantize chain) on the
+//     device; only results cross PCIe: winners, coefficients (or qcoeffs + eob + tx-domain distortion).
+// Everything is enqueued on the context's stream; with b200_ctx_set_async the call returns at once and
+// the host buffers are valid after b200_ctx_synchronize, so frames pipeline over several contexts.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+struct b200_frame_pipe {
+  b200_ctx *ctx = nullptr;
+  b200_frame_pipe_cfg cfg{};
+  b200_plane planes[2]{};
+  int cur = -1;          // index of the most recently pushed frame (-1: none yet)
+  size_t nblocks = 0;
+  void *dbase = nullptr;  // one allocation carved into the buffers below
+  b200_block *d_blocks = nullptr;
+  uint32_t *d_offs_sad = nullptr, *d_offs_satd = nullptr;
+  int8_t *d_o8_sad = nullptr, *d_o8_satd = nullptr;
+  int16_t *d_centers = nullptr;
+  b200_cand *d_cand_sad = nullptr, *d_cand_satd = nullptr;
+  b200_me_result *d_best_sad = nullptr, *d_best_satd = nullptr;
+  void *d_coef = nullptr, *d_q = nullptr;
+  uint16_t *d_eob = nullptr;
+  uint64_t *d_dist = nullptr;
+  size_t coef_bytes = 0, q_bytes = 0;
+};
+
+namespace {
+
+// candidate k of block b = centre_b + 8 * (offset_row, offset_col); lists have `per` entries per block
+__global__ void expand_offsets_kernel(const char2 *offs, const short2 *centers, size_t nblocks, int per,
+                                      b200_cand *out) {
+  const size_t n = nblocks * (size_t)per;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / (size_t)per;
+    const char2 o = offs[i];  // {row, col}, full pel
+    short2 c = make_short2(0, 0);
+    if (centers) c = centers[b];
+    b200_cand r;
+    r.block = (uint32_t)b;
+    r.mv_row = (short)(c.x + (short)(8 * o.x));
+    r.mv_col = (short)(c.y + (short)(8 * o.y));
+    out[i] = r;
+  }
+}
+
+struct Carve {
+  uint8_t *p;
+  size_t used = 0;
+  void *take(size_t bytes) {
+    void *r = p ? p + used : nullptr;
+    used += b200_align_up(bytes, 256);
+    return r;
+  }
+};
+
+}  // namespace
+
+extern "C" int b200_frame_pipe_create(b200_ctx *ctx, const b200_frame_pipe_cfg *cfg, b200_frame_pipe **out) {
+  B200_REQUIRE(ctx, ctx && cfg && out, "b200_frame_pipe_create: NULL argument");
+  *out = nullptr;
+  B200_REQUIRE(ctx, cfg->width > 0 && cfg->height > 0 && cfg->pad >= 0 && (cfg->bpp == 1 || cfg->bpp == 2),
+               "bad frame geometry");
+  B200_REQUIRE(ctx, (cfg->bpp == 1) == (cfg->bit_depth == 8), "bpp %d vs bit depth %d", cfg->bpp, cfg->bit_depth);
+  B200_REQUIRE(ctx, cfg->block_w >= 4 && cfg->block_h >= 4 && cfg->block_w <= 128 && cfg->block_h <= 128 &&
+                        cfg->block_w <= cfg->width && cfg->block_h <= cfg->height,
+               "bad block size %dx%d", cfg->block_w, cfg->block_h);
+  B200_REQUIRE(ctx, cfg->sad_per_block >= 0 && cfg->satd_per_block >= 0, "negative list length");
+  B200_REQUIRE(ctx, cfg->tx_size < 0 || (b200_valid_av1_transform(cfg->tx_size, cfg->tx_type) &&
+                                         b200_tx_width(cfg->tx_size) == cfg->block_w &&
+                                         b200_tx_height(cfg->tx_size) == cfg->block_h),
+               "transform %d/%d does not match the %dx%d blocks", cfg->tx_size, cfg->tx_type, cfg->block_w,
+               cfg->block_h);
+  B200_CUDA(ctx, cudaSetDevice(ctx->device));
+  b200_frame_pipe *p = new b200_frame_pipe();
+  p->ctx = ctx;
+  p->cfg = *cfg;
+  const int nbx = cfg->width / cfg->block_w, nby = cfg->height / cfg->block_h;
+  p->nblocks = (size_t)nbx * nby;
+  const size_t nb = p->nblocks, ns = nb * (size_t)cfg->sad_per_block, nt = nb * (size_t)cfg->satd_per_block;
+  const size_t area = (size_t)cfg->block_w * cfg->block_h;
+  p->coef_bytes = cfg->tx_size >= 0 ? nb * area * (cfg->bpp == 1 ? 2 : 4) : 0;
+  p->q_bytes = (cfg->tx_size >= 0 && cfg->ac_quant) ? nb * (size_t)b200_coded_tx_area(cfg->tx_size) * (cfg->bpp == 1 ? 2 : 4) : 0;
+  for (int pass = 0; pass < 2; pass++) {  // pass 0 sizes the allocation, pass 1 carves it
+    Carve c{(uint8_t *)p->dbase};
+    p->d_blocks = (b200_block *)c.take(nb * sizeof(b200_block));
+    p->d_offs_sad = (uint32_t *)c.take((nb + 1) * 4);
+    p->d_offs_satd = (uint32_t *)c.take((nb + 1) * 4);
+    p->d_o8_sad = (int8_t *)c.take(ns * 2);
+    p->d_o8_satd = (int8_t *)c.take(nt * 2);
+    p->d_centers = (int16_t *)c.take(nb * 4);
+    p->d_cand_sad = (b200_cand *)c.take(ns * sizeof(b200_cand));
+    p->d_cand_satd = (b200_cand *)c.take(nt * sizeof(b200_cand));
+    p->d_best_sad = (b200_me_result *)c.take(nb * sizeof(b200_me_result));
+    p->d_best_satd = (b200_me_result *)c.take(nb * sizeof(b200_me_result));
+    p->d_coef = c.take(p->coef_bytes);
+    p->d_q = c.take(p->q_bytes);
+    p->d_eob = (uint16_t *)c.take(nb * 2);
+    p->d_dist = (uint64_t *)c.take(nb * 8);
+    if (pass == 0) {
+      const cudaError_t e = cudaMalloc(&p->dbase, c.used + 256);
+      if (e != cudaSuccess) {
+        delete p;
+        B200_CUDA(ctx, e);
+      }
+    }
+  }
+  int st = b200_plane_alloc(ctx, cfg->width, cfg->height, cfg->pad, cfg->bpp, &p->planes[0]);
+  if (!st) st = b200_plane_alloc(ctx, cfg->width, cfg->height, cfg->pad, cfg->bpp, &p->planes[1]);
+  if (!st) {  // the block grid and the CSR offsets never change
+    std::vector<b200_block> hb(nb);
+    for (int y = 0; y < nby; y++)
+      for (int x = 0; x < nbx; x++) hb[(size_t)y * nbx + x] = b200_block{(int16_t)(x * cfg->block_w), (int16_t)(y * cfg->block_h)};
+    std::vector<uint32_t> o1(nb + 1), o2(nb + 1);
+    for (size_t i = 0; i <= nb; i++) o1[i] = (uint32_t)(i * cfg->sad_per_block), o2[i] = (uint32_t)(i * cfg->satd_per_block);
+    if (cudaMemcpy(p->d_blocks, hb.data(), nb * sizeof(b200_block), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(p->d_offs_sad, o1.data(), (nb + 1) * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(p->d_offs_satd, o2.data(), (nb + 1) * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess)
+      st = b200_fail(ctx, B200_ERR_CUDA, "b200_frame_pipe_create: descriptor upload failed");
+  }
+  if (st) {
+    b200_frame_pipe_destroy(p);
+    return st;
+  }
+  *out = p;
+  return B200_OK;
+}
+
+extern "C" void b200_frame_pipe_destroy(b200_frame_pipe *p) {
+  if (!p) return;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  for (auto &pl : p->planes)
+    if (pl.alloc) cudaFree(pl.alloc);
+  if (p->dbase) cudaFree(p->dbase);
+  delete p;
+}
+
+extern "C" size_t b200_frame_pipe_nblocks(const b200_frame_pipe *p) { return p ? p->nblocks : 0; }
+
+extern "C" int b200_frame_pipe_push(b200_frame_pipe *p, const void *frame, ptrdiff_t frame_stride_bytes,
+                                    const int8_t *sad_offsets, const int8_t *satd_offsets, const int16_t *centers,
+                                    b200_me_result *best_sad, b200_me_result *best_satd, void *coeffs,
+                                    uint16_t *eob, uint64_t *tx_dist) {
+  if (!p) return b200_fail(nullptr, B200_ERR_ARG, "b200_frame_pipe_push: pipe is NULL");
+  b200_ctx *ctx = p->ctx;
+  const b200_frame_pipe_cfg &cfg = p->cfg;
+  B200_REQUIRE(ctx, frame != nullptr, "frame is NULL");
+  B200_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t nb = p->nblocks, ns = nb * (size_t)cfg.sad_per_block, nt = nb * (size_t)cfg.satd_per_block;
+  // ---- the new frame: uploaded once, the previous one becomes the reference
+  const int nxt = p->cur < 0 ? 0 : p->cur ^ 1;
+  {
+    const int was_async = ctx->async_batch;
+    ctx->async_batch = 1;  // enqueue only; the synchronisation policy is applied once, at the end
+    const int st = b200_plane_upload(ctx, &p->planes[nxt], frame, frame_stride_bytes);
+    ctx->async_batch = was_async;
+    if (st) return st;
+  }
+  const bool first = p->cur < 0;
+  p->cur = nxt;
+  if (first) {  // nothing to search against yet
+    if (!ctx->async_batch) B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+  }
+  const b200_plane *cur = &p->planes[nxt], *ref = &p->planes[nxt ^ 1];
+  B200_REQUIRE(ctx, (ns == 0 || sad_offsets) && (nt == 0 || satd_offsets), "NULL candidate offsets");
+  b200_me_params mp{};
+  mp.w = cfg.block_w, mp.h = cfg.block_h;
+  mp.frame_w_in_b = 2 * ((cfg.width + 7) >> 3);  // encoder.rs:852
+  mp.frame_h_in_b = 2 * ((cfg.height + 7) >> 3);
+  mp.lambda = cfg.lambda;
+  mp.bit_depth = cfg.bit_depth;
+  mp.window_hint_px = cfg.window_hint_px;
+  if (centers) B200_CUDA(ctx, cudaMemcpyAsync(p->d_centers, centers, nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+  const short2 *dc = centers ? (const short2 *)p->d_centers : nullptr;
+  if (ns) {
+    B200_CUDA(ctx, cudaMemcpyAsync(p->d_o8_sad, sad_offsets, ns * 2, cudaMemcpyHostToDevice, ctx->stream));
+    expand_offsets_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>((const char2 *)p->d_o8_sad, dc, nb, cfg.sad_per_block, p->d_cand_sad);
+    B200_LAUNCH_CHECK(ctx);
+    mp.use_satd = 0;
+    if (int st = b200_me_candidates_dev(ctx, cur, ref, p->d_blocks, nb, p->d_cand_sad, ns, p->d_offs_sad, nullptr, &mp,
+                                        nullptr, nullptr, p->d_best_sad))
+      return st;
+    if (best_sad)
+      B200_CUDA(ctx, cudaMemcpyAsync(best_sad, p->d_best_sad, nb * sizeof(b200_me_result), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (nt) {
+    B200_CUDA(ctx, cudaMemcpyAsync(p->d_o8_satd, satd_offsets, nt * 2, cudaMemcpyHostToDevice, ctx->stream));
+    expand_offsets_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>((const char2 *)p->d_o8_satd, dc, nb, cfg.satd_per_block, p->d_cand_satd);
+    B200_LAUNCH_CHECK(ctx);
+    mp.use_satd = 1;
+    if (int st = b200_me_candidates_dev(ctx, cur, ref, p->d_blocks, nb, p->d_cand_satd, nt, p->d_offs_satd, nullptr, &mp,
+                                        nullptr, nullptr, p->d_best_satd))
+      return st;
+    if (best_satd)
+      B200_CUDA(ctx, cudaMemcpyAsync(best_satd, p->d_best_satd, nb * sizeof(b200_me_result), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (cfg.tx_size >= 0) {
+    // residual of every block against the reference displaced by its SAD winner -> forward transform
+    // (-> quantize chain), all on the device
+    if (int st = b200_fwd_txfm_residual_dev(ctx, cur, ref, p->d_blocks, nb, ns ? p->d_best_sad : nullptr, p->d_coef,
+                                            cfg.tx_size, cfg.tx_type, cfg.bit_depth))
+      return st;
+    if (cfg.ac_quant) {
+      if (int st = b200_quantize_dev(ctx, p->d_coef, nb, cfg.tx_size, cfg.tx_type, cfg.dc_quant, cfg.ac_quant, 0,
+                                     cfg.bpp == 2, p->d_q, nullptr, p->d_eob, p->d_dist))
+        return st;
+      if (coeffs) B200_CUDA(ctx, cudaMemcpyAsync(coeffs, p->d_q, p->q_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      if (eob) B200_CUDA(ctx, cudaMemcpyAsync(eob, p->d_eob, nb * 2, cudaMemcpyDeviceToHost, ctx->stream));
+      if (tx_dist) B200_CUDA(ctx, cudaMemcpyAsync(tx_dist, p->d_dist, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (coeffs) {
+      B200_CUDA(ctx, cudaMemcpyAsync(coeffs, p->d_coef, p->coef_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
+  if (!ctx->async_batch) B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}

@@ -1210,6 +1210,21 @@ __global__ void __launch_bounds__(256, B200_SATD_SPARSE_MINBLOCKS)
     return c;
   };
   // stage one batch (and, with_org, the block's org rows) into half `half` of the double buffer
+  // staging roles, fixed per lane: unit u = u0 + lane = (candidate, row, segment) for every step u0
+  constexpr int UPC = H * NSEG;  // units per candidate
+  constexpr int NSTEP = CPP * UPC / 32;
+  int st_src[NSTEP], st_dst[NSTEP], st_lane[NSTEP];  // per step: row * stride is added per block
+  int st_row[NSTEP];
+#pragma unroll
+  for (int k = 0; k < NSTEP; k++) {
+    const int u = k * 32 + lane;
+    const int uc = u / UPC, rem = u - uc * UPC, R = rem / NSEG, seg = rem - R * NSEG;
+    st_row[k] = R;
+    st_src[k] = seg * 16;
+    st_dst[k] = (uc * CANDW + R * ROWW + 4 * (R >> 3) + seg * 4) * 4;
+    st_lane[k] = (uc * NCH) & 31;
+  }
+  constexpr int kNoCand = INT_MIN;
   auto stage = [&](size_t blk, int pi, const SatdHdr &h, uint32_t base, const b200_cand &c, int half,
                    bool with_org) {
     SatdLane L;
@@ -1221,37 +1236,42 @@ __global__ void __launch_bounds__(256, B200_SATD_SPARSE_MINBLOCKS)
       const MvRange r = b200_mv_range(a.w_in_b, a.h_in_b, h.b.x / MI_SIZE, h.b.y / MI_SIZE, W, H);
       L.inr = base + myc < h.hi && !(c.mv_col < r.x_min || c.mv_col > r.x_max || c.mv_row < r.y_min ||
                                      c.mv_row > r.y_max);
-      const uint8_t *rp = px<uint8_t>(ref, h.b.x + c.mv_col / 8, h.b.y + c.mv_row / 8);
-      L.mis = (int)((uintptr_t)rp & 15);
-      const unsigned long long segbase = L.inr ? (unsigned long long)(uintptr_t)(rp - L.mis) : 0ull;
+      // byte offset of the candidate's first pixel from pixel (0,0) of the reference plane (planes
+      // are far smaller than 2 GB), split into its 16-byte aligned part and the misalignment
+      const int off = (h.b.y + c.mv_row / 8) * ref.stride + h.b.x + c.mv_col / 8;
+      L.mis = (int)(((uintptr_t)ref.data + (unsigned)off) & 15);
+      const int segoff = L.inr ? off - L.mis : kNoCand;
       const uint32_t dst0 = wbuf_s + (uint32_t)(half * BUFW) * 4u;
-      // unit u = (candidate, row, segment); lanes walk consecutive units
+      const uint8_t *rbase = (const uint8_t *)ref.data;
 #pragma unroll
-      for (int u0 = 0; u0 < CPP * H * NSEG; u0 += 32) {
-        const int u = u0 + lane;
-        const int uc = u / (H * NSEG), rem = u - uc * (H * NSEG);
-        const int R = rem / NSEG, seg = rem - R * NSEG;
-        const unsigned long long sb = __shfl_sync(0xffffffffu, segbase, (uc * NCH) & 31);
-        if (sb)
-          cp_async16(dst0 + (uint32_t)(uc * CANDW + R * ROWW + 4 * (R >> 3) + seg * 4) * 4u,
-                     (const uint8_t *)(uintptr_t)sb + (long long)R * ref.stride + seg * 16);
+      for (int k = 0; k < NSTEP; k++) {
+        const int so = __shfl_sync(0xffffffffu, segoff, st_lane[k]);
+        if (so != kNoCand) cp_async16(dst0 + (uint32_t)st_dst[k], rbase + (so + st_row[k] * ref.stride + st_src[k]));
       }
-      if (with_org) {  // org rows as [chunk][row][2 words]; word aligned when the block sits on x % 4 == 0
+      if (with_org) {  // org rows as [chunk][row][2 words]
         const uint8_t *op = px<uint8_t>(cur, h.b.x, h.b.y);
         const uint32_t odst = dst0 + (uint32_t)(CPP * CANDW) * 4u;
-        const bool aligned = ((uintptr_t)op & 3) == 0;
+        const int al = (int)((uintptr_t)op | (uintptr_t)(unsigned)cur.stride) & 7;
 #pragma unroll
-        for (int t0 = 0; t0 < NCH * 16; t0 += 32) {
-          const int t = t0 + lane;  // word t = (chunk, row, half)
-          const int ch = t >> 4, row = (t >> 1) & 7, hw = t & 1;
-          const int ocy = ch / CW, ocx = ch - ocy * CW;
-          const uint8_t *q = op + (long long)(ocy * 8 + row) * cur.stride + ocx * 8 + hw * 4;
-          if (aligned) {
-            cp_async4(odst + (uint32_t)t * 4u, q);
-          } else {  // rare: byte-aligned blocks take the synchronous way
-            const int osh = (int)((uintptr_t)q & 3);
-            const uint32_t *qw = (const uint32_t *)(q - osh);
-            wbuf[half * BUFW + CPP * CANDW + t] = __funnelshift_r(__ldg(qw), __ldg(qw + 1), osh * 8);
+        for (int t0 = 0; t0 < NCH * 8; t0 += 32) {
+          const int t = t0 + lane;  // unit t = (chunk, row): 8 pixels
+          if ((NCH * 8) % 32 == 0 || t < NCH * 8) {
+            const int ch = t >> 3, row = t & 7;
+            const int ocy = ch / CW, ocx = ch - ocy * CW;
+            const uint8_t *q = op + (ocy * 8 + row) * cur.stride + ocx * 8;
+            if (al == 0) {
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(odst + (uint32_t)t * 8u), "l"(q) : "memory");
+            } else if ((al & 3) == 0) {
+              cp_async4(odst + (uint32_t)t * 8u, q);
+              cp_async4(odst + (uint32_t)t * 8u + 4u, q + 4);
+            } else {  // rare: byte-aligned blocks take the synchronous way
+              const int osh = (int)((uintptr_t)q & 3);
+              const uint32_t *qw = (const uint32_t *)(q - osh);
+              const uint32_t o0 = __ldg(qw), o1 = __ldg(qw + 1), o2 = __ldg(qw + 2);
+              uint32_t *d = wbuf + half * BUFW + CPP * CANDW + 2 * t;
+              d[0] = __funnelshift_r(o0, o1, osh * 8);
+              d[1] = __funnelshift_r(o1, o2, osh * 8);
+            }
           }
         }
       }
