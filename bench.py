@@ -374,9 +374,9 @@ def run_b200(args, rank, world, local_rank):
                 traffic = int(traffic * pairs_per_launch)
 
     out = None
+    # ---- e2e: same metric through the host-buffer C ABI (H2D + kernels + D2H per frame), on every rank
+    e2e = run_e2e(ctx, blocks, args, world, dist if world > 1 else None)
     if rank == 0:
-        # ---- e2e: same metric through the host-buffer C ABI (H2D + kernels + D2H per frame)
-        e2e = run_e2e(ctx, blocks, args)
         cpu = run_cpu_baseline(blocks)
         out = {
             "metric": METRIC, "value": value, "unit": "blocks/s", "n_gpus": world,
@@ -414,14 +414,15 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def run_e2e(ctx0, blocks, args):
-    """The same metric through the host-buffer C ABI, per frame: pinned host planes uploaded
-    (b200_plane_upload), candidate descriptors host->device, winners device->host
-    (b200_me_candidates_resident x2: SAD and SATD lists), fused residual + 16x16 DCT with the
-    coefficients device->host (b200_fwd_txfm_residual_resident).  Frames are pipelined over three
-    contexts (streams) in asynchronous mode so PCIe copies overlap kernels; everything is
-    synchronised before the clock stops."""
-    import ctypes as C
+def run_e2e(ctx0, blocks, args, world=1, dist=None):
+    """The same metric through the host-buffer C ABI, one call per frame (b200_frame_pipe_push): the
+    frame's visible area travels host->device ONCE from pinned memory (the previously pushed frame is
+    the reference), the candidate lists travel as 2-byte full-pel offsets, the SAD winners feed the
+    fused residual + 16x16 DCT on the device, and winners + coefficients travel device->host.  Frames
+    are pipelined over NCTX contexts (streams) in asynchronous mode, one host thread each (like one
+    rayon worker per tile, encoder.rs:3253), so PCIe copies overlap kernels; everything is synchronised
+    before the clock stops.  Runs on every rank; the ranks' frames add up, the slowest rank's time
+    counts."""
     import torch
     from rav1e_b200 import backend as B
     nb = len(blocks)
@@ -429,62 +430,46 @@ def run_e2e(ctx0, blocks, args):
     Fe = 4 * NCTX
     pinned = lambda n, dt=np.uint8: torch.empty(n, dtype=torch.uint8).pin_memory().numpy().view(dt)
     ctxs = [B.Context(ctx0.device) for _ in range(NCTX)]
-    slots = []
+    pipes = []
     for c in ctxs:
         c.set_async(True)
-        pl = []
-        for _ in range(2):
-            # visible W x H area travels; the PAD-pixel border is replicated on the device
-            # (b200_plane_upload = v_frame Plane::pad semantics, like rav1e's own frames)
-            p = B.Plane()
-            c.check(c.L.b200_plane_alloc(c.h, W, H, PAD, 1, C.byref(p)))
-            pl.append((p, p))
-        slots.append(pl)
-    hblocks = pinned(blocks.nbytes).view(B.BLOCK_DTYPE)
-    hblocks[:] = blocks
+        pipes.append(B.FramePipe(c, W, H, PAD, (BW, BH), LAMBDA, CAND_SAD, CAND_SATD, MV_RANGE_PX, tx_size=2, tx_type=0))
+        assert pipes[-1].nblocks == nb
     frames = []
     for f in range(Fe):
-        cur_img, ref_img = synth_frame_pair(5000 + (f % 2))
+        cur_img, _ = synth_frame_pair(5000 + (f % 4))
         hc = pinned(W * H).reshape(H, W)
-        hr = pinned(W * H).reshape(H, W)
-        hc[:], hr[:] = cur_img[PAD:PAD + H, PAD:PAD + W], ref_img[PAD:PAD + H, PAD:PAD + W]
-        c, offs = cand_list(nb, CAND_SAD, 900 + f)
-        c2, offs2 = cand_list(nb, CAND_SATD, 1900 + f)
-        # candidates travel as MotionVector lists (row, col: 4 B each); the CSR names the block
-        hcand = pinned(len(c) * 4).view(np.int16).reshape(len(c), 2)
-        hcand[:, 0], hcand[:, 1] = c["mv_row"], c["mv_col"]
-        hcand2 = pinned(len(c2) * 4).view(np.int16).reshape(len(c2), 2)
-        hcand2[:, 0], hcand2[:, 1] = c2["mv_row"], c2["mv_col"]
-        hoffs, hoffs2 = pinned(offs.nbytes).view(np.uint32), pinned(offs2.nbytes).view(np.uint32)
-        hoffs[:], hoffs2[:] = offs, offs2
+        hc[:] = cur_img[PAD:PAD + H, PAD:PAD + W]
+        c, _ = cand_list(nb, CAND_SAD, 900 + f)
+        c2, _ = cand_list(nb, CAND_SATD, 1900 + f)
+        # a search stage's pattern around its predictor: (row, col) full-pel offsets, 2 bytes per candidate
+        so = pinned(len(c) * 2).view(np.int8).reshape(len(c), 2)
+        so[:, 0], so[:, 1] = c["mv_row"] // 8, c["mv_col"] // 8
+        to = pinned(len(c2) * 2).view(np.int8).reshape(len(c2), 2)
+        to[:, 0], to[:, 1] = c2["mv_row"] // 8, c2["mv_col"] // 8
         best = pinned(nb * 16).view(B.ME_RESULT_DTYPE)
         best2 = pinned(nb * 16).view(B.ME_RESULT_DTYPE)
         coef = pinned(nb * BW * BH * 2).view(np.int16).reshape(nb, BW * BH)
-        frames.append((hc, hr, hcand, hcand2, hoffs, hoffs2, best, best2, coef))
-    p_sad = B.me_params(BW, BH, W, H, LAMBDA, window_hint_px=MV_RANGE_PX)
-    p_satd = B.me_params(BW, BH, W, H, LAMBDA, use_satd=True, window_hint_px=MV_RANGE_PX)
-    h2d = d2h = 0
+        frames.append((hc, so, to, best, best2, coef))
+    for k in range(NCTX):           # each pipe needs a reference before its first timed frame
+        pipes[k].push(frames[k][0])
+        ctxs[k].synchronize()
 
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(NCTX)
 
     def drive(k):
-        """One host thread per context (like one rayon worker per tile, encoder.rs:3253): ctypes
-        releases the GIL inside the C ABI, so the CUDA API work of the contexts overlaps too."""
-        cx = ctxs[k]
-        (pc, qc), (pr, qr) = slots[k]
+        """ctypes releases the GIL inside the C ABI, so the CUDA API work of the contexts overlaps."""
         nb_h2d = nb_d2h = 0
         for f in range(k, Fe, NCTX):
-            hc, hr, c, c2, o, o2, best, best2, coef = frames[f]
-            cx.plane_upload(pc, hc)
-            cx.plane_upload(pr, hr)
-            cx.me_mvs_resident(qc, qr, hblocks, c, p_sad, o, (None, None, best))
-            cx.me_mvs_resident(qc, qr, hblocks, c2, p_satd, o2, (None, None, best2))
-            cx.fwd_txfm_residual_resident(qc, qr, hblocks, best, coef, 2, 0, 8)
-            nb_h2d += hc.nbytes + hr.nbytes + c.nbytes + c2.nbytes + 3 * hblocks.nbytes + o.nbytes + o2.nbytes + best.nbytes
+            hc, so, to, best, best2, coef = frames[f]
+            pipes[k].push(hc, so, to, None, best, best2, coef)
+            nb_h2d += hc.nbytes + so.nbytes + to.nbytes
             nb_d2h += best.nbytes + best2.nbytes + coef.nbytes
-        cx.synchronize()
+        ctxs[k].synchronize()
         return nb_h2d, nb_d2h
+
+    h2d = d2h = 0
 
     def step():
         nonlocal h2d, d2h
@@ -492,37 +477,50 @@ def run_e2e(ctx0, blocks, args):
         h2d, d2h = sum(r[0] for r in res), sum(r[1] for r in res)
     for _ in range(2):
         step()
-    l0 = sum(cx.launches for cx in ctxs)
-    t0 = time.perf_counter()
     reps = max(3, min(args.steps, 10))
+    l0 = sum(cx.launches for cx in ctxs)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
     for _ in range(reps):
         step()
     dt = time.perf_counter() - t0
     launches = sum(cx.launches for cx in ctxs) - l0
-    units = Fe * nb * (CAND_SAD + CAND_SATD + 1)
-    # what the link itself sustains on this box: pinned host -> device, 256 MB, CUDA events
+    if world > 1:       # whole job: every rank's frames, the slowest rank's time
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_job = float(t.item())
+    else:
+        dt_job = dt
+    units = world * Fe * nb * (CAND_SAD + CAND_SATD + 1)
+    # what the link itself sustains on this box: pinned host <-> device, 256 MB, CUDA events
     big = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
     dbig = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    dbig.copy_(big, non_blocking=True)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(4):
-        dbig.copy_(big, non_blocking=True)
-    e1.record()
-    torch.cuda.synchronize()
-    h2d_gbs = 4 * big.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+    def link(dst, src):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        return 4 * big.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    h2d_gbs, d2h_gbs = link(dbig, big), link(big, dbig)
     del big, dbig
-    res = {"value": units * reps / dt, "unit": "blocks/s", "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": int(d2h), "frames_per_step": Fe, "kernel_launches_per_step": launches // reps,
-           "h2d_GBps_achieved": h2d * reps / dt / 1e9, "h2d_GBps_link_measured": h2d_gbs,
-           "api": "per frame: b200_plane_upload x2 + b200_me_mvs_resident x2 (MotionVector lists in, winners "
-                  f"out) + b200_fwd_txfm_residual_resident (coefficients out); {NCTX} contexts in async mode, "
-                  "one host thread each"}
+    res = {"value": units * reps / dt_job, "unit": "blocks/s", "h2d_bytes_per_step": int(h2d) * world,
+           "d2h_bytes_per_step": int(d2h) * world, "frames_per_step": Fe * world,
+           "kernel_launches_per_step": launches // reps * world,
+           "h2d_GBps_achieved": h2d * reps / dt / 1e9, "d2h_GBps_achieved": d2h * reps / dt / 1e9,
+           "h2d_GBps_link_measured": h2d_gbs, "d2h_GBps_link_measured": d2h_gbs, "ranks": world,
+           "api": "per frame: ONE b200_frame_pipe_push (frame uploaded once - the previous frame is the reference; "
+                  "candidate lists as 2-byte full-pel offsets; SAD winners -> residual + 16x16 DCT on the device; "
+                  f"winners + coefficients out); {NCTX} contexts in async mode, one host thread each; "
+                  "per-rank link rates shown, bytes and frames summed over ranks"}
     pool.shutdown()
-    for c, pl in zip(ctxs, slots):
-        for p, q in pl:
-            c.check(c.L.b200_plane_free(c.h, C.byref(p)))
+    for c, pp in zip(ctxs, pipes):
+        pp.close()
         c.close()
     return res
 
