@@ -137,11 +137,14 @@ def run_reference(args, rank, world):
         return
     from tests import oracle_lib as O
     threads = O.host_threads()
+    tiles_mode = args.workload == "4k-tiles" or (args.workload == "auto" and world > 1)
     blocks = grid_blocks()
     cur_img, ref_img = synth_frame_pair(0)
     ocur, oref = O.Plane(W, H, PAD), O.Plane(W, H, PAD)
     ocur.data[:], oref.data[:] = cur_img, ref_img
-    # bounded sample: one frame pair, 1/4 of its candidate lists per step
+    # bounded sample: one 1080p frame pair's worth of 16x16 blocks per step.  The same sample serves the
+    # 4K tile workload: its unit is the same 16x16 candidate block (two 960x1088 tiles hold as many
+    # blocks as one 1080p frame) and the CPU's cost per block does not depend on the frame size.
     sad_c, _ = cand_list(len(blocks), CAND_SAD, 100)
     satd_c, _ = cand_list(len(blocks), CAND_SATD, 200)
     resid = np.random.default_rng(5).integers(-255, 256, (len(blocks), BH, BW)).astype(np.int16)
@@ -167,7 +170,8 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": "1080p-8bit-speed6-me16x16", "sample": sample,
+        "config": {"workload": "4k-8bit-speed6-8tiles (BASELINE configs[4])" if tiles_mode else "1080p-8bit-speed6-me16x16",
+                   "sample": sample,
                    "note": "rav1e cannot be built here (no rustc/nasm); this is the C restatement "
                            "of its rust:: kernels (oracle/), OpenMP over candidates"},
         "cpu_baseline": {"value": v, "unit": "blocks/s", "cores": threads, "kind": "port",
@@ -414,6 +418,241 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- B200 arm, 4K tiles
+W4K, H4K = 3840, 2160
+TILE_COLS_LOG2, TILE_ROWS_LOG2 = 2, 1     # 4 x 2 tiles of 15 x 17 superblocks (BASELINE configs[4])
+
+
+def run_b200_tiles(args, rank, world, local_rank):
+    """BASELINE configs[4]: 4K 8-bit, 8 tiles, speed-6 RDO legs + CDEF, tile t owned by rank t mod N
+    (encoder.rs:3249-3257 runs one worker per tile; tiling/tiler.rs:97-132 lays the grid out).  STRONG
+    scaling: the job - F 4K frame pairs, every tile of every frame - is the same at every N; a rank
+    works on its own tiles of all frames (candidate evaluations only READ the shared reference planes,
+    so every rank holds the planes and nothing but the winners is exchanged).  Per step and rank:
+      SAD lists (64 / block) + winners, SATD lists (8 / block), residual + 16x16 DCT of the winners -
+      one launch each over the F frames - then cdef_find_dir + cdef_filter of the rank's tiles;
+      the 8-byte winner records {sad, mv} go to every rank by an NCCL all-gather enqueued on a SIDE
+      stream as soon as the SAD leg is done, overlapped with the SATD / transform / CDEF legs.
+    The whole step is captured into one CUDA graph (hundreds of tile-sized launches at N = 1)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from rav1e_b200 import backend as B
+    from rav1e_b200 import shard
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream(device=local_rank)
+    side = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    ctx = B.Context(local_rank, use_torch_stream=True)
+    F = args.frames_4k
+    tiles = shard.tile_grid(W4K, H4K, TILE_COLS_LOG2, TILE_ROWS_LOG2)
+    NT = len(tiles)
+    mine = shard.owned_units(NT, rank, world)
+    blocks = np.concatenate([shard.blocks_in_rect(tiles[t], BW, BH, B.BLOCK_DTYPE) for t in mine])
+    nb = len(blocks)                                       # this rank's blocks per frame
+    nb_all = sum(len(shard.blocks_in_rect(t, BW, BH, B.BLOCK_DTYPE)) for t in tiles)
+    upr = shard.units_per_rank(NT, world)
+    nb_pad = max(len(shard.blocks_in_rect(t, BW, BH, B.BLOCK_DTYPE)) for t in tiles) * upr   # all-gather slot
+    # ---- planes: every rank holds every frame (tiles read across their borders)
+    uniq = []
+    for i in range(min(2, F)):
+        rng = np.random.default_rng(4000 + i)
+        ref = rng.integers(0, 256, (H4K + 2 * PAD, W4K + 2 * PAD), dtype=np.uint8)
+        cur = np.clip(np.roll(ref, (2 - i, -3 + i), axis=(0, 1)).astype(np.int16)
+                      + rng.integers(-2, 3, ref.shape, dtype=np.int16), 0, 255).astype(np.uint8)
+        uniq.append((cur, ref))
+    planes, outs = [], []
+    for f in range(F):
+        pr = []
+        for img in uniq[f % len(uniq)]:
+            p = B.Plane()
+            ctx.check(ctx.L.b200_plane_alloc(ctx.h, W4K + 2 * PAD, H4K + 2 * PAD, 0, 1, C.byref(p)))
+            ctx.check(ctx.L.b200_plane_upload(ctx.h, C.byref(p), img.ctypes.data, img.strides[0]))
+            q = B.Plane()
+            q.data = p.data + PAD * p.stride + PAD
+            q.stride, q.width, q.height, q.pad, q.bpp, q.alloc = p.stride, W4K, H4K, PAD, 1, None
+            pr.append(q)
+        planes.append(pr)
+        outs.append(ctx.plane_alloc(W4K, H4K, 0, 1))       # the frame's CDEF output
+    # ---- descriptors of this rank's blocks, frame after frame (b200_*_multi_dev layout)
+    n_sad, n_satd = nb * CAND_SAD, nb * CAND_SATD
+    sad_np, satd_np = [], []
+    for f in range(F):
+        c, _ = cand_list(nb, CAND_SAD, 11 * f + 1 + 1000 * rank)
+        c["block"] += f * nb
+        sad_np.append(c)
+        c2, _ = cand_list(nb, CAND_SATD, 11 * f + 2 + 1000 * rank)
+        c2["block"] += f * nb
+        satd_np.append(c2)
+    d_sad_c = torch.from_numpy(np.concatenate(sad_np).view(np.uint8)).cuda()
+    d_satd_c = torch.from_numpy(np.concatenate(satd_np).view(np.uint8)).cuda()
+    del sad_np, satd_np
+    d_blocks_all = torch.from_numpy(np.tile(blocks, F).view(np.uint8)).cuda()
+    d_offs = torch.from_numpy((np.arange(F * nb + 1, dtype=np.uint64) * CAND_SAD).astype(np.uint32).view(np.uint8)).cuda()
+    d_offs2 = torch.from_numpy((np.arange(F * nb + 1, dtype=np.uint64) * CAND_SATD).astype(np.uint32).view(np.uint8)).cuda()
+    d_best = torch.zeros(F * nb * 16, dtype=torch.uint8, device="cuda")
+    d_best2 = torch.empty(F * nb * 16, dtype=torch.uint8, device="cuda")
+    d_coef = torch.empty(F * nb * BW * BH, dtype=torch.int16, device="cuda")
+    pairs = B.PlanePairs([planes[f][0] for f in range(F)], [planes[f][1] for f in range(F)],
+                         [(i + 1) * nb for i in range(F)], [(i + 1) * n_sad for i in range(F)])
+    pairs2 = B.PlanePairs([planes[f][0] for f in range(F)], [planes[f][1] for f in range(F)],
+                          [(i + 1) * nb for i in range(F)], [(i + 1) * n_satd for i in range(F)])
+    p_sad = B.me_params(BW, BH, W4K, H4K, LAMBDA, window_hint_px=MV_RANGE_PX)
+    p_satd = B.me_params(BW, BH, W4K, H4K, LAMBDA, use_satd=True, window_hint_px=MV_RANGE_PX)
+    # CDEF state per frame (frame-indexed arrays; a rank fills the entries of its own tiles)
+    n8 = (W4K // 8) * (H4K // 8)
+    sbw, sbh = (W4K + 63) // 64, (H4K + 63) // 64
+    d_dir = torch.zeros(F * n8, dtype=torch.uint8, device="cuda")
+    d_var = torch.zeros(F * n8, dtype=torch.int32, device="cuda")
+    d_str = torch.from_numpy(np.random.default_rng(9).integers(0, 64, sbw * sbh).astype(np.uint8)).cuda()
+    rects8 = [(tiles[t][0] // 8, tiles[t][1] // 8, tiles[t][2] // 8, tiles[t][3] // 8) for t in mine]
+    # winner records: 8 bytes {sad u32, mv_row i16, mv_col i16} = bytes 8..15 of b200_me_result
+    rec_local = torch.zeros((F, nb_pad, 8), dtype=torch.uint8, device="cuda")
+    gathered = torch.empty((world, F, nb_pad, 8), dtype=torch.uint8, device="cuda") if world > 1 else None
+    ev_sad, ev_comm = torch.cuda.Event(), torch.cuda.Event()
+
+    def leg_sad():
+        ctx.me_candidates_multi_dev(pairs, d_blocks_all, F * nb, d_sad_c, F * n_sad, p_sad, d_offs, None, None, None, d_best)
+
+    def leg_satd():
+        ctx.me_candidates_multi_dev(pairs2, d_blocks_all, F * nb, d_satd_c, F * n_satd, p_satd, d_offs2, None, None, None, d_best2)
+
+    def leg_txfm():
+        ctx.fwd_txfm_residual_multi_dev(pairs, d_blocks_all, F * nb, d_best, d_coef, 2, 0, 8)
+
+    def leg_cdef_dir():
+        for f in range(F):
+            for r8 in rects8:
+                ctx.cdef_find_dir_rect_dev(planes[f][0], 8, None, d_dir[f * n8:], d_var[f * n8:], r8)
+
+    def leg_cdef_filter():
+        for f in range(F):
+            for r8 in rects8:
+                ctx.cdef_filter_rect_dev(planes[f][0], outs[f], 0, 0, 0, W4K, H4K, 8, 5, None, d_dir[f * n8:],
+                                         d_var[f * n8:], d_str, r8)
+
+    def leg_comm():
+        """on the side stream: pack the winners to 8-byte records, all-gather them"""
+        rec_local[:, :nb].copy_(d_best.view(F, nb, 16)[:, :, 8:16])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, rec_local)
+
+    def step_body():
+        leg_sad()
+        ev_sad.record(stream)
+        with torch.cuda.stream(side):
+            side.wait_event(ev_sad)
+            leg_comm()
+            ev_comm.record(side)
+        leg_satd()
+        leg_txfm()
+        leg_cdef_dir()
+        leg_cdef_filter()
+        stream.wait_event(ev_comm)          # the step is over when the winners have arrived everywhere
+
+    for _ in range(2):                       # eager warm-up (one-time attribute / tensor-map setup)
+        step_body()
+    torch.cuda.synchronize()
+    graph = None
+    if not args.no_graph:
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                step_body()
+            g.replay()
+            torch.cuda.synchronize()
+            graph = g
+        except Exception as e:  # noqa: BLE001 - capture is an optimisation, eager is always valid
+            sys.stderr.write(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly\n")
+            torch.cuda.synchronize()
+    step = (lambda: graph.replay()) if graph is not None else step_body
+
+    def timed(fn, reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    clk = ClockSampler(local_rank)
+    if rank == 0:
+        clk.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    l0 = ctx.launches
+    step_body() if graph is not None else None     # launch count of one step (graph replays do not count)
+    torch.cuda.synchronize()
+    launches_per_step = (ctx.launches - l0) if graph is not None else None
+    l0 = ctx.launches
+    ms = timed(step, args.steps)
+    if launches_per_step is None:
+        launches_per_step = (ctx.launches - l0) // args.steps
+    units_per_step = F * nb_all * (CAND_SAD + CAND_SATD + 1)        # the whole job, every tile
+    value = units_per_step * args.steps / (ms * 1e-3)
+    legs = {}
+    for name, fn in (("sad_cand", leg_sad), ("satd_cand", leg_satd), ("residual+fwd_txfm", leg_txfm),
+                     ("cdef_find_dir", leg_cdef_dir), ("cdef_filter", leg_cdef_filter)):
+        fn()
+        legs[name] = timed(fn, max(2, args.steps // 2)) / max(2, args.steps // 2)
+
+    def comm_alone():
+        leg_comm()
+    comm_alone()
+    ms_comm = timed(comm_alone, max(2, args.steps // 2)) / max(2, args.steps // 2)
+    clocks = clk.stop() if rank == 0 else None
+    # the same job on ONE GPU is the strong-scaling baseline: rank 0 cannot run it inside an N-rank
+    # launch without the other ranks idling, so it is measured by `--gpus 1 --workload 4k-tiles`
+    e2e = run_e2e(ctx, grid_blocks(), args, world, dist if world > 1 else None)
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_bytes = int((F * n_sad * (BW * BH + 4) + F * nb * BW * BH))
+        out = {
+            "metric": METRIC, "value": value, "unit": "blocks/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "4k-8bit-speed6-8tiles (BASELINE configs[4])", "frame": [W4K, H4K],
+                       "tiles": NT, "tile_grid": "4x2 (tile_cols_log2 2, tile_rows_log2 1; 960x1088 / 960x1072 px)",
+                       "frame_pairs": F, "blocks_per_frame": nb_all, "block": "16x16",
+                       "legs": {"sad_candidates_per_block": CAND_SAD, "satd_candidates_per_block": CAND_SATD,
+                                "fwd_txfm_per_block": "1 x TX_16X16 DCT_DCT of the SAD winner's residual",
+                                "cdef": "cdef_find_dir + cdef_filter (luma) over every tile; not counted in `value`'s units"},
+                       "parallelism": f"tile t -> rank t mod {world} ({len(mine)} tile(s) per rank); total work fixed",
+                       "collective": {"what": "NCCL all-gather of 8-byte winner records {sad, mv} per block to every rank, "
+                                              "on a side stream after the SAD leg, overlapped with the SATD / transform / CDEF legs",
+                                      "bytes_per_rank": int(rec_local.numel()), "ms_alone": ms_comm},
+                       "cuda_graph": graph is not None,
+                       "l2": "planes %.0f MB on every rank; a rank touches its tiles (1/%d of them)" % (
+                           F * 2 * (W4K + 2 * PAD) * (H4K + 2 * PAD) / 1e6, world),
+                       "per_rank_leg_ms (rank 0, each leg alone)": legs,
+                       "mv_range_px": MV_RANGE_PX, "lambda": LAMBDA},
+            "roofline": {"kernel": "me_cand_group_u8<16,16,SAD> over rank 0's tiles of all frames",
+                         "bound": "hbm", "achieved": alg_bytes / (legs["sad_cand"] * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg_bytes / (legs["sad_cand"] * 1e-3) / 1e9 / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "launch_ms": legs["sad_cand"]},
+            "cpu_baseline": run_cpu_baseline(grid_blocks()), "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(launches_per_step * args.steps),
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_e2e(ctx0, blocks, args, world=1, dist=None):
     """The same metric through the host-buffer C ABI, one call per frame (b200_frame_pipe_push): the
     frame's visible area travels host->device ONCE from pinned memory (the previously pushed frame is
@@ -426,7 +665,7 @@ def run_e2e(ctx0, blocks, args, world=1, dist=None):
     import torch
     from rav1e_b200 import backend as B
     nb = len(blocks)
-    NCTX = int(os.environ.get("B200_E2E_CONTEXTS", "3"))
+    NCTX = int(os.environ.get("B200_E2E_CONTEXTS", "4"))
     Fe = 4 * NCTX
     pinned = lambda n, dt=np.uint8: torch.empty(n, dtype=torch.uint8).pin_memory().numpy().view(dt)
     ctxs = [B.Context(ctx0.device) for _ in range(NCTX)]
@@ -436,20 +675,25 @@ def run_e2e(ctx0, blocks, args, world=1, dist=None):
         pipes.append(B.FramePipe(c, W, H, PAD, (BW, BH), LAMBDA, CAND_SAD, CAND_SATD, MV_RANGE_PX, tx_size=2, tx_type=0))
         assert pipes[-1].nblocks == nb
     frames = []
+    n_so, n_to = nb * CAND_SAD * 2, nb * CAND_SATD * 2
     for f in range(Fe):
         cur_img, _ = synth_frame_pair(5000 + (f % 4))
-        hc = pinned(W * H).reshape(H, W)
+        # one pinned packet per frame: [frame | SAD offsets | SATD offsets] back to back travels as ONE
+        # copy; the results come back as one block [SAD winners | SATD winners | coefficients]
+        pin = pinned(W * H + n_so + n_to)
+        hc = pin[:W * H].reshape(H, W)
         hc[:] = cur_img[PAD:PAD + H, PAD:PAD + W]
         c, _ = cand_list(nb, CAND_SAD, 900 + f)
         c2, _ = cand_list(nb, CAND_SATD, 1900 + f)
         # a search stage's pattern around its predictor: (row, col) full-pel offsets, 2 bytes per candidate
-        so = pinned(len(c) * 2).view(np.int8).reshape(len(c), 2)
+        so = pin[W * H:W * H + n_so].view(np.int8).reshape(len(c), 2)
         so[:, 0], so[:, 1] = c["mv_row"] // 8, c["mv_col"] // 8
-        to = pinned(len(c2) * 2).view(np.int8).reshape(len(c2), 2)
+        to = pin[W * H + n_so:].view(np.int8).reshape(len(c2), 2)
         to[:, 0], to[:, 1] = c2["mv_row"] // 8, c2["mv_col"] // 8
-        best = pinned(nb * 16).view(B.ME_RESULT_DTYPE)
-        best2 = pinned(nb * 16).view(B.ME_RESULT_DTYPE)
-        coef = pinned(nb * BW * BH * 2).view(np.int16).reshape(nb, BW * BH)
+        pout = pinned(2 * nb * 16 + nb * BW * BH * 2)
+        best = pout[:nb * 16].view(B.ME_RESULT_DTYPE)
+        best2 = pout[nb * 16:2 * nb * 16].view(B.ME_RESULT_DTYPE)
+        coef = pout[2 * nb * 16:].view(np.int16).reshape(nb, BW * BH)
         frames.append((hc, so, to, best, best2, coef))
     for k in range(NCTX):           # each pipe needs a reference before its first timed frame
         pipes[k].push(frames[k][0])
@@ -514,6 +758,7 @@ def run_e2e(ctx0, blocks, args, world=1, dist=None):
            "kernel_launches_per_step": launches // reps * world,
            "h2d_GBps_achieved": h2d * reps / dt / 1e9, "d2h_GBps_achieved": d2h * reps / dt / 1e9,
            "h2d_GBps_link_measured": h2d_gbs, "d2h_GBps_link_measured": d2h_gbs, "ranks": world,
+           "workload": "1080p-8bit-speed6-me16x16 frames, one stream of frames per rank (per-GPU work fixed)",
            "api": "per frame: ONE b200_frame_pipe_push (frame uploaded once - the previous frame is the reference; "
                   "candidate lists as 2-byte full-pel offsets; SAD winners -> residual + 16x16 DCT on the device; "
                   f"winners + coefficients out); {NCTX} contexts in async mode, one host thread each; "
@@ -556,6 +801,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU)
+    ap.add_argument("--workload", default="auto", choices=["auto", "1080p", "4k-tiles"],
+                    help="auto: BASELINE configs[1] (1080p lookahead batch, per-GPU work fixed) on 1 GPU, "
+                         "configs[4] (4K, 8 tiles sharded over the ranks, total work fixed) on several")
+    ap.add_argument("--frames-4k", type=int, default=16, help="4K frame pairs of the tile workload")
+    ap.add_argument("--no-graph", action="store_true", help="4k-tiles: launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--pairs-per-launch", type=int, default=32,
                     help="frame pairs served by one launch of each leg (b200_*_multi_dev); 1 = a launch per pair")
     args = ap.parse_args()
@@ -564,6 +814,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "4k-tiles" or (args.workload == "auto" and world > 1):
+        run_b200_tiles(args, rank, world, local_rank)
     else:
         run_b200(args, rank, world, local_rank)
 

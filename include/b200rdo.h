@@ -390,7 +390,11 @@ size_t b200_frame_pipe_nblocks(const b200_frame_pipe *pipe);
  * (zero).  Outputs (each may be NULL): best_sad / best_satd [nblocks]; coeffs: nblocks x w*h raw
  * coefficients, or nblocks x b200_coded_tx_area() quantized ones with eob [nblocks] and tx_dist
  * [nblocks] (i16 for 8-bit frames, i32 for HBD).  The first push only uploads (there is no reference
- * yet) and leaves the outputs untouched. */
+ * yet) and leaves the outputs untouched.
+ * Copies: inputs that lie back to back in host memory in the order [frame (dense rows) | sad_offsets |
+ * satd_offsets | centers] travel as ONE host->device copy, outputs laid out [best_sad | best_satd |
+ * coeffs | eob | (8-byte aligned) tx_dist] as ONE device->host copy; any other layout works with a copy
+ * per buffer. */
 int b200_frame_pipe_push(b200_frame_pipe *pipe, const void *frame, ptrdiff_t frame_stride_bytes,
                          const int8_t *sad_offsets, const int8_t *satd_offsets, const int16_t *centers,
                          b200_me_result *best_sad, b200_me_result *best_satd, void *coeffs, uint16_t *eob,
@@ -525,6 +529,16 @@ int b200_cdef_filter_plane_dev(b200_ctx *ctx, const b200_plane *in, const b200_p
                                int bit_depth, int damping, const uint8_t *d_skip8,
                                const uint8_t *d_dir, const int32_t *d_var,
                                const uint8_t *d_strength_sb);
+
+/* The same restricted to the luma 8x8 blocks [rx8, rx8 + rw8) x [ry8, ry8 + rh8) of the frame (a tile of
+ * cdef_filter_tile, cdef.rs:597-625: tiles run concurrently, taps still read across tile borders and
+ * see the sentinel only outside the FRAME); dir / var / skip / strength arrays stay frame-indexed. */
+int b200_cdef_find_dir_rect_dev(b200_ctx *ctx, const b200_plane *luma, int bit_depth, const uint8_t *d_skip8,
+                                uint8_t *d_dir, int32_t *d_var, int rx8, int ry8, int rw8, int rh8);
+int b200_cdef_filter_rect_dev(b200_ctx *ctx, const b200_plane *in, const b200_plane *out, int plane, int xdec,
+                              int ydec, int luma_width, int luma_height, int bit_depth, int damping,
+                              const uint8_t *d_skip8, const uint8_t *d_dir, const int32_t *d_var,
+                              const uint8_t *d_strength_sb, int rx8, int ry8, int rw8, int rh8);
 
 /* ------------------------------------------------------- intra prediction (predict.rs)
  * Boundary = rust::dispatch_predict_intra(mode, variant, dst, tx_size, bit_depth, ac, angle,

@@ -177,6 +177,8 @@ def lib():
     L.b200_cdef_filter_block.restype = None
     L.b200_cdef_find_dir_dev.argtypes = [vp, pp, i32, vp, vp, vp]
     L.b200_cdef_filter_plane_dev.argtypes = [vp, pp, pp] + [i32] * 7 + [vp, vp, vp, vp]
+    L.b200_cdef_find_dir_rect_dev.argtypes = [vp, pp, i32, vp, vp, vp] + [i32] * 4
+    L.b200_cdef_filter_rect_dev.argtypes = [vp, pp, pp] + [i32] * 7 + [vp, vp, vp, vp] + [i32] * 4
     L.b200_predict_intra.argtypes = [i32, i32, vp, C.c_ssize_t, i32, i32, i32, vp, i32, i32, vp] + [i32] * 6
     L.b200_predict_intra.restype = None
     L.b200_predict_intra_dev.argtypes = [vp, vp, vp, sz, vp, i32, i32, i32, i32, i32, vp]
@@ -376,6 +378,16 @@ class Context:
         self.check(self.L.b200_cdef_filter_plane_dev(
             self.h, C.byref(inp), C.byref(out), plane, xdec, ydec, luma_w, luma_h, bit_depth,
             damping, _dev_ptr(d_skip8), _dev_ptr(d_dir), _dev_ptr(d_var), _dev_ptr(d_strength_sb)))
+
+    def cdef_find_dir_rect_dev(self, luma, bit_depth, d_skip8, d_dir, d_var, rect8):
+        self.check(self.L.b200_cdef_find_dir_rect_dev(self.h, C.byref(luma), bit_depth, _dev_ptr(d_skip8),
+                                                      _dev_ptr(d_dir), _dev_ptr(d_var), *rect8))
+
+    def cdef_filter_rect_dev(self, inp, out, plane, xdec, ydec, luma_w, luma_h, bit_depth, damping, d_skip8, d_dir,
+                             d_var, d_strength_sb, rect8):
+        self.check(self.L.b200_cdef_filter_rect_dev(
+            self.h, C.byref(inp), C.byref(out), plane, xdec, ydec, luma_w, luma_h, bit_depth, damping,
+            _dev_ptr(d_skip8), _dev_ptr(d_dir), _dev_ptr(d_var), _dev_ptr(d_strength_sb), *rect8))
 
     # ---- intra prediction
     def predict_intra_dev(self, d_edges, d_items, n, d_ac, w, h, bit_depth, plane_w, plane_h, d_out):

@@ -225,6 +225,18 @@ __global__ void unpack_pad_plane_kernel(T *p0, int stride, int width, int height
   }
 }
 
+// Internal (frame_pipe.cu): fill plane `p` (border included) from a packed device copy of its visible area.
+int b200_plane_unpack_internal(b200_ctx *ctx, const b200_plane *p, const void *d_packed) {
+  if (p->bpp == 1)
+    unpack_pad_plane_kernel<uint8_t><<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(
+        (uint8_t *)p->data, p->stride, p->width, p->height, p->pad, (const uint8_t *)d_packed);
+  else
+    unpack_pad_plane_kernel<uint16_t><<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(
+        (uint16_t *)p->data, p->stride, p->width, p->height, p->pad, (const uint16_t *)d_packed);
+  B200_LAUNCH_CHECK(ctx);
+  return B200_OK;
+}
+
 extern "C" int b200_plane_upload(b200_ctx *ctx, const b200_plane *p, const void *host,
                                  ptrdiff_t host_stride_bytes) {
   B200_REQUIRE(ctx, ctx && p && host && p->data, "b200_plane_upload: NULL argument");

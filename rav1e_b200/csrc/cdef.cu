@@ -3,14 +3,14 @@
 //
 //   cdef_find_dir_kernel   one thread per 8x8 luma block: the 8 directional partial-sum costs
 //                          (cdef.rs:84-143) held in registers, first-max direction, variance.
-//   cdef_filter_kernel     one thread per output pixel.  Instead of materialising the
-//                          reference's padded 12x12 u16 scratch with CDEF_VERY_LARGE sentinels
-//                          (cdef.rs:161-231) the tap loader decides availability from the block's
-//                          edge flags and returns the sentinel itself, so taps read the input
-//                          plane directly (L1/L2 resident) and nothing is staged.
+//   cdef_filter_kernel     a CTA stages a 64 x 16 tile + halo once (sentinels where the reference's
+//                          padded scratch has them, cdef.rs:161-231), a thread filters 4 pixels of
+//                          one block row with the block's parameters computed once.
 // The frame-level driver reproduces cdef_filter_superblock (cdef.rs:401-570): edge flags from
 // the block's position in the frame, skip -> copy, strength split, adjust_strength on luma,
 // chroma damping - 1 and the 4:2:2 direction remap.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -85,9 +85,11 @@ __device__ int find_dir_8x8(const T *img, int stride, int coeff_shift, unsigned 
 
 template <typename T>
 __global__ void cdef_find_dir_kernel(const T *luma, int stride, int w8, int h8, int coeff_shift,
-                                     const uint8_t *skip8, uint8_t *dir, int *var) {
-  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < w8 * h8; b += gridDim.x * blockDim.x) {
-    const int by = b / w8, bx = b - by * w8;
+                                     const uint8_t *skip8, uint8_t *dir, int *var, int rx8, int ry8, int rw8,
+                                     int rh8) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < rw8 * rh8; k += gridDim.x * blockDim.x) {
+    const int by = ry8 + k / rw8, bx = rx8 + k % rw8;
+    const int b = by * w8 + bx;
     unsigned v = 0;
     int d = 0;
     if (!(skip8 && skip8[b]))
@@ -162,6 +164,7 @@ struct CdefPlaneArgs {
   int in_stride, out_stride;  // elements
   int plane, xdec, ydec;
   int w8, h8, sbw;            // luma 8x8 grid and superblocks per row
+  int rx8, ry8, rw8, rh8;     // the part of the grid this launch filters (a tile), in 8x8 luma blocks
   int bit_depth, damping;
   const uint8_t *skip8;
   const uint8_t *dir;
@@ -169,57 +172,108 @@ struct CdefPlaneArgs {
   const uint8_t *strength_sb;
 };
 
+// Frame-level filter.  A CTA owns a 64 x 16 pixel tile of the plane (8 x 2 luma blocks): the tile and
+// its 2-pixel halo are staged ONCE into shared memory as int16, with CDEF_VERY_LARGE written wherever
+// the reference's padded scratch would hold the sentinel (outside the frame: cdef.rs:161-231,
+// :446-466), so the taps are plain LDS.S16 and no tap tests availability.  A thread filters 4
+// horizontally adjacent pixels of one block row: strength split, adjust_strength, direction remap
+// and the constrain shifts are computed once per thread, the twelve tap offsets once per thread.
+// Sentinel handling without a compare per tap: the sentinel is stored as int16 0x8000 = -32768, so
+// `max` ignores it on its own (every real pixel is >= 0) and `min` runs on the value reinterpreted as
+// unsigned (0xffff8000: larger than any pixel); its difference to the centre is so large that
+// constrain() returns 0 for it, exactly like the reference's 0x8000 does.
+constexpr int kCdefTW = 64, kCdefTH = 16, kCdefPitch = 70;  // pitch: rows 35 words apart -> odd bank shift
+
 template <typename T>
-__global__ void __launch_bounds__(256) cdef_filter_kernel(CdefPlaneArgs a) {
-  const int xsize = 8 >> a.xdec, ysize = 8 >> a.ydec;
-  const int pw = a.w8 * xsize, ph = a.h8 * ysize;
+__global__ void __launch_bounds__(256) cdef_filter_kernel(const __grid_constant__ CdefPlaneArgs a) {
+  __shared__ short s_tile[(kCdefTH + 4) * kCdefPitch];
+  const int xs_log2 = 3 - a.xdec, ys_log2 = 3 - a.ydec;
+  const int pw = a.w8 << xs_log2, ph = a.h8 << ys_log2;
   const int coeff_shift = a.bit_depth - 8;
   const T *in = (const T *)a.in;
   T *out = (T *)a.out;
-  // 2-D launch: 64 x 4 pixels per CTA, one pixel per thread; block sizes are powers of two
-  const int xs_log2 = 3 - a.xdec, ys_log2 = 3 - a.ydec;
-  {
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x >= pw || y >= ph) return;
-    const int gy = y >> ys_log2, gx = x >> xs_log2, i = y - (gy << ys_log2), j = x - (gx << xs_log2);
-    const int b = gy * a.w8 + gx;
-    const T *blk = in + (long long)(gy * ysize) * a.in_stride + gx * xsize;
-    int v;
-    if (a.skip8 && a.skip8[b]) {
-      v = (int)blk[(long long)i * a.in_stride + j];  // cdef.rs:557-564
+  const int rx1 = (a.rx8 + a.rw8) << xs_log2, ry1 = (a.ry8 + a.rh8) << ys_log2;
+  const int tx0 = (a.rx8 << xs_log2) + blockIdx.x * kCdefTW, ty0 = (a.ry8 << ys_log2) + blockIdx.y * kCdefTH;
+  // ---- stage the tile + halo
+  for (int i = threadIdx.x; i < (kCdefTH + 4) * (kCdefTW + 4); i += 256) {
+    const int r = i / (kCdefTW + 4), c = i - r * (kCdefTW + 4);
+    const int y = ty0 + r - 2, x = tx0 + c - 2;
+    short v = (short)0x8000;
+    if (x >= 0 && x < pw && y >= 0 && y < ph) v = (short)in[(long long)y * a.in_stride + x];
+    s_tile[r * kCdefPitch + c] = v;
+  }
+  __syncthreads();
+  // ---- 4 pixels per thread
+  const int row = threadIdx.x >> 4, col = (threadIdx.x & 15) * 4;
+  const int x = tx0 + col, y = ty0 + row;
+  if (x >= rx1 || y >= ry1) return;
+  const int gy = y >> ys_log2, gx = x >> xs_log2;
+  const int b = gy * a.w8 + gx;
+  const short *ctr = s_tile + (row + 2) * kCdefPitch + col + 2;
+  int res[4];
+  if (a.skip8 && a.skip8[b]) {  // cdef.rs:557-564
+#pragma unroll
+    for (int j = 0; j < 4; j++) res[j] = ctr[j];
+  } else {
+    const int strength = a.strength_sb[(gy >> 3) * a.sbw + (gx >> 3)];
+    const int pri = strength >> 2;
+    int sec = strength & 3;
+    if (sec == 3) sec = 4;  // cdef.rs:421-426
+    const int d = a.dir[b];
+    int local_pri, local_dir, local_damping = a.damping + coeff_shift;
+    const int local_sec = sec << coeff_shift;
+    if (a.plane == 0) {
+      local_pri = adjust_strength(pri << coeff_shift, a.var[b]);
+      local_dir = pri != 0 ? d : 0;
     } else {
-      int edges = 0;  // cdef.rs:446-466 flattened: frame position decides the padding we have
-      if (gy > 0) edges |= HAVE_TOP;
-      if (gx > 0) edges |= HAVE_LEFT;
-      if (gy + 1 < a.h8) edges |= HAVE_BOTTOM;
-      if (gx + 1 < a.w8) edges |= HAVE_RIGHT;
-      const int strength = a.strength_sb[(gy >> 3) * a.sbw + (gx >> 3)];
-      const int pri = strength >> 2;
-      int sec = strength & 3;
-      if (sec == 3) sec = 4;  // cdef.rs:421-426
-      const int d = a.dir[b];
-      int local_pri, local_dir, local_damping = a.damping + coeff_shift;
-      const int local_sec = sec << coeff_shift;
-      if (a.plane == 0) {
-        local_pri = adjust_strength(pri << coeff_shift, a.var[b]);
-        local_dir = pri != 0 ? d : 0;
-      } else {
-        local_pri = pri << coeff_shift;
-        local_damping -= 1;
-        const int remap = (0x66654207 >> (4 * d)) & 7;  // [7,0,2,4,5,6,6,6], cdef.rs:505-509
-        local_dir = pri != 0 ? (a.xdec != a.ydec ? remap : d) : 0;
-      }
-      const int stride = a.in_stride;
-      auto load = [&](int dy, int dx) -> int {
-        const int yy = i + dy, xx = j + dx;
-        if ((xx < 0 && !(edges & HAVE_LEFT)) || (xx >= xsize && !(edges & HAVE_RIGHT)) ||
-            (yy < 0 && !(edges & HAVE_TOP)) || (yy >= ysize && !(edges & HAVE_BOTTOM)))
-          return kVeryLarge;
-        return (int)blk[(long long)yy * stride + xx];
-      };
-      v = cdef_pixel(load, local_pri, local_sec, local_dir, local_damping, coeff_shift);
+      local_pri = pri << coeff_shift;
+      local_damping -= 1;
+      const int remap = (0x66654207 >> (4 * d)) & 7;  // [7,0,2,4,5,6,6,6], cdef.rs:505-509
+      local_dir = pri != 0 ? (a.xdec != a.ydec ? remap : d) : 0;
     }
-    out[(long long)y * a.out_stride + x] = (T)v;
+    const int pri_shift = constrain_shift(local_pri, local_damping);
+    const int sec_shift = constrain_shift(local_sec, local_damping);
+    const int sel = (local_pri >> coeff_shift) & 1;
+    const int pt0 = sel ? 3 : 4, pt1 = sel ? 3 : 2;
+    int off[6];  // tap offsets in the tile: primary k = 0, 1; secondary (dir + 2) k = 0, 1; (dir + 6) k = 0, 1
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      off[k] = kDirs[local_dir][k][0] * kCdefPitch + kDirs[local_dir][k][1];
+      off[2 + k] = kDirs[(local_dir + 2) & 7][k][0] * kCdefPitch + kDirs[(local_dir + 2) & 7][k][1];
+      off[4 + k] = kDirs[(local_dir + 6) & 7][k][0] * kCdefPitch + kDirs[(local_dir + 6) & 7][k][1];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const short *c = ctr + j;
+      const int xv = c[0];
+      int sum = 0, mx = xv;
+      unsigned mn = (unsigned)xv;
+      auto tap = [&](int o, int thr, int shift, int w) {
+        const int p0 = c[o], p1 = c[-o];
+        sum += w * (constrain(p0 - xv, thr, shift) + constrain(p1 - xv, thr, shift));
+        mx = max(mx, max(p0, p1));
+        mn = min(mn, min((unsigned)p0, (unsigned)p1));
+      };
+      tap(off[0], local_pri, pri_shift, pt0);
+      tap(off[1], local_pri, pri_shift, pt1);
+      tap(off[2], local_sec, sec_shift, 2);
+      tap(off[3], local_sec, sec_shift, 1);
+      tap(off[4], local_sec, sec_shift, 2);
+      tap(off[5], local_sec, sec_shift, 1);
+      const int v = xv + ((8 + sum - (sum < 0)) >> 4);
+      res[j] = min(max(v, (int)mn), mx);
+    }
+  }
+  T *o = out + (long long)y * a.out_stride + x;
+  if (x + 4 <= rx1 && ((uintptr_t)o & (4 * sizeof(T) - 1)) == 0) {
+    if (sizeof(T) == 1)
+      *(uchar4 *)o = make_uchar4((unsigned char)res[0], (unsigned char)res[1], (unsigned char)res[2], (unsigned char)res[3]);
+    else
+      *(ushort4 *)o = make_ushort4((unsigned short)res[0], (unsigned short)res[1], (unsigned short)res[2], (unsigned short)res[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (x + j < rx1) o[j] = (T)res[j];
   }
 }
 
@@ -237,31 +291,34 @@ __global__ void cdef_filter_tmp16_kernel(T *dst, int dst_stride, const uint16_t 
 
 }  // namespace
 
-extern "C" int b200_cdef_find_dir_dev(b200_ctx *ctx, const b200_plane *luma, int bit_depth,
-                                      const uint8_t *d_skip8, uint8_t *d_dir, int32_t *d_var) {
+namespace {
+
+int find_dir_rect(b200_ctx *ctx, const b200_plane *luma, int bit_depth, const uint8_t *d_skip8, uint8_t *d_dir,
+                  int32_t *d_var, int rx8, int ry8, int rw8, int rh8) {
   B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
   B200_REQUIRE(ctx, luma && luma->data && d_dir && d_var, "NULL argument");
   B200_REQUIRE(ctx, (luma->width & 7) == 0 && (luma->height & 7) == 0,
                "luma %dx%d must be a multiple of 8 (rav1e pads frames to 8)", luma->width, luma->height);
   B200_REQUIRE(ctx, (luma->bpp == 1) == (bit_depth == 8), "bpp %d vs bit depth %d", luma->bpp, bit_depth);
-  B200_CUDA(ctx, cudaSetDevice(ctx->device));
   const int w8 = luma->width >> 3, h8 = luma->height >> 3;
-  const int grid = std::min((w8 * h8 + 127) / 128, ctx->num_sms * 16);
+  B200_REQUIRE(ctx, rx8 >= 0 && ry8 >= 0 && rw8 > 0 && rh8 > 0 && rx8 + rw8 <= w8 && ry8 + rh8 <= h8,
+               "block rect (%d, %d, %d, %d) outside the %d x %d grid", rx8, ry8, rw8, rh8, w8, h8);
+  B200_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int grid = std::min((rw8 * rh8 + 127) / 128, ctx->num_sms * 16);
   if (luma->bpp == 1)
     cdef_find_dir_kernel<uint8_t><<<grid, 128, 0, ctx->stream>>>((const uint8_t *)luma->data, luma->stride, w8, h8,
-                                                                  bit_depth - 8, d_skip8, d_dir, d_var);
+                                                                  bit_depth - 8, d_skip8, d_dir, d_var, rx8, ry8, rw8, rh8);
   else
-    cdef_find_dir_kernel<uint16_t><<<grid, 128, 0, ctx->stream>>>((const uint16_t *)luma->data, luma->stride, w8,
-                                                                   h8, bit_depth - 8, d_skip8, d_dir, d_var);
+    cdef_find_dir_kernel<uint16_t><<<grid, 128, 0, ctx->stream>>>((const uint16_t *)luma->data, luma->stride, w8, h8,
+                                                                   bit_depth - 8, d_skip8, d_dir, d_var, rx8, ry8, rw8, rh8);
   B200_LAUNCH_CHECK(ctx);
   return B200_OK;
 }
 
-extern "C" int b200_cdef_filter_plane_dev(b200_ctx *ctx, const b200_plane *in, const b200_plane *out,
-                                          int plane, int xdec, int ydec, int luma_width,
-                                          int luma_height, int bit_depth, int damping,
-                                          const uint8_t *d_skip8, const uint8_t *d_dir,
-                                          const int32_t *d_var, const uint8_t *d_strength_sb) {
+int filter_rect(b200_ctx *ctx, const b200_plane *in, const b200_plane *out, int plane, int xdec, int ydec,
+                int luma_width, int luma_height, int bit_depth, int damping, const uint8_t *d_skip8,
+                const uint8_t *d_dir, const int32_t *d_var, const uint8_t *d_strength_sb, int rx8, int ry8, int rw8,
+                int rh8) {
   B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
   B200_REQUIRE(ctx, in && out && in->data && out->data && in->bpp == out->bpp, "bad planes");
   B200_REQUIRE(ctx, in->data != out->data, "CDEF cannot run in place (taps read unfiltered neighbours)");
@@ -269,6 +326,9 @@ extern "C" int b200_cdef_filter_plane_dev(b200_ctx *ctx, const b200_plane *in, c
   B200_REQUIRE(ctx, (xdec == 0 || xdec == 1) && (ydec == 0 || ydec == 1) && plane >= 0 && plane < 3, "bad plane");
   B200_REQUIRE(ctx, (in->bpp == 1) == (bit_depth == 8), "bpp %d vs bit depth %d", in->bpp, bit_depth);
   B200_REQUIRE(ctx, d_dir && d_var && d_strength_sb, "NULL dir/var/strength");
+  B200_REQUIRE(ctx, rx8 >= 0 && ry8 >= 0 && rw8 > 0 && rh8 > 0 && rx8 + rw8 <= (luma_width >> 3) &&
+                        ry8 + rh8 <= (luma_height >> 3),
+               "block rect (%d, %d, %d, %d) outside the grid", rx8, ry8, rw8, rh8);
   B200_CUDA(ctx, cudaSetDevice(ctx->device));
   CdefPlaneArgs a;
   a.in = in->data;
@@ -281,19 +341,52 @@ extern "C" int b200_cdef_filter_plane_dev(b200_ctx *ctx, const b200_plane *in, c
   a.w8 = luma_width >> 3;
   a.h8 = luma_height >> 3;
   a.sbw = (luma_width + 63) >> 6;
+  a.rx8 = rx8, a.ry8 = ry8, a.rw8 = rw8, a.rh8 = rh8;
   a.bit_depth = bit_depth;
   a.damping = damping;
   a.skip8 = d_skip8;
   a.dir = d_dir;
   a.var = d_var;
   a.strength_sb = d_strength_sb;
-  const dim3 grid(((luma_width >> xdec) + 63) / 64, ((luma_height >> ydec) + 3) / 4);
+  const dim3 grid((((rw8 * 8) >> xdec) + kCdefTW - 1) / kCdefTW, (((rh8 * 8) >> ydec) + kCdefTH - 1) / kCdefTH);
   if (in->bpp == 1)
     cdef_filter_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(a);
   else
     cdef_filter_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(a);
   B200_LAUNCH_CHECK(ctx);
   return B200_OK;
+}
+
+}  // namespace
+
+extern "C" int b200_cdef_find_dir_dev(b200_ctx *ctx, const b200_plane *luma, int bit_depth,
+                                      const uint8_t *d_skip8, uint8_t *d_dir, int32_t *d_var) {
+  B200_REQUIRE(ctx, ctx != nullptr && luma != nullptr, "NULL argument");
+  return find_dir_rect(ctx, luma, bit_depth, d_skip8, d_dir, d_var, 0, 0, luma->width >> 3, luma->height >> 3);
+}
+
+extern "C" int b200_cdef_find_dir_rect_dev(b200_ctx *ctx, const b200_plane *luma, int bit_depth,
+                                           const uint8_t *d_skip8, uint8_t *d_dir, int32_t *d_var, int rx8, int ry8,
+                                           int rw8, int rh8) {
+  return find_dir_rect(ctx, luma, bit_depth, d_skip8, d_dir, d_var, rx8, ry8, rw8, rh8);
+}
+
+extern "C" int b200_cdef_filter_plane_dev(b200_ctx *ctx, const b200_plane *in, const b200_plane *out,
+                                          int plane, int xdec, int ydec, int luma_width,
+                                          int luma_height, int bit_depth, int damping,
+                                          const uint8_t *d_skip8, const uint8_t *d_dir,
+                                          const int32_t *d_var, const uint8_t *d_strength_sb) {
+  return filter_rect(ctx, in, out, plane, xdec, ydec, luma_width, luma_height, bit_depth, damping, d_skip8, d_dir,
+                     d_var, d_strength_sb, 0, 0, luma_width >> 3, luma_height >> 3);
+}
+
+extern "C" int b200_cdef_filter_rect_dev(b200_ctx *ctx, const b200_plane *in, const b200_plane *out, int plane,
+                                         int xdec, int ydec, int luma_width, int luma_height, int bit_depth,
+                                         int damping, const uint8_t *d_skip8, const uint8_t *d_dir,
+                                         const int32_t *d_var, const uint8_t *d_strength_sb, int rx8, int ry8,
+                                         int rw8, int rh8) {
+  return filter_rect(ctx, in, out, plane, xdec, ydec, luma_width, luma_height, bit_depth, damping, d_skip8, d_dir,
+                     d_var, d_strength_sb, rx8, ry8, rw8, rh8);
 }
 
 // ---- per-call forms with the reference's asm signatures (asm/x86/cdef.rs:16-37, :184-191)

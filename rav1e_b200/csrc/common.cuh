@@ -73,6 +73,7 @@ int b200_reserve_dwork(b200_ctx *ctx, size_t bytes);
 int b200_mc_cands_internal(b200_ctx *ctx, const b200_plane *ref, const b200_block *d_blocks,
                            const b200_cand *d_cands, size_t ncands, int w, int h, int mode,
                            int bit_depth, void *d_out);
+int b200_plane_unpack_internal(b200_ctx *ctx, const b200_plane *p, const void *d_packed);
 b200_ctx *b200_default_ctx();  // lazily created; aborts loudly if no device (no CPU fallback)
 
 #ifdef __CUDACC__

@@ -34,11 +34,18 @@ struct b200_frame_pipe {
   void *dbase = nullptr;  // one allocation carved into the buffers below
   b200_block *d_blocks = nullptr;
   uint32_t *d_offs_sad = nullptr, *d_offs_satd = nullptr;
+  // one staging area for everything a push sends: [frame (packed rows) | sad offsets | satd offsets |
+  // centres]; inputs that lie back to back in host memory travel as ONE copy
+  uint8_t *d_stage = nullptr;
+  size_t frame_bytes = 0;
   int8_t *d_o8_sad = nullptr, *d_o8_satd = nullptr;
   int16_t *d_centers = nullptr;
   b200_cand *d_cand_sad = nullptr, *d_cand_satd = nullptr;
+  // outputs, contiguous in this order so that host buffers laid out the same way take one copy:
+  // [best_sad | best_satd | coefficients (raw, or quantized) | eob | tx_dist]
   b200_me_result *d_best_sad = nullptr, *d_best_satd = nullptr;
-  void *d_coef = nullptr, *d_q = nullptr;
+  void *d_coef = nullptr, *d_q = nullptr;  // d_coef is scratch when the quantize chain is on
+  void *d_cout = nullptr;                  // what travels: d_coef (raw) or d_q
   uint16_t *d_eob = nullptr;
   uint64_t *d_dist = nullptr;
   size_t coef_bytes = 0, q_bytes = 0;
@@ -47,19 +54,22 @@ struct b200_frame_pipe {
 namespace {
 
 // candidate k of block b = centre_b + 8 * (offset_row, offset_col); lists have `per` entries per block
-__global__ void expand_offsets_kernel(const char2 *offs, const short2 *centers, size_t nblocks, int per,
-                                      b200_cand *out) {
-  const size_t n = nblocks * (size_t)per;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t b = i / (size_t)per;
-    const char2 o = offs[i];  // {row, col}, full pel
+// both lists of a push in one launch
+__global__ void expand_offsets_kernel(const char2 *offs1, int per1, b200_cand *out1, const char2 *offs2, int per2,
+                                      b200_cand *out2, const short2 *centers, size_t nblocks) {
+  const size_t n1 = nblocks * (size_t)per1, n = n1 + nblocks * (size_t)per2;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    const bool first = k < n1;
+    const size_t i = first ? k : k - n1;
+    const size_t b = i / (size_t)(first ? per1 : per2);
+    const char2 o = (first ? offs1 : offs2)[i];  // {row, col}, full pel
     short2 c = make_short2(0, 0);
     if (centers) c = centers[b];
     b200_cand r;
     r.block = (uint32_t)b;
     r.mv_row = (short)(c.x + (short)(8 * o.x));
     r.mv_col = (short)(c.y + (short)(8 * o.y));
-    out[i] = r;
+    (first ? out1 : out2)[i] = r;
   }
 }
 
@@ -105,17 +115,23 @@ extern "C" int b200_frame_pipe_create(b200_ctx *ctx, const b200_frame_pipe_cfg *
     p->d_blocks = (b200_block *)c.take(nb * sizeof(b200_block));
     p->d_offs_sad = (uint32_t *)c.take((nb + 1) * 4);
     p->d_offs_satd = (uint32_t *)c.take((nb + 1) * 4);
-    p->d_o8_sad = (int8_t *)c.take(ns * 2);
-    p->d_o8_satd = (int8_t *)c.take(nt * 2);
-    p->d_centers = (int16_t *)c.take(nb * 4);
+    p->frame_bytes = (size_t)cfg->width * cfg->height * cfg->bpp;
+    p->d_stage = (uint8_t *)c.take(p->frame_bytes + ns * 2 + nt * 2 + nb * 4);  // dense: mirrors the host layout
+    p->d_o8_sad = p->d_stage ? (int8_t *)(p->d_stage + p->frame_bytes) : nullptr;
+    p->d_o8_satd = p->d_stage ? p->d_o8_sad + ns * 2 : nullptr;
+    p->d_centers = p->d_stage ? (int16_t *)(p->d_o8_satd + nt * 2) : nullptr;
     p->d_cand_sad = (b200_cand *)c.take(ns * sizeof(b200_cand));
     p->d_cand_satd = (b200_cand *)c.take(nt * sizeof(b200_cand));
-    p->d_best_sad = (b200_me_result *)c.take(nb * sizeof(b200_me_result));
-    p->d_best_satd = (b200_me_result *)c.take(nb * sizeof(b200_me_result));
-    p->d_coef = c.take(p->coef_bytes);
-    p->d_q = c.take(p->q_bytes);
-    p->d_eob = (uint16_t *)c.take(nb * 2);
-    p->d_dist = (uint64_t *)c.take(nb * 8);
+    const bool quant = p->q_bytes != 0;
+    if (quant) p->d_coef = c.take(p->coef_bytes);  // scratch: only the quantized coefficients travel
+    // dense output block (16-byte multiples keep every member aligned)
+    uint8_t *ob = (uint8_t *)c.take(2 * nb * sizeof(b200_me_result) + (quant ? p->q_bytes : p->coef_bytes) + nb * 2 + 16 + nb * 8);
+    p->d_best_sad = (b200_me_result *)ob;
+    p->d_best_satd = ob ? p->d_best_sad + nb : nullptr;
+    p->d_cout = ob ? (void *)(p->d_best_satd + nb) : nullptr;
+    if (quant) p->d_q = p->d_cout; else p->d_coef = p->d_cout;
+    p->d_eob = ob ? (uint16_t *)((uint8_t *)p->d_cout + (quant ? p->q_bytes : p->coef_bytes)) : nullptr;
+    p->d_dist = ob ? (uint64_t *)((uint8_t *)p->d_eob + b200_align_up(nb * 2, 8)) : nullptr;
     if (pass == 0) {
       const cudaError_t e = cudaMalloc(&p->dbase, c.used + 256);
       if (e != cudaSuccess) {
@@ -168,23 +184,43 @@ extern "C" int b200_frame_pipe_push(b200_frame_pipe *p, const void *frame, ptrdi
   B200_REQUIRE(ctx, frame != nullptr, "frame is NULL");
   B200_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t nb = p->nblocks, ns = nb * (size_t)cfg.sad_per_block, nt = nb * (size_t)cfg.satd_per_block;
-  // ---- the new frame: uploaded once, the previous one becomes the reference
+  // ---- inputs -> the device staging area.  The frame is uploaded once (the previous one becomes the
+  // reference); a dense frame followed in host memory by its lists travels as ONE copy.
   const int nxt = p->cur < 0 ? 0 : p->cur ^ 1;
-  {
-    const int was_async = ctx->async_batch;
-    ctx->async_batch = 1;  // enqueue only; the synchronisation policy is applied once, at the end
-    const int st = b200_plane_upload(ctx, &p->planes[nxt], frame, frame_stride_bytes);
-    ctx->async_batch = was_async;
-    if (st) return st;
-  }
   const bool first = p->cur < 0;
+  const size_t row_bytes = (size_t)cfg.width * cfg.bpp;
+  B200_REQUIRE(ctx, first || ((ns == 0 || sad_offsets) && (nt == 0 || satd_offsets)), "NULL candidate offsets");
+  const uint8_t *fend = (const uint8_t *)frame + p->frame_bytes;
+  const bool dense = (size_t)frame_stride_bytes == row_bytes;
+  size_t one = 0;  // bytes covered by the first (possibly only) copy
+  if (dense) {
+    one = p->frame_bytes;
+    if (!first && (ns == 0 || (const uint8_t *)sad_offsets == fend)) {
+      one += ns * 2;
+      if (nt == 0 || (const uint8_t *)satd_offsets == fend + ns * 2) {
+        one += nt * 2;
+        if (centers && (const uint8_t *)centers == fend + ns * 2 + nt * 2) one += nb * 4;
+      }
+    }
+    B200_CUDA(ctx, cudaMemcpyAsync(p->d_stage, frame, one, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    B200_CUDA(ctx, cudaMemcpy2DAsync(p->d_stage, row_bytes, frame, (size_t)frame_stride_bytes, row_bytes, cfg.height,
+                                     cudaMemcpyHostToDevice, ctx->stream));
+    one = p->frame_bytes;
+  }
+  if (int st = b200_plane_unpack_internal(ctx, &p->planes[nxt], p->d_stage)) return st;
   p->cur = nxt;
   if (first) {  // nothing to search against yet
     if (!ctx->async_batch) B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return B200_OK;
   }
+  if (ns && one < p->frame_bytes + ns * 2)
+    B200_CUDA(ctx, cudaMemcpyAsync(p->d_o8_sad, sad_offsets, ns * 2, cudaMemcpyHostToDevice, ctx->stream));
+  if (nt && one < p->frame_bytes + ns * 2 + nt * 2)
+    B200_CUDA(ctx, cudaMemcpyAsync(p->d_o8_satd, satd_offsets, nt * 2, cudaMemcpyHostToDevice, ctx->stream));
+  if (centers && one < p->frame_bytes + ns * 2 + nt * 2 + nb * 4)
+    B200_CUDA(ctx, cudaMemcpyAsync(p->d_centers, centers, nb * 4, cudaMemcpyHostToDevice, ctx->stream));
   const b200_plane *cur = &p->planes[nxt], *ref = &p->planes[nxt ^ 1];
-  B200_REQUIRE(ctx, (ns == 0 || sad_offsets) && (nt == 0 || satd_offsets), "NULL candidate offsets");
   b200_me_params mp{};
   mp.w = cfg.block_w, mp.h = cfg.block_h;
   mp.frame_w_in_b = 2 * ((cfg.width + 7) >> 3);  // encoder.rs:852
@@ -192,47 +228,60 @@ extern "C" int b200_frame_pipe_push(b200_frame_pipe *p, const void *frame, ptrdi
   mp.lambda = cfg.lambda;
   mp.bit_depth = cfg.bit_depth;
   mp.window_hint_px = cfg.window_hint_px;
-  if (centers) B200_CUDA(ctx, cudaMemcpyAsync(p->d_centers, centers, nb * 4, cudaMemcpyHostToDevice, ctx->stream));
-  const short2 *dc = centers ? (const short2 *)p->d_centers : nullptr;
-  if (ns) {
-    B200_CUDA(ctx, cudaMemcpyAsync(p->d_o8_sad, sad_offsets, ns * 2, cudaMemcpyHostToDevice, ctx->stream));
-    expand_offsets_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>((const char2 *)p->d_o8_sad, dc, nb, cfg.sad_per_block, p->d_cand_sad);
+  if (ns + nt) {
+    expand_offsets_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(
+        (const char2 *)p->d_o8_sad, cfg.sad_per_block, p->d_cand_sad, (const char2 *)p->d_o8_satd, cfg.satd_per_block,
+        p->d_cand_satd, centers ? (const short2 *)p->d_centers : nullptr, nb);
     B200_LAUNCH_CHECK(ctx);
+  }
+  if (ns) {
     mp.use_satd = 0;
     if (int st = b200_me_candidates_dev(ctx, cur, ref, p->d_blocks, nb, p->d_cand_sad, ns, p->d_offs_sad, nullptr, &mp,
                                         nullptr, nullptr, p->d_best_sad))
       return st;
-    if (best_sad)
-      B200_CUDA(ctx, cudaMemcpyAsync(best_sad, p->d_best_sad, nb * sizeof(b200_me_result), cudaMemcpyDeviceToHost, ctx->stream));
   }
   if (nt) {
-    B200_CUDA(ctx, cudaMemcpyAsync(p->d_o8_satd, satd_offsets, nt * 2, cudaMemcpyHostToDevice, ctx->stream));
-    expand_offsets_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>((const char2 *)p->d_o8_satd, dc, nb, cfg.satd_per_block, p->d_cand_satd);
-    B200_LAUNCH_CHECK(ctx);
     mp.use_satd = 1;
     if (int st = b200_me_candidates_dev(ctx, cur, ref, p->d_blocks, nb, p->d_cand_satd, nt, p->d_offs_satd, nullptr, &mp,
                                         nullptr, nullptr, p->d_best_satd))
       return st;
-    if (best_satd)
-      B200_CUDA(ctx, cudaMemcpyAsync(best_satd, p->d_best_satd, nb * sizeof(b200_me_result), cudaMemcpyDeviceToHost, ctx->stream));
   }
+  const bool quant = cfg.tx_size >= 0 && cfg.ac_quant;
   if (cfg.tx_size >= 0) {
     // residual of every block against the reference displaced by its SAD winner -> forward transform
     // (-> quantize chain), all on the device
     if (int st = b200_fwd_txfm_residual_dev(ctx, cur, ref, p->d_blocks, nb, ns ? p->d_best_sad : nullptr, p->d_coef,
                                             cfg.tx_size, cfg.tx_type, cfg.bit_depth))
       return st;
-    if (cfg.ac_quant) {
+    if (quant)
       if (int st = b200_quantize_dev(ctx, p->d_coef, nb, cfg.tx_size, cfg.tx_type, cfg.dc_quant, cfg.ac_quant, 0,
                                      cfg.bpp == 2, p->d_q, nullptr, p->d_eob, p->d_dist))
         return st;
-      if (coeffs) B200_CUDA(ctx, cudaMemcpyAsync(coeffs, p->d_q, p->q_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-      if (eob) B200_CUDA(ctx, cudaMemcpyAsync(eob, p->d_eob, nb * 2, cudaMemcpyDeviceToHost, ctx->stream));
-      if (tx_dist) B200_CUDA(ctx, cudaMemcpyAsync(tx_dist, p->d_dist, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    } else if (coeffs) {
-      B200_CUDA(ctx, cudaMemcpyAsync(coeffs, p->d_coef, p->coef_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    }
   }
+  // ---- results -> host.  Buffers laid out like the device's output block
+  // ([best_sad | best_satd | coefficients | eob | tx_dist], each directly behind the other) take one copy.
+  const size_t cbytes = cfg.tx_size < 0 ? 0 : quant ? p->q_bytes : p->coef_bytes;
+  const size_t rb = nb * sizeof(b200_me_result);
+  const bool out_dense = ns && nt && best_sad && best_satd == best_sad + nb &&
+                         (cbytes == 0 || (coeffs && (uint8_t *)coeffs == (uint8_t *)(best_satd + nb)));
+  if (out_dense) {
+    size_t bytes = 2 * rb + cbytes;
+    if (quant && eob && (uint8_t *)eob == (uint8_t *)coeffs + cbytes) {
+      bytes += nb * 2;
+      eob = nullptr;  // travelled with the block
+      if (tx_dist && (uint8_t *)tx_dist == (uint8_t *)coeffs + cbytes + b200_align_up(nb * 2, 8)) {
+        bytes = 2 * rb + cbytes + b200_align_up(nb * 2, 8) + nb * 8;
+        tx_dist = nullptr;
+      }
+    }
+    B200_CUDA(ctx, cudaMemcpyAsync(best_sad, p->d_best_sad, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    if (ns && best_sad) B200_CUDA(ctx, cudaMemcpyAsync(best_sad, p->d_best_sad, rb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nt && best_satd) B200_CUDA(ctx, cudaMemcpyAsync(best_satd, p->d_best_satd, rb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cbytes && coeffs) B200_CUDA(ctx, cudaMemcpyAsync(coeffs, p->d_cout, cbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (quant && eob) B200_CUDA(ctx, cudaMemcpyAsync(eob, p->d_eob, nb * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  if (quant && tx_dist) B200_CUDA(ctx, cudaMemcpyAsync(tx_dist, p->d_dist, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (!ctx->async_batch) B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return B200_OK;
 }

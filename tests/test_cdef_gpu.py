@@ -131,3 +131,39 @@ def test_4k_frame_properties():
     np.testing.assert_array_equal(got[y0:y1], want[8:-8])
     c.plane_free(pin)
     c.plane_free(pout)
+
+
+def test_tile_rects_equal_the_whole_frame():
+    """b200_cdef_find_dir_rect_dev / b200_cdef_filter_rect_dev over the tiles of a frame (each tile its
+    own launch, like one rank per tile) == the whole-frame calls: taps cross tile borders, the
+    sentinel appears only outside the frame."""
+    import torch
+    from rav1e_b200 import shard
+    c = G.ctx()
+    rng = np.random.default_rng(77)
+    W, H, bd = 256, 192, 8
+    luma = rng.integers(0, 256, (H, W)).astype(np.uint8)
+    skip8 = (rng.random((H // 8, W // 8)) < 0.15).astype(np.uint8)
+    sbw, sbh = (W + 63) // 64, (H + 63) // 64
+    strength = rng.integers(0, 64, (sbh, sbw)).astype(np.uint8)
+    src = c.plane_from_host(luma, 8)
+    whole, tiled = c.plane_from_host(np.zeros_like(luma), 0), c.plane_from_host(np.zeros_like(luma), 0)
+    n8 = (H // 8) * (W // 8)
+    d_skip, d_str = G.to_dev(skip8), G.to_dev(strength)
+    d_dir, d_var = torch.zeros(n8, dtype=torch.uint8, device="cuda"), torch.zeros(n8, dtype=torch.int32, device="cuda")
+    d_dir2, d_var2 = torch.zeros_like(d_dir), torch.zeros_like(d_var)
+    c.cdef_find_dir_dev(src, bd, d_skip, d_dir, d_var)
+    c.cdef_filter_plane_dev(src, whole, 0, 0, 0, W, H, bd, 5, d_skip, d_dir, d_var, d_str)
+    for (x, y, w, h) in shard.tile_grid(W, H, 1, 1):                     # 2 x 2 tiles of 128 x 128 / 128 x 64
+        r8 = (x // 8, y // 8, w // 8, h // 8)
+        c.cdef_find_dir_rect_dev(src, bd, d_skip, d_dir2, d_var2, r8)
+        c.cdef_filter_rect_dev(src, tiled, 0, 0, 0, W, H, bd, 5, d_skip, d_dir2, d_var2, d_str, r8)
+    c.synchronize()
+    assert torch.equal(d_dir, d_dir2) and torch.equal(d_var, d_var2)
+    import ctypes
+    a, b = np.zeros_like(luma), np.zeros_like(luma)
+    c.check(c.L.b200_plane_download(c.h, ctypes.byref(whole), a.ctypes.data, a.strides[0]))
+    c.check(c.L.b200_plane_download(c.h, ctypes.byref(tiled), b.ctypes.data, b.strides[0]))
+    np.testing.assert_array_equal(a, b)
+    for p in (src, whole, tiled):
+        c.plane_free(p)
