@@ -523,16 +523,23 @@ def run_b200_tiles(args, rank, world, local_rank):
     def leg_txfm():
         ctx.fwd_txfm_residual_multi_dev(pairs, d_blocks_all, F * nb, d_best, d_coef, 2, 0, 8)
 
+    # every (frame, owned tile) of the batch as one item list: 32 items per launch
+    items = (B.CdefItem * (F * len(rects8)))()
+    k = 0
+    for f in range(F):
+        for r8 in rects8:
+            it = items[k]
+            it.inp, it.out = C.pointer(planes[f][0]), C.pointer(outs[f])
+            it.d_skip8 = None
+            it.d_dir, it.d_var = d_dir.data_ptr() + f * n8, d_var.data_ptr() + f * n8 * 4
+            it.rx8, it.ry8, it.rw8, it.rh8 = r8
+            k += 1
+
     def leg_cdef_dir():
-        for f in range(F):
-            for r8 in rects8:
-                ctx.cdef_find_dir_rect_dev(planes[f][0], 8, None, d_dir[f * n8:], d_var[f * n8:], r8)
+        ctx.cdef_tiles_dev(items, 0, 0, 0, W4K, H4K, 8, 5, d_str, find_dir=True, filter=False)
 
     def leg_cdef_filter():
-        for f in range(F):
-            for r8 in rects8:
-                ctx.cdef_filter_rect_dev(planes[f][0], outs[f], 0, 0, 0, W4K, H4K, 8, 5, None, d_dir[f * n8:],
-                                         d_var[f * n8:], d_str, r8)
+        ctx.cdef_tiles_dev(items, 0, 0, 0, W4K, H4K, 8, 5, d_str, find_dir=False, filter=True)
 
     def leg_comm():
         """on the side stream: pack the winners to 8-byte records, all-gather them"""

@@ -161,6 +161,70 @@ def main():
     emit("winner put_8tap + residual + fwd_txfm 16x16 10-bit", nb, "blocks", ms, 2598,
          "SURVEY §8d fused MC->SATD->txfm figure (2598 B/block)")
 
+    # ---- config 4, fused: sub-pel refinement + winner's residual + 16x16 DCT in ONE kernel
+    # (b200_subpel_rdo_dev): no prediction touches HBM
+    for name, cur, ref, bd, bpp in (("8-bit", cur8, ref8, 8, 1), ("10-bit", cur10, ref10, 10, 2)):
+        p = B.me_params(16, 16, W, H, 6400, allow_hp=True, use_satd=True, bit_depth=bd)
+        d_fc = torch.empty(nb * 256, dtype=torch.int16 if bd == 8 else torch.int32, device="cuda")
+        ms = timed(lambda: ctx.subpel_rdo_dev(cur, ref, d_blocks, nb, d_c, n, d_o, p, 0, 2, 0, None, None, None,
+                                              d_best, d_fc), reps=10)
+        emit(f"FUSED subpel RDO (8 x [put_8tap + SATD + cost] + argmin + residual + DCT 16x16) {name}", nb, "blocks",
+             ms, 8 * 23 * 23 * bpp + 256 * bpp + 256 * (2 if bd == 8 else 4) + 16,
+             "BASELINE configs[3]; bytes: 8 source footprints + org block + coefficients + winner "
+             "(SURVEY 8d quotes 2598 B per single-candidate block at 10 bit)")
+
+    # ---- lookahead (api/lookahead.rs): pyramid, intra / inter cost maps, importance-block difference
+    hres = ctx.plane_alloc(W // 2, H // 2, PAD // 2, 1)
+    qres = ctx.plane_alloc(W // 4, H // 4, PAD // 4, 1)
+
+    def pyramid():
+        ctx.plane_downsample_dev(cur8, hres, W // 2, H // 2)
+        ctx.plane_downsample_dev(hres, qres, W // 4, H // 4)
+    ms = timed(pyramid, reps=10)
+    emit("Plane::downsampled x2 (half + quarter resolution ME pyramid) 1080p 8-bit", W * H, "source pixels", ms,
+         1 + 0.25 + 0.25 + 0.0625, "reads the level above, writes the padded level below")
+    nimp = (W // 8) * (H // 8)
+    d_ic = torch.empty(nimp, dtype=torch.int32, device="cuda")
+    ms = timed(lambda: ctx.estimate_intra_costs_dev(cur8, 8, d_ic), reps=10)
+    hic = np.zeros(nimp, np.uint32)
+    OLk = O.lib()
+    OLk.orc_estimate_intra_costs.restype = None
+    OLk.orc_estimate_intra_costs.argtypes = [C.c_void_p, C.c_ssize_t] + [C.c_int] * 4 + [C.c_void_p]
+    oc = oplanes["cur8"]
+    cpu = cpu_rate(lambda: OLk.orc_estimate_intra_costs(oc.at(0, 0), oc.stride, W, H, 1, 8, hic.ctypes.data), nimp)
+    emit("estimate_intra_costs (edges + DC + SATD 8x8, fused) 1080p 8-bit", nimp, "8x8 blocks", ms, 64 + 16 + 4, cpu=cpu)
+    d_imv = dev((rng.integers(-32, 33, (nimp, 2)) * 4).astype(np.int16))
+    d_scr, d_mean = torch.zeros(1, dtype=torch.int64, device="cuda"), torch.zeros(1, dtype=torch.float64, device="cuda")
+    ms = timed(lambda: ctx.estimate_inter_costs_dev(cur8, ref8, d_imv, d_ic, d_scr, d_mean), reps=10)
+    emit("estimate_inter_costs cost part (SATD 8x8 vs displaced reference + f64 mean) 1080p 8-bit", nimp, "8x8 blocks",
+         ms, 128 + 4 + 4)
+    ms = timed(lambda: ctx.importance_block_difference_dev(cur8, ref8, d_scr, d_mean), reps=10)
+    emit("estimate_importance_block_difference 1080p 8-bit", nimp, "8x8 blocks", ms, 128)
+
+    # ---- get_intra_edges for every 16x16 block of a frame x 13 modes, then the predictions from them
+    eitems = np.zeros(nb * 13, B.EDGE_ITEM_DTYPE)
+    eitems["po_x"], eitems["po_y"] = np.repeat(blocks["x"], 13), np.repeat(blocks["y"], 13)
+    eitems["part_x"], eitems["part_y"] = eitems["po_x"] // 4, eitems["po_y"] // 4
+    eitems["bsize"], eitems["tx_size"] = 6, 2                                  # BLOCK_16X16, TX_16X16
+    eitems["mode"] = np.tile([0, 2, 1, 9, 11, 10, 12, 3, 4, 5, 6, 7, 8], nb)   # RAV1E_INTRA_MODES
+    eitems["enable_ief"] = 1
+    d_ei = dev(eitems)
+    d_eb = torch.empty(len(eitems) * 257, dtype=torch.uint8, device="cuda")
+    d_el = torch.empty(len(eitems) * 2, dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: ctx.get_intra_edges_dev(cur8, (0, 0, W, H), 0, 0, 8, d_ei, len(eitems), d_eb, d_el), reps=10)
+    emit("get_intra_edges 16x16 x 13 modes 1080p 8-bit", len(eitems), "edge buffers", ms, 257 + 16 + 2,
+         "item + up to 65 plane pixels in, 257-pixel buffer + lengths out")
+
+    # ---- compute_rd_cost: 16 candidates per block, cost + first minimum
+    nrd = nb * 16
+    d_rate = dev(rng.integers(0, 1 << 16, nrd).astype(np.uint32))
+    d_dist = dev(rng.integers(0, 1 << 30, nrd).astype(np.uint64))
+    d_roffs = dev((np.arange(nb + 1) * 16).astype(np.uint32))
+    d_rc = torch.empty(nrd, dtype=torch.float64, device="cuda")
+    d_rb = torch.empty(nb, dtype=torch.int32, device="cuda")
+    ms = timed(lambda: ctx.compute_rd_cost_dev(117.25, d_rate, d_dist, nrd, d_rc, d_roffs, nb, d_rb), reps=10)
+    emit("compute_rd_cost (f64 fma) + first minimum per block, 16 candidates per block", nrd, "candidates", ms, 4 + 8 + 8)
+
     # ---- device-side search stages of full_pixel_me (me.rs:692-856), 1080p, 16x16 blocks.
     # Structured content (low-passed noise displaced by (+6, -3) px + noise) so the walks are real;
     # predictors scatter within +-8 px of the true motion like neighbouring blocks' vectors do.
@@ -235,6 +299,16 @@ def main():
                                                         hr.ctypes.data, he.ctypes.data, hd.ctypes.data, TH), nb)
     emit("quantize + dequantize + tx-dist 16x16 8-bit (noise residual: long scans)", nb, "blocks", ms,
          3 * 512 + 10, "coefficients in, qcoeffs + rcoeffs + eob + distortion out", cpu)
+
+    # ---- inverse transform + reconstruct, and encode_tx_block's numeric core in one call
+    rec = ctx.plane_from_host(np.zeros((H, W), np.uint8) + 128, 0)
+    ms = timed(lambda: ctx.inverse_transform_add_dev(d_r16, rec, d_blocks, nb, 2, 0, 8), reps=10)
+    emit("inverse_transform_add 16x16 DCT_DCT 8-bit", nb, "blocks", ms, 512 + 2 * 256, "rcoeffs in, plane read-modify-write")
+    d_co2 = torch.empty(nb * 256, dtype=torch.int16, device="cuda")
+    ms = timed(lambda: ctx.encode_tx_blocks_dev(cur8, ref8, rec, d_blocks, nb, None, 2, 0, 8, 120, 96, False, True,
+                                                d_co2, d_q16, d_r16, d_eob, d_txd), reps=10)
+    emit("encode_tx_blocks (diff + fwd txfm + quantize + dequantize + tx-dist + inverse add) 16x16 8-bit", nb, "blocks",
+         ms, 2 * 256 + 3 * 512 + 10 + 2 * 256, "")
 
     # ---- RDO distortion kernels on the 1080p 8-bit planes: every 16x16 block / every 8x8 block
     d_scale = dev(rng.integers(1 << 12, 1 << 16, ((H + 3) // 4, W // 4)).astype(np.uint32))

@@ -159,7 +159,8 @@ typedef struct {
  * d_pmv: NULL (both predictors zero) or 2 MotionVectors (row,col int16) per block.
  * d_cand_offsets: NULL, or nblocks+1 CSR offsets when cands are grouped by block in
  *   ascending block order — required for d_best (per-block first-minimum winner in list
- *   order, the serial scan's tie-break, me.rs:898,974).
+ *   order, the serial scan's tie-break, me.rs:898,974).  A block's list holds fewer than 2^24
+ *   candidates (the winner's index inside its block is packed into 24 bits).
  * Outputs (each may be NULL): d_sad[ncands], d_cost[ncands], d_best[nblocks].
  * Padding contract (the reference's, frame/mod.rs:22-23 + me.rs:339-362): candidates are accepted
  * up to get_mv_range's border, 16 + block size pixels outside the frame, so both planes must be
@@ -224,6 +225,19 @@ int b200_me_subpel_candidates_dev(b200_ctx *ctx, const b200_plane *cur, const b2
                                   const uint32_t *d_cand_offsets, const int16_t *d_pmv,
                                   const b200_me_params *params, int filter_mode, uint32_t *d_sad,
                                   uint64_t *d_cost, b200_me_result *d_best);
+
+/* Sub-pel refinement FUSED with the winner's residual and forward transform (BASELINE configs[3]): per
+ * block, every candidate of its list is predicted (8-tap `filter_mode`), measured (SAD / SATD + mv cost)
+ * and the first minimum kept, exactly like b200_me_subpel_candidates_dev; then the winner's prediction -
+ * still in shared memory - is subtracted from the source and run through the forward transform
+ * (tx_size / tx_type; block size = transform size; tx_size < 0: no transform), like
+ * b200_mc_blocks_dev + b200_fwd_txfm_pred_dev would, without any prediction touching HBM.
+ * 8x8, 16x16 and 32x32 blocks; d_cand_offsets required.  d_coeffs: nblocks x w*h (i16 for 8-bit planes,
+ * i32 for HBD); blocks whose candidates are all out of range get zeros. */
+int b200_subpel_rdo_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref, const b200_block *d_blocks,
+                        size_t nblocks, const b200_cand *d_cands, size_t ncands, const uint32_t *d_cand_offsets,
+                        const int16_t *d_pmv, const b200_me_params *params, int filter_mode, int tx_size,
+                        int tx_type, uint32_t *d_sad, uint64_t *d_cost, b200_me_result *d_best, void *d_coeffs);
 
 /* full_search (me.rs:1464-1509) as called from full_pixel_me (me.rs:822-846) for every
  * block: window po +- (range_x, range_y) px clamped to get_mv_range, positions every
@@ -539,6 +553,21 @@ int b200_cdef_filter_rect_dev(b200_ctx *ctx, const b200_plane *in, const b200_pl
                               int ydec, int luma_width, int luma_height, int bit_depth, int damping,
                               const uint8_t *d_skip8, const uint8_t *d_dir, const int32_t *d_var,
                               const uint8_t *d_strength_sb, int rx8, int ry8, int rw8, int rh8);
+
+/* Many (plane, tile) items per call - the tiles a rank owns across the frames of a batch - served by
+ * as few launches as possible (32 items per launch): with find_dir the directions / variances of every
+ * item's blocks are (re)computed from `in` (luma only), with filter every item's rect of `in` is
+ * filtered into `out`.  `items` is a HOST array; the arrays an item points to are frame-indexed. */
+typedef struct {
+  const b200_plane *in, *out; /* out may be NULL when only the directions are wanted */
+  const uint8_t *d_skip8;     /* may be NULL */
+  uint8_t *d_dir;
+  int32_t *d_var;
+  int32_t rx8, ry8, rw8, rh8; /* the tile in 8x8 luma blocks */
+} b200_cdef_item;
+int b200_cdef_tiles_dev(b200_ctx *ctx, const b200_cdef_item *items, size_t nitems, int plane, int xdec, int ydec,
+                        int luma_width, int luma_height, int bit_depth, int damping, const uint8_t *d_strength_sb,
+                        int find_dir, int filter);
 
 /* ------------------------------------------------------- intra prediction (predict.rs)
  * Boundary = rust::dispatch_predict_intra(mode, variant, dst, tx_size, bit_depth, ac, angle,

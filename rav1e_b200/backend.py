@@ -40,6 +40,12 @@ class MeParams(C.Structure):
                 ("bit_depth", C.c_int32), ("window_hint_px", C.c_int32)]
 
 
+class CdefItem(C.Structure):
+    _fields_ = [("inp", C.POINTER(Plane)), ("out", C.POINTER(Plane)), ("d_skip8", C.c_void_p),
+                ("d_dir", C.c_void_p), ("d_var", C.c_void_p), ("rx8", C.c_int32), ("ry8", C.c_int32),
+                ("rw8", C.c_int32), ("rh8", C.c_int32)]
+
+
 class FramePipeCfg(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("pad", C.c_int32), ("bpp", C.c_int32),
                 ("bit_depth", C.c_int32), ("block_w", C.c_int32), ("block_h", C.c_int32), ("lambda_", C.c_uint32),
@@ -146,6 +152,7 @@ def lib():
     L.b200_me_search_multi_dev.argtypes = [vp, sz, vp, vp, vp, vp, sz, vp, vp, i32, vp, vp, pmp, i32, vp]
     L.b200_me_candidates_multi_dev.argtypes = [vp, sz, vp, vp, vp, vp, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
     L.b200_me_subpel_candidates_dev.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, i32, vp, vp, vp]
+    L.b200_subpel_rdo_dev.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, i32, i32, i32, vp, vp, vp, vp]
     L.b200_me_full_search_dev.argtypes = [vp, pp, pp, vp, sz, pmp, i32, i32, i32, vp]
     L.b200_block_residual_dev.argtypes = [vp, pp, pp, vp, sz, vp, i32, i32, vp]
     L.b200_me_candidates_batch.argtypes = [vp, php, php, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
@@ -179,6 +186,7 @@ def lib():
     L.b200_cdef_filter_plane_dev.argtypes = [vp, pp, pp] + [i32] * 7 + [vp, vp, vp, vp]
     L.b200_cdef_find_dir_rect_dev.argtypes = [vp, pp, i32, vp, vp, vp] + [i32] * 4
     L.b200_cdef_filter_rect_dev.argtypes = [vp, pp, pp] + [i32] * 7 + [vp, vp, vp, vp] + [i32] * 4
+    L.b200_cdef_tiles_dev.argtypes = [vp, vp, sz] + [i32] * 7 + [vp, i32, i32]
     L.b200_predict_intra.argtypes = [i32, i32, vp, C.c_ssize_t, i32, i32, i32, vp, i32, i32, vp] + [i32] * 6
     L.b200_predict_intra.restype = None
     L.b200_predict_intra_dev.argtypes = [vp, vp, vp, sz, vp, i32, i32, i32, i32, i32, vp]
@@ -291,6 +299,13 @@ class Context:
             _dev_ptr(d_offsets), _dev_ptr(d_pmv), C.byref(params), filter_mode, _dev_ptr(d_sad),
             _dev_ptr(d_cost), _dev_ptr(d_best)))
 
+    def subpel_rdo_dev(self, cur, ref, d_blocks, nblocks, d_cands, ncands, d_offsets, params, filter_mode=0,
+                       tx_size=-1, tx_type=0, d_pmv=None, d_sad=None, d_cost=None, d_best=None, d_coeffs=None):
+        self.check(self.L.b200_subpel_rdo_dev(
+            self.h, C.byref(cur), C.byref(ref), _dev_ptr(d_blocks), nblocks, _dev_ptr(d_cands), ncands,
+            _dev_ptr(d_offsets), _dev_ptr(d_pmv), C.byref(params), filter_mode, tx_size, tx_type, _dev_ptr(d_sad),
+            _dev_ptr(d_cost), _dev_ptr(d_best), _dev_ptr(d_coeffs)))
+
     def me_full_search_dev(self, cur, ref, d_blocks, nblocks, params, range_x, range_y, step, d_best):
         self.check(self.L.b200_me_full_search_dev(
             self.h, C.byref(cur), C.byref(ref), _dev_ptr(d_blocks), nblocks, C.byref(params),
@@ -388,6 +403,13 @@ class Context:
         self.check(self.L.b200_cdef_filter_rect_dev(
             self.h, C.byref(inp), C.byref(out), plane, xdec, ydec, luma_w, luma_h, bit_depth, damping,
             _dev_ptr(d_skip8), _dev_ptr(d_dir), _dev_ptr(d_var), _dev_ptr(d_strength_sb), *rect8))
+
+    def cdef_tiles_dev(self, items, plane, xdec, ydec, luma_w, luma_h, bit_depth, damping, d_strength_sb,
+                       find_dir=True, filter=True):
+        """items: a ctypes array of CdefItem (keep the Plane objects it points to alive)."""
+        self.check(self.L.b200_cdef_tiles_dev(self.h, C.addressof(items), len(items), plane, xdec, ydec, luma_w,
+                                              luma_h, bit_depth, damping, _dev_ptr(d_strength_sb), int(find_dir),
+                                              int(filter)))
 
     # ---- intra prediction
     def predict_intra_dev(self, d_edges, d_items, n, d_ac, w, h, bit_depth, plane_w, plane_h, d_out):

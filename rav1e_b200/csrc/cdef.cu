@@ -83,19 +83,34 @@ __device__ int find_dir_8x8(const T *img, int stride, int coeff_shift, unsigned 
   return best;
 }
 
+// Up to kCdefMaxItems (plane, tile rect) items per launch: tiles of several frames share a grid
+// (blockIdx.z / the item table in the kernel parameters), so tile-sized launches are not all ramp.
+constexpr int kCdefMaxItems = 32;
+struct CdefItems {
+  int n;
+  const void *in[kCdefMaxItems];
+  void *out[kCdefMaxItems];
+  int in_stride[kCdefMaxItems], out_stride[kCdefMaxItems];
+  const uint8_t *skip8[kCdefMaxItems];
+  uint8_t *dir[kCdefMaxItems];
+  int *var[kCdefMaxItems];
+  short rx8[kCdefMaxItems], ry8[kCdefMaxItems], rw8[kCdefMaxItems], rh8[kCdefMaxItems];
+};
+
 template <typename T>
-__global__ void cdef_find_dir_kernel(const T *luma, int stride, int w8, int h8, int coeff_shift,
-                                     const uint8_t *skip8, uint8_t *dir, int *var, int rx8, int ry8, int rw8,
-                                     int rh8) {
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < rw8 * rh8; k += gridDim.x * blockDim.x) {
-    const int by = ry8 + k / rw8, bx = rx8 + k % rw8;
+__global__ void cdef_find_dir_kernel(const __grid_constant__ CdefItems it, int w8, int coeff_shift) {
+  const int k = blockIdx.y;
+  const T *luma = (const T *)it.in[k];
+  const int stride = it.in_stride[k], rw8 = it.rw8[k], rh8 = it.rh8[k];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rw8 * rh8; i += gridDim.x * blockDim.x) {
+    const int by = it.ry8[k] + i / rw8, bx = it.rx8[k] + i % rw8;
     const int b = by * w8 + bx;
     unsigned v = 0;
     int d = 0;
-    if (!(skip8 && skip8[b]))
+    if (!(it.skip8[k] && it.skip8[k][b]))
       d = find_dir_8x8<T>(luma + (long long)(8 * by) * stride + 8 * bx, stride, coeff_shift, &v);
-    dir[b] = (uint8_t)d;
-    var[b] = (int)v;
+    it.dir[k][b] = (uint8_t)d;
+    it.var[k][b] = (int)v;
   }
 }
 
@@ -159,16 +174,9 @@ __device__ __forceinline__ int cdef_pixel(Load load, int pri_strength, int sec_s
 }
 
 struct CdefPlaneArgs {
-  const void *in;
-  void *out;
-  int in_stride, out_stride;  // elements
   int plane, xdec, ydec;
-  int w8, h8, sbw;            // luma 8x8 grid and superblocks per row
-  int rx8, ry8, rw8, rh8;     // the part of the grid this launch filters (a tile), in 8x8 luma blocks
+  int w8, h8, sbw;  // luma 8x8 grid and superblocks per row
   int bit_depth, damping;
-  const uint8_t *skip8;
-  const uint8_t *dir;
-  const int *var;
   const uint8_t *strength_sb;
 };
 
@@ -185,21 +193,29 @@ struct CdefPlaneArgs {
 constexpr int kCdefTW = 64, kCdefTH = 16, kCdefPitch = 70;  // pitch: rows 35 words apart -> odd bank shift
 
 template <typename T>
-__global__ void __launch_bounds__(256) cdef_filter_kernel(const __grid_constant__ CdefPlaneArgs a) {
+__global__ void __launch_bounds__(256) cdef_filter_kernel(const __grid_constant__ CdefPlaneArgs a,
+                                                          const __grid_constant__ CdefItems it) {
   __shared__ short s_tile[(kCdefTH + 4) * kCdefPitch];
+  const int item = blockIdx.z;
+  const int rx8 = it.rx8[item], ry8 = it.ry8[item], rw8 = it.rw8[item], rh8 = it.rh8[item];
+  const int in_stride = it.in_stride[item], out_stride = it.out_stride[item];
+  const uint8_t *skip8 = it.skip8[item];
+  const uint8_t *dirs = it.dir[item];
+  const int *vars = it.var[item];
   const int xs_log2 = 3 - a.xdec, ys_log2 = 3 - a.ydec;
   const int pw = a.w8 << xs_log2, ph = a.h8 << ys_log2;
   const int coeff_shift = a.bit_depth - 8;
-  const T *in = (const T *)a.in;
-  T *out = (T *)a.out;
-  const int rx1 = (a.rx8 + a.rw8) << xs_log2, ry1 = (a.ry8 + a.rh8) << ys_log2;
-  const int tx0 = (a.rx8 << xs_log2) + blockIdx.x * kCdefTW, ty0 = (a.ry8 << ys_log2) + blockIdx.y * kCdefTH;
+  const T *in = (const T *)it.in[item];
+  T *out = (T *)it.out[item];
+  const int rx1 = (rx8 + rw8) << xs_log2, ry1 = (ry8 + rh8) << ys_log2;
+  const int tx0 = (rx8 << xs_log2) + blockIdx.x * kCdefTW, ty0 = (ry8 << ys_log2) + blockIdx.y * kCdefTH;
+  if (tx0 >= rx1 || ty0 >= ry1) return;  // the grid covers the largest item of the launch
   // ---- stage the tile + halo
   for (int i = threadIdx.x; i < (kCdefTH + 4) * (kCdefTW + 4); i += 256) {
     const int r = i / (kCdefTW + 4), c = i - r * (kCdefTW + 4);
     const int y = ty0 + r - 2, x = tx0 + c - 2;
     short v = (short)0x8000;
-    if (x >= 0 && x < pw && y >= 0 && y < ph) v = (short)in[(long long)y * a.in_stride + x];
+    if (x >= 0 && x < pw && y >= 0 && y < ph) v = (short)in[(long long)y * in_stride + x];
     s_tile[r * kCdefPitch + c] = v;
   }
   __syncthreads();
@@ -211,7 +227,7 @@ __global__ void __launch_bounds__(256) cdef_filter_kernel(const __grid_constant_
   const int b = gy * a.w8 + gx;
   const short *ctr = s_tile + (row + 2) * kCdefPitch + col + 2;
   int res[4];
-  if (a.skip8 && a.skip8[b]) {  // cdef.rs:557-564
+  if (skip8 && skip8[b]) {  // cdef.rs:557-564
 #pragma unroll
     for (int j = 0; j < 4; j++) res[j] = ctr[j];
   } else {
@@ -219,11 +235,11 @@ __global__ void __launch_bounds__(256) cdef_filter_kernel(const __grid_constant_
     const int pri = strength >> 2;
     int sec = strength & 3;
     if (sec == 3) sec = 4;  // cdef.rs:421-426
-    const int d = a.dir[b];
+    const int d = dirs[b];
     int local_pri, local_dir, local_damping = a.damping + coeff_shift;
     const int local_sec = sec << coeff_shift;
     if (a.plane == 0) {
-      local_pri = adjust_strength(pri << coeff_shift, a.var[b]);
+      local_pri = adjust_strength(pri << coeff_shift, vars[b]);
       local_dir = pri != 0 ? d : 0;
     } else {
       local_pri = pri << coeff_shift;
@@ -264,7 +280,7 @@ __global__ void __launch_bounds__(256) cdef_filter_kernel(const __grid_constant_
       res[j] = min(max(v, (int)mn), mx);
     }
   }
-  T *o = out + (long long)y * a.out_stride + x;
+  T *o = out + (long long)y * out_stride + x;
   if (x + 4 <= rx1 && ((uintptr_t)o & (4 * sizeof(T) - 1)) == 0) {
     if (sizeof(T) == 1)
       *(uchar4 *)o = make_uchar4((unsigned char)res[0], (unsigned char)res[1], (unsigned char)res[2], (unsigned char)res[3]);
@@ -293,67 +309,90 @@ __global__ void cdef_filter_tmp16_kernel(T *dst, int dst_stride, const uint16_t 
 
 namespace {
 
-int find_dir_rect(b200_ctx *ctx, const b200_plane *luma, int bit_depth, const uint8_t *d_skip8, uint8_t *d_dir,
-                  int32_t *d_var, int rx8, int ry8, int rw8, int rh8) {
-  B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
-  B200_REQUIRE(ctx, luma && luma->data && d_dir && d_var, "NULL argument");
-  B200_REQUIRE(ctx, (luma->width & 7) == 0 && (luma->height & 7) == 0,
-               "luma %dx%d must be a multiple of 8 (rav1e pads frames to 8)", luma->width, luma->height);
-  B200_REQUIRE(ctx, (luma->bpp == 1) == (bit_depth == 8), "bpp %d vs bit depth %d", luma->bpp, bit_depth);
-  const int w8 = luma->width >> 3, h8 = luma->height >> 3;
+int check_rect(b200_ctx *ctx, int w8, int h8, int rx8, int ry8, int rw8, int rh8) {
   B200_REQUIRE(ctx, rx8 >= 0 && ry8 >= 0 && rw8 > 0 && rh8 > 0 && rx8 + rw8 <= w8 && ry8 + rh8 <= h8,
                "block rect (%d, %d, %d, %d) outside the %d x %d grid", rx8, ry8, rw8, rh8, w8, h8);
-  B200_CUDA(ctx, cudaSetDevice(ctx->device));
-  const int grid = std::min((rw8 * rh8 + 127) / 128, ctx->num_sms * 16);
-  if (luma->bpp == 1)
-    cdef_find_dir_kernel<uint8_t><<<grid, 128, 0, ctx->stream>>>((const uint8_t *)luma->data, luma->stride, w8, h8,
-                                                                  bit_depth - 8, d_skip8, d_dir, d_var, rx8, ry8, rw8, rh8);
-  else
-    cdef_find_dir_kernel<uint16_t><<<grid, 128, 0, ctx->stream>>>((const uint16_t *)luma->data, luma->stride, w8, h8,
-                                                                   bit_depth - 8, d_skip8, d_dir, d_var, rx8, ry8, rw8, rh8);
-  B200_LAUNCH_CHECK(ctx);
   return B200_OK;
 }
 
-int filter_rect(b200_ctx *ctx, const b200_plane *in, const b200_plane *out, int plane, int xdec, int ydec,
-                int luma_width, int luma_height, int bit_depth, int damping, const uint8_t *d_skip8,
-                const uint8_t *d_dir, const int32_t *d_var, const uint8_t *d_strength_sb, int rx8, int ry8, int rw8,
-                int rh8) {
+// items [k0, k0 + n) of a host item array -> one launch of each requested kernel
+int cdef_launch(b200_ctx *ctx, const b200_cdef_item *items, int n, int plane, int xdec, int ydec, int luma_width,
+                int luma_height, int bit_depth, int damping, const uint8_t *d_strength_sb, int do_dir, int do_filter) {
+  CdefItems it{};
+  it.n = n;
+  int max_w8 = 0, max_h8 = 0, bpp = 0;
+  for (int k = 0; k < n; k++) {
+    const b200_cdef_item &q = items[k];
+    B200_REQUIRE(ctx, q.in && q.in->data && q.d_dir && q.d_var, "item %d: NULL plane / dir / var", k);
+    B200_REQUIRE(ctx, !do_filter || (q.out && q.out->data && q.out->data != q.in->data && q.out->bpp == q.in->bpp),
+                 "item %d: the filter needs a distinct output plane (taps read unfiltered neighbours)", k);
+    B200_REQUIRE(ctx, (q.in->bpp == 1) == (bit_depth == 8), "bpp %d vs bit depth %d", q.in->bpp, bit_depth);
+    if (int st = check_rect(ctx, luma_width >> 3, luma_height >> 3, q.rx8, q.ry8, q.rw8, q.rh8)) return st;
+    bpp = q.in->bpp;
+    it.in[k] = q.in->data;
+    it.in_stride[k] = q.in->stride;
+    it.out[k] = do_filter ? q.out->data : nullptr;
+    it.out_stride[k] = do_filter ? q.out->stride : 0;
+    it.skip8[k] = q.d_skip8;
+    it.dir[k] = q.d_dir;
+    it.var[k] = q.d_var;
+    it.rx8[k] = (short)q.rx8, it.ry8[k] = (short)q.ry8, it.rw8[k] = (short)q.rw8, it.rh8[k] = (short)q.rh8;
+    max_w8 = std::max(max_w8, q.rw8);
+    max_h8 = std::max(max_h8, q.rh8);
+  }
+  if (do_dir) {
+    B200_REQUIRE(ctx, plane == 0 && xdec == 0 && ydec == 0, "directions are searched on the luma plane");
+    const dim3 grid(std::max(1, std::min((max_w8 * max_h8 + 127) / 128, ctx->num_sms * 16 / n)), n);
+    if (bpp == 1)
+      cdef_find_dir_kernel<uint8_t><<<grid, 128, 0, ctx->stream>>>(it, luma_width >> 3, bit_depth - 8);
+    else
+      cdef_find_dir_kernel<uint16_t><<<grid, 128, 0, ctx->stream>>>(it, luma_width >> 3, bit_depth - 8);
+    B200_LAUNCH_CHECK(ctx);
+  }
+  if (do_filter) {
+    B200_REQUIRE(ctx, d_strength_sb, "NULL strengths");
+    CdefPlaneArgs a;
+    a.plane = plane;
+    a.xdec = xdec;
+    a.ydec = ydec;
+    a.w8 = luma_width >> 3;
+    a.h8 = luma_height >> 3;
+    a.sbw = (luma_width + 63) >> 6;
+    a.bit_depth = bit_depth;
+    a.damping = damping;
+    a.strength_sb = d_strength_sb;
+    const dim3 grid((((max_w8 * 8) >> xdec) + kCdefTW - 1) / kCdefTW, (((max_h8 * 8) >> ydec) + kCdefTH - 1) / kCdefTH, n);
+    if (bpp == 1)
+      cdef_filter_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(a, it);
+    else
+      cdef_filter_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(a, it);
+    B200_LAUNCH_CHECK(ctx);
+  }
+  return B200_OK;
+}
+
+int cdef_items(b200_ctx *ctx, const b200_cdef_item *items, size_t nitems, int plane, int xdec, int ydec,
+               int luma_width, int luma_height, int bit_depth, int damping, const uint8_t *d_strength_sb, int do_dir,
+               int do_filter) {
   B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
-  B200_REQUIRE(ctx, in && out && in->data && out->data && in->bpp == out->bpp, "bad planes");
-  B200_REQUIRE(ctx, in->data != out->data, "CDEF cannot run in place (taps read unfiltered neighbours)");
-  B200_REQUIRE(ctx, (luma_width & 7) == 0 && (luma_height & 7) == 0, "luma size must be a multiple of 8");
+  B200_REQUIRE(ctx, (luma_width & 7) == 0 && (luma_height & 7) == 0 && luma_width > 0 && luma_height > 0,
+               "luma %dx%d must be a multiple of 8 (rav1e pads frames to 8)", luma_width, luma_height);
   B200_REQUIRE(ctx, (xdec == 0 || xdec == 1) && (ydec == 0 || ydec == 1) && plane >= 0 && plane < 3, "bad plane");
-  B200_REQUIRE(ctx, (in->bpp == 1) == (bit_depth == 8), "bpp %d vs bit depth %d", in->bpp, bit_depth);
-  B200_REQUIRE(ctx, d_dir && d_var && d_strength_sb, "NULL dir/var/strength");
-  B200_REQUIRE(ctx, rx8 >= 0 && ry8 >= 0 && rw8 > 0 && rh8 > 0 && rx8 + rw8 <= (luma_width >> 3) &&
-                        ry8 + rh8 <= (luma_height >> 3),
-               "block rect (%d, %d, %d, %d) outside the grid", rx8, ry8, rw8, rh8);
+  B200_REQUIRE(ctx, bit_depth == 8 || bit_depth == 10 || bit_depth == 12, "bad bit depth %d", bit_depth);
+  if (nitems == 0) return B200_OK;
+  B200_REQUIRE(ctx, items != nullptr, "NULL items");
   B200_CUDA(ctx, cudaSetDevice(ctx->device));
-  CdefPlaneArgs a;
-  a.in = in->data;
-  a.out = out->data;
-  a.in_stride = in->stride;
-  a.out_stride = out->stride;
-  a.plane = plane;
-  a.xdec = xdec;
-  a.ydec = ydec;
-  a.w8 = luma_width >> 3;
-  a.h8 = luma_height >> 3;
-  a.sbw = (luma_width + 63) >> 6;
-  a.rx8 = rx8, a.ry8 = ry8, a.rw8 = rw8, a.rh8 = rh8;
-  a.bit_depth = bit_depth;
-  a.damping = damping;
-  a.skip8 = d_skip8;
-  a.dir = d_dir;
-  a.var = d_var;
-  a.strength_sb = d_strength_sb;
-  const dim3 grid((((rw8 * 8) >> xdec) + kCdefTW - 1) / kCdefTW, (((rh8 * 8) >> ydec) + kCdefTH - 1) / kCdefTH);
-  if (in->bpp == 1)
-    cdef_filter_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(a);
-  else
-    cdef_filter_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(a);
-  B200_LAUNCH_CHECK(ctx);
+  // all the directions first: a tile's filter reads only its own blocks' directions, but keeping the
+  // two phases apart lets one call serve callers that filter several planes from one analysis
+  for (int phase = 0; phase < 2; phase++) {
+    if (!(phase == 0 ? do_dir : do_filter)) continue;
+    for (size_t k0 = 0; k0 < nitems; k0 += kCdefMaxItems) {
+      const int n = (int)std::min<size_t>(kCdefMaxItems, nitems - k0);
+      if (int st = cdef_launch(ctx, items + k0, n, plane, xdec, ydec, luma_width, luma_height, bit_depth, damping,
+                               d_strength_sb, phase == 0, phase == 1))
+        return st;
+    }
+  }
   return B200_OK;
 }
 
@@ -362,13 +401,16 @@ int filter_rect(b200_ctx *ctx, const b200_plane *in, const b200_plane *out, int 
 extern "C" int b200_cdef_find_dir_dev(b200_ctx *ctx, const b200_plane *luma, int bit_depth,
                                       const uint8_t *d_skip8, uint8_t *d_dir, int32_t *d_var) {
   B200_REQUIRE(ctx, ctx != nullptr && luma != nullptr, "NULL argument");
-  return find_dir_rect(ctx, luma, bit_depth, d_skip8, d_dir, d_var, 0, 0, luma->width >> 3, luma->height >> 3);
+  const b200_cdef_item q{luma, nullptr, d_skip8, d_dir, d_var, 0, 0, luma->width >> 3, luma->height >> 3};
+  return cdef_items(ctx, &q, 1, 0, 0, 0, luma->width, luma->height, bit_depth, 0, nullptr, 1, 0);
 }
 
 extern "C" int b200_cdef_find_dir_rect_dev(b200_ctx *ctx, const b200_plane *luma, int bit_depth,
                                            const uint8_t *d_skip8, uint8_t *d_dir, int32_t *d_var, int rx8, int ry8,
                                            int rw8, int rh8) {
-  return find_dir_rect(ctx, luma, bit_depth, d_skip8, d_dir, d_var, rx8, ry8, rw8, rh8);
+  B200_REQUIRE(ctx, ctx != nullptr && luma != nullptr, "NULL argument");
+  const b200_cdef_item q{luma, nullptr, d_skip8, d_dir, d_var, rx8, ry8, rw8, rh8};
+  return cdef_items(ctx, &q, 1, 0, 0, 0, luma->width, luma->height, bit_depth, 0, nullptr, 1, 0);
 }
 
 extern "C" int b200_cdef_filter_plane_dev(b200_ctx *ctx, const b200_plane *in, const b200_plane *out,
@@ -376,8 +418,8 @@ extern "C" int b200_cdef_filter_plane_dev(b200_ctx *ctx, const b200_plane *in, c
                                           int luma_height, int bit_depth, int damping,
                                           const uint8_t *d_skip8, const uint8_t *d_dir,
                                           const int32_t *d_var, const uint8_t *d_strength_sb) {
-  return filter_rect(ctx, in, out, plane, xdec, ydec, luma_width, luma_height, bit_depth, damping, d_skip8, d_dir,
-                     d_var, d_strength_sb, 0, 0, luma_width >> 3, luma_height >> 3);
+  const b200_cdef_item q{in, out, d_skip8, (uint8_t *)d_dir, (int32_t *)d_var, 0, 0, luma_width >> 3, luma_height >> 3};
+  return cdef_items(ctx, &q, 1, plane, xdec, ydec, luma_width, luma_height, bit_depth, damping, d_strength_sb, 0, 1);
 }
 
 extern "C" int b200_cdef_filter_rect_dev(b200_ctx *ctx, const b200_plane *in, const b200_plane *out, int plane,
@@ -385,8 +427,15 @@ extern "C" int b200_cdef_filter_rect_dev(b200_ctx *ctx, const b200_plane *in, co
                                          int damping, const uint8_t *d_skip8, const uint8_t *d_dir,
                                          const int32_t *d_var, const uint8_t *d_strength_sb, int rx8, int ry8,
                                          int rw8, int rh8) {
-  return filter_rect(ctx, in, out, plane, xdec, ydec, luma_width, luma_height, bit_depth, damping, d_skip8, d_dir,
-                     d_var, d_strength_sb, rx8, ry8, rw8, rh8);
+  const b200_cdef_item q{in, out, d_skip8, (uint8_t *)d_dir, (int32_t *)d_var, rx8, ry8, rw8, rh8};
+  return cdef_items(ctx, &q, 1, plane, xdec, ydec, luma_width, luma_height, bit_depth, damping, d_strength_sb, 0, 1);
+}
+
+extern "C" int b200_cdef_tiles_dev(b200_ctx *ctx, const b200_cdef_item *items, size_t nitems, int plane, int xdec,
+                                   int ydec, int luma_width, int luma_height, int bit_depth, int damping,
+                                   const uint8_t *d_strength_sb, int find_dir, int filter) {
+  return cdef_items(ctx, items, nitems, plane, xdec, ydec, luma_width, luma_height, bit_depth, damping, d_strength_sb,
+                    find_dir, filter);
 }
 
 // ---- per-call forms with the reference's asm signatures (asm/x86/cdef.rs:16-37, :184-191)

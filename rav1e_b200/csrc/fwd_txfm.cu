@@ -9,50 +9,9 @@
 // are irregular lifting ladders with per-node constants, so a lane-per-coefficient layout
 // would diverge on every step, while a thread-per-vector layout needs no communication at all
 // inside a 1-D pass.
-#include "common.cuh"
-#include "txfm_networks.cuh"
+#include "fwd_txfm_dev.cuh"
 
 namespace {
-
-enum { T1_DCT = 0, T1_ADST = 1, T1_FLIPADST = 2, T1_IDTX = 3, T1_WHT = 4 };
-enum { TX_DCT_DCT = 0, TX_IDTX = 9, TX_WHT_WHT = 16 };
-
-// transform/mod.rs:101-123 (declaration order)
-const uint8_t kTxW[19] = {4, 8, 16, 32, 64, 4, 8, 8, 16, 16, 32, 32, 64, 4, 16, 8, 32, 16, 64};
-const uint8_t kTxH[19] = {4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16};
-// transform/mod.rs:364-402
-const uint8_t kVtx[17] = {T1_DCT, T1_ADST, T1_DCT, T1_ADST, T1_FLIPADST, T1_DCT, T1_FLIPADST,
-                          T1_ADST, T1_FLIPADST, T1_IDTX, T1_DCT, T1_IDTX, T1_ADST, T1_IDTX,
-                          T1_FLIPADST, T1_IDTX, T1_WHT};
-const uint8_t kHtx[17] = {T1_DCT, T1_DCT, T1_ADST, T1_ADST, T1_DCT, T1_FLIPADST, T1_FLIPADST,
-                          T1_FLIPADST, T1_ADST, T1_IDTX, T1_IDTX, T1_DCT, T1_IDTX, T1_ADST,
-                          T1_IDTX, T1_FLIPADST, T1_WHT};
-// forward_shared.rs:22-64, indexed [class][(bd-8)/2][stage]
-const int8_t kShift4x4[3][3] = {{3, 0, 0}, {2, 0, 1}, {0, 0, 3}};
-const int8_t kShiftA[3][3] = {{4, -1, 0}, {2, 0, 1}, {0, 0, 3}};    // 8x8,16x16,4x8,...,32x8
-const int8_t kShiftB[3][3] = {{4, -2, 0}, {2, 0, 0}, {0, 0, 2}};    // 32x32,16x32,32x16,16x64,64x16
-const int8_t kShiftC[3][3] = {{4, -1, -2}, {2, 0, -1}, {0, 0, 1}};  // 64x64,32x64,64x32
-const int8_t kShiftWht[3] = {0, 0, 2};
-// class per TxSize: 0 = 4x4, 1 = A, 2 = B, 3 = C
-const uint8_t kShiftClass[19] = {0, 1, 1, 2, 3, 1, 1, 1, 1, 2, 2, 3, 3, 1, 1, 1, 1, 2, 2};
-
-int size_index(int n) { return n == 4 ? 0 : n == 8 ? 1 : n == 16 ? 2 : n == 32 ? 3 : 4; }
-
-// mod.rs:405-417 plus the `.unwrap()`s of Txfm2DFlipCfg::fwd (forward_shared.rs:128-134)
-bool valid_transform(int tx_size, int tx_type) {
-  if (tx_size < 0 || tx_size >= 19 || tx_type < 0 || tx_type > 16) return false;
-  const int w = kTxW[tx_size], h = kTxH[tx_size], m = w > h ? w : h;
-  if (m == 64 && tx_type != TX_DCT_DCT) return false;
-  if (m == 32 && tx_type != TX_DCT_DCT && tx_type != TX_IDTX) return false;
-  const int t1[2] = {kVtx[tx_type], kHtx[tx_type]}, n[2] = {h, w};
-  for (int k = 0; k < 2; k++) {
-    const int idx = size_index(n[k]);
-    if (t1[k] == T1_WHT && idx != 0) return false;
-    if ((t1[k] == T1_ADST || t1[k] == T1_FLIPADST) && idx > 2) return false;
-    if (t1[k] == T1_IDTX && idx > 3) return false;
-  }
-  return true;
-}
 
 // Several (cur, ref) plane pairs per launch (see b200_me_candidates_multi_dev): pair k owns
 // blocks [block_end[k-1], block_end[k]) of the launch.
@@ -81,32 +40,6 @@ struct TxArgs {
   int ud_flip, lr_flip;
   int bit0, bit1, bit2;    // av1_round_shift_array `bit` = -shift[k]: >0 round-shift right, <0 left
 };
-
-// mod.rs:320-336
-__device__ __forceinline__ int round_shift_bit(int v, int bit) {
-  if (bit > 0) return (v + ((1 << bit) >> 1)) >> bit;
-  return (int)((unsigned)v << (-bit));
-}
-
-template <int N>
-__device__ __forceinline__ void run_1d(int type, TXV (&c)[N]) {
-  if (type == T1_IDTX) return;  // fidentity, forward_shared.rs:1775
-  if constexpr (N == 4) {
-    if (type == T1_DCT) tx_fdct4(c);
-    else if (type == T1_WHT) tx_fwht4(c);
-    else tx_fdst_vii_4(c);
-  } else if constexpr (N == 8) {
-    if (type == T1_DCT) tx_fdct8(c);
-    else tx_fdst8(c);
-  } else if constexpr (N == 16) {
-    if (type == T1_DCT) tx_fdct16(c);
-    else tx_fdst16(c);
-  } else if constexpr (N == 32) {
-    tx_fdct32(c);
-  } else {
-    tx_fdct64(c);
-  }
-}
 
 constexpr int kTxThreads = 128;
 
@@ -240,13 +173,7 @@ static int fwd_txfm_impl(b200_ctx *ctx, const b200_plane *cur, const b200_plane 
   B200_REQUIRE(ctx, cur || in_row_stride >= (size_t)w, "row stride %zu < width %d", in_row_stride, w);
   (void)h;
   B200_CUDA(ctx, cudaSetDevice(ctx->device));
-  const int8_t *sh;
-  if (tx_type == TX_WHT_WHT) {
-    sh = kShiftWht;
-  } else {
-    const int cls = kShiftClass[tx_size], b = (bd - 8) / 2;
-    sh = cls == 0 ? kShift4x4[b] : cls == 1 ? kShiftA[b] : cls == 2 ? kShiftB[b] : kShiftC[b];
-  }
+  const TxSetup ts = tx_setup(tx_size, tx_type, bd);
   TxArgs a;
   a.cur = cur ? cur->data : nullptr;
   a.ref = ref ? ref->data : nullptr;
@@ -264,13 +191,13 @@ static int fwd_txfm_impl(b200_ctx *ctx, const b200_plane *cur, const b200_plane 
   a.n = nblocks;
   a.in_block_stride = in_block_stride;
   a.in_row_stride = (int)in_row_stride;
-  a.col_type = kVtx[tx_type];
-  a.row_type = kHtx[tx_type];
-  a.ud_flip = a.col_type == T1_FLIPADST;  // forward_shared.rs:155-164
-  a.lr_flip = a.row_type == T1_FLIPADST;
-  a.bit0 = -sh[0];
-  a.bit1 = -sh[1];
-  a.bit2 = -sh[2];
+  a.col_type = ts.col_type;
+  a.row_type = ts.row_type;
+  a.ud_flip = ts.ud_flip;
+  a.lr_flip = ts.lr_flip;
+  a.bit0 = ts.bit0;
+  a.bit1 = ts.bit1;
+  a.bit2 = ts.bit2;
   switch (tx_size) {
 #define B200_TX(ID, W_, H_) \
   case ID:                  \

@@ -1884,8 +1884,9 @@ int me_candidates_pairs(b200_ctx *ctx, size_t npairs, const b200_plane *curs, co
 
   // Fast path: 8-bit, candidates grouped by block (CSR), block sizes up to 64x64; kMaxPairs plane
   // pairs per launch.
-  if (curs[0].bpp == 1 && d_cand_offsets && nblocks > 0 && fast_planes &&
-      ncands <= (1ull << kKeyIdxBits)) {
+  // (the packed argmin key holds a candidate's index INSIDE its block in kKeyIdxBits = 24 bits: a
+  // precondition on the lists - no block has 2^24 candidates - not on their total)
+  if (curs[0].bpp == 1 && d_cand_offsets && nblocks > 0 && fast_planes) {
     int (*launch)(b200_ctx *, MeArgs, int, const b200_plane *) = nullptr;
 #define B200_CASE(W_, H_)            \
   if (p->w == W_ && p->h == H_)      \

@@ -117,7 +117,9 @@ __device__ __forceinline__ uint32_t load_word(const uint8_t *p0, long long pitch
 template <typename T>
 __device__ __forceinline__ uint32_t word_sad(uint32_t a, uint32_t b, uint32_t acc) {
   if (sizeof(T) == 1) return sad4_acc(a, b, acc);
-  const uint32_t d = __vabsdiffu2(a, b);  // two u16 lanes, no carry between them
+  // |a - b| per u16 lane = max - min (VIMNMX.U16x2 twice; max >= min per lane, so the 32-bit subtraction
+  // never borrows across lanes) - __vabsdiffu2 expands to ten instructions on sm_100
+  const uint32_t d = __vmaxu2(a, b) - __vminu2(a, b);
   return acc + (d & 0xffffu) + (d >> 16);
 }
 

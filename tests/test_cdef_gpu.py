@@ -160,10 +160,27 @@ def test_tile_rects_equal_the_whole_frame():
         c.cdef_filter_rect_dev(src, tiled, 0, 0, 0, W, H, bd, 5, d_skip, d_dir2, d_var2, d_str, r8)
     c.synchronize()
     assert torch.equal(d_dir, d_dir2) and torch.equal(d_var, d_var2)
+    # the same tiles (twice over: 8 items) through the many-items entry point, one call
+    tiled2 = c.plane_from_host(np.zeros_like(luma), 0)
+    d_dir3, d_var3 = torch.zeros_like(d_dir), torch.zeros_like(d_var)
+    tl = shard.tile_grid(W, H, 1, 1)
+    items = (B.CdefItem * (2 * len(tl)))()
+    for k, (x, y, w, h) in enumerate(tl + tl):
+        it = items[k]
+        it.inp, it.out = C.pointer(src), C.pointer(tiled2)
+        it.d_skip8, it.d_dir, it.d_var = d_skip.data_ptr(), d_dir3.data_ptr(), d_var3.data_ptr()
+        it.rx8, it.ry8, it.rw8, it.rh8 = x // 8, y // 8, w // 8, h // 8
+    c.cdef_tiles_dev(items, 0, 0, 0, W, H, bd, 5, d_str)
+    c.synchronize()
+    assert torch.equal(d_dir, d_dir3) and torch.equal(d_var, d_var3)
+    t2 = np.zeros_like(luma)
     import ctypes
+    c.check(c.L.b200_plane_download(c.h, ctypes.byref(tiled2), t2.ctypes.data, t2.strides[0]))
+    c.plane_free(tiled2)
     a, b = np.zeros_like(luma), np.zeros_like(luma)
     c.check(c.L.b200_plane_download(c.h, ctypes.byref(whole), a.ctypes.data, a.strides[0]))
     c.check(c.L.b200_plane_download(c.h, ctypes.byref(tiled), b.ctypes.data, b.strides[0]))
     np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(a, t2)
     for p in (src, whole, tiled):
         c.plane_free(p)
