@@ -239,6 +239,18 @@ int b200_subpel_rdo_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *
                         const int16_t *d_pmv, const b200_me_params *params, int filter_mode, int tx_size,
                         int tx_type, uint32_t *d_sad, uint64_t *d_cost, b200_me_result *d_best, void *d_coeffs);
 
+/* subpel_diamond_search (me.rs:1311-1383) for every block, the move-to-best loop on the device: starting
+ * from d_start[i] (the full-pel stage's MotionSearchResult: vector, cost, sad - blocks whose start is the
+ * empty result are undefined upstream, `assert!(!current.is_empty())`), the four diamond points at 1/2 pel
+ * are evaluated with get_subpel_mv_rd (8-tap prediction + SAD / SATD + mv cost), the centre moves while a
+ * point is strictly better, then the radius halves down to 1/4 pel (1/8 with allow_high_precision_mv).
+ * d_best[i] = the final result (d_start may equal d_best); with tx_size >= 0 the final vector's prediction
+ * is subtracted from the source and transformed like b200_subpel_rdo_dev does.  Same block sizes. */
+int b200_subpel_search_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref, const b200_block *d_blocks,
+                           size_t nblocks, const b200_me_result *d_start, const int16_t *d_pmv,
+                           const b200_me_params *params, int filter_mode, int tx_size, int tx_type,
+                           b200_me_result *d_best, void *d_coeffs);
+
 /* full_search (me.rs:1464-1509) as called from full_pixel_me (me.rs:822-846) for every
  * block: window po +- (range_x, range_y) px clamped to get_mv_range, positions every
  * `step` px, pmv = 0, first-minimum winner in row-major scan order. */

@@ -417,3 +417,50 @@ void orc_full_pixel_me_blocks(const void *cur0, ptrdiff_t cur_stride, const void
     out[i] = best;
   }
 }
+
+/* subpel_diamond_search (me.rs:1311-1383) for every block: `current` starts as the caller's result
+ * (the full-pel stage's winner with its cost); radius 1/2 pel down to 1/4 pel (1/8 with
+ * allow_high_precision_mv); per radius the four DIAMOND_R1_PATTERN_SUBPEL candidates (me.rs:931-934:
+ * row+1, col+1, row-1, col-1 in that order, first minimum kept) are evaluated with get_subpel_mv_rd and
+ * the centre moves while a candidate is strictly better.  results: in / out, one per block. */
+void orc_subpel_diamond_search_blocks(const void *cur0, ptrdiff_t cur_stride, const void *ref0, ptrdiff_t ref_stride,
+                                      int bpp, int frame_w_in_b, int frame_h_in_b, const orc_block *blocks, size_t n,
+                                      int w, int h, int use_satd, uint32_t lambda, const orc_mv *pmv, int allow_hp,
+                                      int filter_mode, int bit_depth, orc_me_result *results, int threads) {
+  static const int8_t pat[4][2] = {{1, 0}, {0, 1}, {-1, 0}, {0, -1}}; /* {row, col} */
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : orc_num_threads())
+  for (ptrdiff_t i = 0; i < (ptrdiff_t)n; i++) {
+    orc_me_result cur = results[i];
+    int radius_log2 = 2;
+    const int end_log2 = allow_hp ? 0 : 1;
+    for (;;) {
+      orc_me_result best;
+      best.cost = UINT64_MAX;
+      best.sad = UINT32_MAX;
+      best.mv.row = best.mv.col = 0;
+      for (int k = 0; k < 4; k++) {
+        orc_cand c;
+        c.block = (uint32_t)i;
+        c.mv_row = (int16_t)(cur.mv.row + (int16_t)(pat[k][0] << radius_log2)); /* i16 wrapping add */
+        c.mv_col = (int16_t)(cur.mv.col + (int16_t)(pat[k][1] << radius_log2));
+        uint32_t sad;
+        uint64_t cost;
+        orc_subpel_candidates(cur0, cur_stride, ref0, ref_stride, bpp, frame_w_in_b, frame_h_in_b, blocks, &c, 1, w, h,
+                              use_satd, lambda, pmv, allow_hp, filter_mode, bit_depth, &sad, &cost, 1);
+        if (cost < best.cost) {
+          best.cost = cost;
+          best.sad = sad;
+          best.mv.row = c.mv_row;
+          best.mv.col = c.mv_col;
+        }
+      }
+      if (cur.cost <= best.cost) {
+        if (radius_log2 == end_log2) break;
+        radius_log2--;
+      } else {
+        cur = best;
+      }
+    }
+    results[i] = cur;
+  }
+}

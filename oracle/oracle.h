@@ -217,6 +217,11 @@ void orc_cdef_filter_plane(const void *in, ptrdiff_t in_stride, void *out, ptrdi
 
 int orc_num_threads(void);
 
+void orc_subpel_diamond_search_blocks(const void *cur0, ptrdiff_t cur_stride, const void *ref0, ptrdiff_t ref_stride,
+                                      int bpp, int frame_w_in_b, int frame_h_in_b, const orc_block *blocks, size_t n,
+                                      int w, int h, int use_satd, uint32_t lambda, const orc_mv *pmv, int allow_hp,
+                                      int filter_mode, int bit_depth, orc_me_result *results, int threads);
+
 /* ------------------------------------------- partition.rs / recon_intra.rs: intra edges */
 int orc_block_size_index(int w, int h);
 int orc_intra_avail_table(int kind, int bsize, uint8_t *out);

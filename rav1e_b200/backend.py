@@ -153,6 +153,7 @@ def lib():
     L.b200_me_candidates_multi_dev.argtypes = [vp, sz, vp, vp, vp, vp, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
     L.b200_me_subpel_candidates_dev.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, i32, vp, vp, vp]
     L.b200_subpel_rdo_dev.argtypes = [vp, pp, pp, vp, sz, vp, sz, vp, vp, pmp, i32, i32, i32, vp, vp, vp, vp]
+    L.b200_subpel_search_dev.argtypes = [vp, pp, pp, vp, sz, vp, vp, pmp, i32, i32, i32, vp, vp]
     L.b200_me_full_search_dev.argtypes = [vp, pp, pp, vp, sz, pmp, i32, i32, i32, vp]
     L.b200_block_residual_dev.argtypes = [vp, pp, pp, vp, sz, vp, i32, i32, vp]
     L.b200_me_candidates_batch.argtypes = [vp, php, php, vp, sz, vp, sz, vp, vp, pmp, vp, vp, vp]
@@ -305,6 +306,12 @@ class Context:
             self.h, C.byref(cur), C.byref(ref), _dev_ptr(d_blocks), nblocks, _dev_ptr(d_cands), ncands,
             _dev_ptr(d_offsets), _dev_ptr(d_pmv), C.byref(params), filter_mode, tx_size, tx_type, _dev_ptr(d_sad),
             _dev_ptr(d_cost), _dev_ptr(d_best), _dev_ptr(d_coeffs)))
+
+    def subpel_search_dev(self, cur, ref, d_blocks, nblocks, d_start, params, d_best, filter_mode=0, tx_size=-1,
+                          tx_type=0, d_pmv=None, d_coeffs=None):
+        self.check(self.L.b200_subpel_search_dev(
+            self.h, C.byref(cur), C.byref(ref), _dev_ptr(d_blocks), nblocks, _dev_ptr(d_start), _dev_ptr(d_pmv),
+            C.byref(params), filter_mode, tx_size, tx_type, _dev_ptr(d_best), _dev_ptr(d_coeffs)))
 
     def me_full_search_dev(self, cur, ref, d_blocks, nblocks, params, range_x, range_y, step, d_best):
         self.check(self.L.b200_me_full_search_dev(

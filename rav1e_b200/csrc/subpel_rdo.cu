@@ -37,6 +37,7 @@ struct SrdoArgs {
   const b200_cand *cands;
   const uint32_t *cand_offsets;
   const short *pmv;
+  const b200_me_result *start;  // non-NULL: subpel_diamond_search from this result instead of a list
   size_t nblocks;
   int w_in_b, h_in_b;
   uint32_t lambda;
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(256) subpel_rdo_kernel(const __grid_constant__
 
   for (size_t blk = (size_t)blockIdx.x * nw + wid; blk < a.nblocks; blk += (size_t)gridDim.x * nw) {
     const b200_block b = a.blocks[blk];
-    const uint32_t lo = a.cand_offsets[blk], hi = a.cand_offsets[blk + 1];
+    const uint32_t lo = a.start ? 0u : a.cand_offsets[blk], hi = a.start ? 0u : a.cand_offsets[blk + 1];
     const MvRange rng = b200_mv_range(a.w_in_b, a.h_in_b, b.x / MI_SIZE, b.y / MI_SIZE, W, H);
     int p0r = 0, p0c = 0, p1r = 0, p1c = 0;
     if (a.pmv) {
@@ -151,67 +152,104 @@ __global__ void __launch_bounds__(256) subpel_rdo_kernel(const __grid_constant__
     unsigned long long best_cost = kEmptyCost;
     uint32_t best_sad = kEmptySad;
     int best_row = 0, best_col = 0;
-    for (uint32_t i = lo; i < hi; i++) {
-      const b200_cand c = a.cands[i];
-      uint32_t sad = kEmptySad;
-      unsigned long long cost = kEmptyCost;
-      // get_subpel_mv_rd, me.rs:1420-1427
-      if (!(c.mv_col < rng.x_min || c.mv_col > rng.x_max || c.mv_row < rng.y_min || c.mv_row > rng.y_max)) {
-        // predict.rs:284-297 get_mv_params (luma)
-        const int y0 = b.y + (c.mv_row >> 3), x0 = b.x + (c.mv_col >> 3);
-        const int row_frac = (int)(((unsigned)c.mv_row << 1) & 0xf), col_frac = (int)(((unsigned)c.mv_col << 1) & 0xf);
-        const T *src = (const T *)a.ref + (long long)y0 * a.ref_stride + x0;
-        int xf[8], yf[8];
+    // get_subpel_mv_rd (me.rs:1411-1442) of one vector: prediction into `pcur`, distortion, cost
+    auto eval = [&](int mv_row, int mv_col, uint32_t &sad) -> unsigned long long {
+      sad = kEmptySad;
+      if (mv_col < rng.x_min || mv_col > rng.x_max || mv_row < rng.y_min || mv_row > rng.y_max) return kEmptyCost;
+      // predict.rs:284-297 get_mv_params (luma)
+      const int y0 = b.y + (mv_row >> 3), x0 = b.x + (mv_col >> 3);
+      const int row_frac = (int)(((unsigned)mv_row << 1) & 0xf), col_frac = (int)(((unsigned)mv_col << 1) & 0xf);
+      const T *src = (const T *)a.ref + (long long)y0 * a.ref_stride + x0;
+      int xf[8], yf[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-          xf[k] = kSubpel[xb][col_frac][k];
-          yf[k] = kSubpel[yb][row_frac][k];
+      for (int k = 0; k < 8; k++) {
+        xf[k] = kSubpel[xb][col_frac][k];
+        yf[k] = kSubpel[yb][row_frac][k];
+      }
+      __syncwarp();
+      for (int r = 0; r < TH; r++) {
+        const T *srow = src + (long long)(r - 3) * a.ref_stride - 3;
+        for (int cc = lane; cc < TW; cc += 32) tile[r * TW + cc] = srow[cc];
+      }
+      __syncwarp();
+      // put_8tap, mc.rs:250-353: the four cases
+      if (col_frac != 0 && row_frac != 0) {
+        for (int k = lane; k < TH * W; k += 32) {
+          const int r = k >> wlog2, cc = k & (W - 1);
+          int acc = 0;
+#pragma unroll
+          for (int t = 0; t < 8; t++) acc += xf[t] * (int)tile[r * TW + cc + t];
+          inter[k] = (short)rshift_round(acc, 7 - ib);  // `as i16`, mc.rs:323
         }
         __syncwarp();
-        for (int r = 0; r < TH; r++) {
-          const T *srow = src + (long long)(r - 3) * a.ref_stride - 3;
-          for (int cc = lane; cc < TW; cc += 32) tile[r * TW + cc] = srow[cc];
+        for (int k = lane; k < H * W; k += 32) {
+          int acc = 0;
+#pragma unroll
+          for (int t = 0; t < 8; t++) acc += yf[t] * (int)inter[k + t * W];
+          pcur[k] = (T)min(max(rshift_round(acc, 7 + ib), 0), maxv);
         }
-        __syncwarp();
-        // put_8tap, mc.rs:250-353: the four cases
-        if (col_frac != 0 && row_frac != 0) {
-          for (int k = lane; k < TH * W; k += 32) {
-            const int r = k >> wlog2, cc = k & (W - 1);
-            int s = 0;
+      } else {
+        for (int k = lane; k < H * W; k += 32) {
+          const int r = k >> wlog2, cc = k & (W - 1);
+          int v;
+          if (col_frac == 0 && row_frac == 0) {
+            v = (int)tile[(r + 3) * TW + cc + 3];
+          } else if (col_frac == 0) {  // V only, mc.rs:277-296
+            int acc = 0;
 #pragma unroll
-            for (int t = 0; t < 8; t++) s += xf[t] * (int)tile[r * TW + cc + t];
-            inter[k] = (short)rshift_round(s, 7 - ib);  // `as i16`, mc.rs:323
-          }
-          __syncwarp();
-          for (int k = lane; k < H * W; k += 32) {
-            int s = 0;
+            for (int t = 0; t < 8; t++) acc += yf[t] * (int)tile[(r + t) * TW + cc + 3];
+            v = min(max(rshift_round(acc, 7), 0), maxv);
+          } else {  // H only with its double rounding, mc.rs:297-311
+            int acc = 0;
 #pragma unroll
-            for (int t = 0; t < 8; t++) s += yf[t] * (int)inter[k + t * W];
-            pcur[k] = (T)min(max(rshift_round(s, 7 + ib), 0), maxv);
+            for (int t = 0; t < 8; t++) acc += xf[t] * (int)tile[(r + 3) * TW + cc + t];
+            v = min(max(rshift_round(rshift_round(acc, 7 - ib), ib), 0), maxv);
           }
+          pcur[k] = (T)v;
+        }
+      }
+      __syncwarp();
+      sad = a.use_satd ? warp_satd<T, W, H>(org, a.cur_stride, pcur, lane) : warp_sad<T, W, H>(org, a.cur_stride, pcur, lane);
+      return b200_mv_cost(sad, mv_row, mv_col, p0r, p0c, p1r, p1c, a.lambda, a.allow_hp);
+    };
+    if (a.start) {
+      // ---- subpel_diamond_search, me.rs:1311-1383: move to the best of the four diamond points while
+      // one is strictly better, then halve the radius (1/2 pel down to 1/4, or 1/8 with high precision)
+      const b200_me_result st = a.start[blk];
+      best_cost = st.cost, best_sad = st.sad, best_row = st.mv_row, best_col = st.mv_col;
+      int radius_log2 = 2;
+      const int end_log2 = a.allow_hp ? 0 : 1;
+      for (;;) {
+        unsigned long long cc = kEmptyCost;
+        uint32_t cs = kEmptySad;
+        int cr = 0, ccol = 0;
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) {  // DIAMOND_R1_PATTERN_SUBPEL, me.rs:931-934: row+1, col+1, row-1, col-1
+          const int dr = (k == 0) - (k == 2), dc = (k == 1) - (k == 3);
+          const int mr = (short)(best_row + (short)(dr << radius_log2)), mc = (short)(best_col + (short)(dc << radius_log2));
+          uint32_t sad;
+          const unsigned long long cost = eval(mr, mc, sad);
+          if (cost < cc) cc = cost, cs = sad, cr = mr, ccol = mc;
+        }
+        if (best_cost <= cc) {
+          if (radius_log2 == end_log2) break;
+          radius_log2--;
         } else {
-          for (int k = lane; k < H * W; k += 32) {
-            const int r = k >> wlog2, cc = k & (W - 1);
-            int v;
-            if (col_frac == 0 && row_frac == 0) {
-              v = (int)tile[(r + 3) * TW + cc + 3];
-            } else if (col_frac == 0) {  // V only, mc.rs:277-296
-              int s = 0;
-#pragma unroll
-              for (int t = 0; t < 8; t++) s += yf[t] * (int)tile[(r + t) * TW + cc + 3];
-              v = min(max(rshift_round(s, 7), 0), maxv);
-            } else {  // H only with its double rounding, mc.rs:297-311
-              int s = 0;
-#pragma unroll
-              for (int t = 0; t < 8; t++) s += xf[t] * (int)tile[(r + 3) * TW + cc + t];
-              v = min(max(rshift_round(rshift_round(s, 7 - ib), ib), 0), maxv);
-            }
-            pcur[k] = (T)v;
-          }
+          best_cost = cc, best_sad = cs, best_row = cr, best_col = ccol;
         }
-        __syncwarp();
-        sad = a.use_satd ? warp_satd<T, W, H>(org, a.cur_stride, pcur, lane) : warp_sad<T, W, H>(org, a.cur_stride, pcur, lane);
-        cost = b200_mv_cost(sad, c.mv_row, c.mv_col, p0r, p0c, p1r, p1c, a.lambda, a.allow_hp);
+      }
+      if (a.tx_on && best_cost != kEmptyCost) {  // the winner's prediction for the transform below
+        uint32_t sad;
+        (void)eval(best_row, best_col, sad);
+        T *t = pcur;
+        pcur = pbest;
+        pbest = t;
+      }
+    } else {
+      for (uint32_t i = lo; i < hi; i++) {
+        const b200_cand c = a.cands[i];
+        uint32_t sad;
+        const unsigned long long cost = eval(c.mv_row, c.mv_col, sad);
         if (cost < best_cost) {  // strict: the first minimum in list order wins (me.rs:1360-1365)
           best_cost = cost;
           best_sad = sad;
@@ -221,10 +259,10 @@ __global__ void __launch_bounds__(256) subpel_rdo_kernel(const __grid_constant__
           pcur = pbest;
           pbest = t;
         }
-      }
-      if (lane == 0) {
-        if (a.out_sad) a.out_sad[i] = sad;
-        if (a.out_cost) a.out_cost[i] = cost;
+        if (lane == 0) {
+          if (a.out_sad) a.out_sad[i] = sad;
+          if (a.out_cost) a.out_cost[i] = cost;
+        }
       }
     }
     if (lane == 0 && a.out_best) {
@@ -297,11 +335,11 @@ int launch_srdo(b200_ctx *ctx, SrdoArgs a) {
 
 }  // namespace
 
-extern "C" int b200_subpel_rdo_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
-                                   const b200_block *d_blocks, size_t nblocks, const b200_cand *d_cands,
-                                   size_t ncands, const uint32_t *d_cand_offsets, const int16_t *d_pmv,
-                                   const b200_me_params *p, int filter_mode, int tx_size, int tx_type,
-                                   uint32_t *d_sad, uint64_t *d_cost, b200_me_result *d_best, void *d_coeffs) {
+static int subpel_rdo_impl(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref, const b200_block *d_blocks,
+                           size_t nblocks, const b200_cand *d_cands, size_t ncands, const uint32_t *d_cand_offsets,
+                           const b200_me_result *d_start, const int16_t *d_pmv, const b200_me_params *p,
+                           int filter_mode, int tx_size, int tx_type, uint32_t *d_sad, uint64_t *d_cost,
+                           b200_me_result *d_best, void *d_coeffs) {
   B200_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
   B200_REQUIRE(ctx, cur && ref && p && cur->data && ref->data, "NULL plane / params");
   B200_REQUIRE(ctx, cur->bpp == ref->bpp && (cur->bpp == 1 || cur->bpp == 2), "planes must share bpp (1 or 2)");
@@ -311,12 +349,12 @@ extern "C" int b200_subpel_rdo_dev(b200_ctx *ctx, const b200_plane *cur, const b
                "fused sub-pel RDO serves 8x8, 16x16 and 32x32 blocks (got %dx%d): use "
                "b200_me_subpel_candidates_dev + b200_fwd_txfm_pred_dev for other sizes", p->w, p->h);
   B200_REQUIRE(ctx, filter_mode >= 0 && filter_mode <= 3, "bad FilterMode %d", filter_mode);
-  B200_REQUIRE(ctx, d_cand_offsets != nullptr, "candidates must be grouped by block (CSR d_cand_offsets)");
+  B200_REQUIRE(ctx, d_start != nullptr || d_cand_offsets != nullptr, "candidates must be grouped by block (CSR d_cand_offsets)");
   B200_REQUIRE(ctx, tx_size < 0 || (valid_transform(tx_size, tx_type) && kTxW[tx_size] == p->w && kTxH[tx_size] == p->h),
                "transform %d/%d does not match the %dx%d blocks", tx_size, tx_type, p->w, p->h);
   B200_REQUIRE(ctx, tx_size < 0 || d_coeffs, "transform requested without an output buffer");
   if (nblocks == 0) return B200_OK;
-  B200_REQUIRE(ctx, d_blocks && (d_cands || ncands == 0), "NULL blocks / candidates");
+  B200_REQUIRE(ctx, d_blocks && (d_start || d_cands || ncands == 0), "NULL blocks / candidates");
   B200_CUDA(ctx, cudaSetDevice(ctx->device));
   SrdoArgs a{};
   a.cur = cur->data, a.ref = ref->data;
@@ -324,6 +362,7 @@ extern "C" int b200_subpel_rdo_dev(b200_ctx *ctx, const b200_plane *cur, const b
   a.blocks = d_blocks;
   a.cands = d_cands;
   a.cand_offsets = d_cand_offsets;
+  a.start = d_start;
   a.pmv = d_pmv;
   a.nblocks = nblocks;
   a.w_in_b = p->frame_w_in_b, a.h_in_b = p->frame_h_in_b;
@@ -346,4 +385,23 @@ extern "C" int b200_subpel_rdo_dev(b200_ctx *ctx, const b200_plane *cur, const b
   B200_SRDO(32)
 #undef B200_SRDO
   return b200_fail(ctx, B200_ERR_ARG, "unreachable block size");
+}
+
+extern "C" int b200_subpel_rdo_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                                   const b200_block *d_blocks, size_t nblocks, const b200_cand *d_cands,
+                                   size_t ncands, const uint32_t *d_cand_offsets, const int16_t *d_pmv,
+                                   const b200_me_params *p, int filter_mode, int tx_size, int tx_type,
+                                   uint32_t *d_sad, uint64_t *d_cost, b200_me_result *d_best, void *d_coeffs) {
+  B200_REQUIRE(ctx, ctx != nullptr && d_cand_offsets != nullptr, "NULL ctx / candidates must be grouped by block (CSR)");
+  return subpel_rdo_impl(ctx, cur, ref, d_blocks, nblocks, d_cands, ncands, d_cand_offsets, nullptr, d_pmv, p,
+                         filter_mode, tx_size, tx_type, d_sad, d_cost, d_best, d_coeffs);
+}
+
+extern "C" int b200_subpel_search_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
+                                      const b200_block *d_blocks, size_t nblocks, const b200_me_result *d_start,
+                                      const int16_t *d_pmv, const b200_me_params *p, int filter_mode, int tx_size,
+                                      int tx_type, b200_me_result *d_best, void *d_coeffs) {
+  B200_REQUIRE(ctx, ctx != nullptr && d_start != nullptr && d_best != nullptr, "NULL ctx / start results / output");
+  return subpel_rdo_impl(ctx, cur, ref, d_blocks, nblocks, nullptr, 0, nullptr, d_start, d_pmv, p, filter_mode, tx_size,
+                         tx_type, nullptr, nullptr, d_best, d_coeffs);
 }
