@@ -353,6 +353,31 @@ def run_b200(args, rank, world, local_rank):
             ctx.me_full_search_dev(cur, ref, d_blocks, nb, p_fs, 192, 64, 4, d_fs)
     fs_only()
     ms_fs = timed(fs_only, max(2, args.steps // 2)) / (max(2, args.steps // 2) * FS_FRAMES)
+    # ---- extra leg (not part of `value`): BASELINE configs[3] - 1080p 10-bit speed-2 inter RDO, sub-pel
+    # MC + SATD + forward transform FUSED (b200_subpel_rdo_dev): per 16x16 block the 8 vectors of the
+    # sub-pel diamond at radius 4 and 2 around a full-pel centre -> put_8tap(REGULAR) -> SATD + cost ->
+    # first minimum -> residual -> DCT_DCT 16x16, one launch per frame pair, nothing but source pixels read
+    rng4 = np.random.default_rng(77 + rank)
+    img10 = [rng4.integers(0, 1024, (H, W)).astype(np.uint16) for _ in range(2)]
+    p10 = [ctx.plane_from_host(im, PAD) for im in img10]
+    pattern = np.array([(r * s_, c * s_) for s_ in (4, 2) for r, c in ((1, 0), (0, 1), (-1, 0), (0, -1))])
+    centre = rng4.integers(-16, 17, (nb, 2)) * 8
+    c4 = np.zeros(nb * 8, B.CAND_DTYPE)
+    c4["block"] = np.repeat(np.arange(nb, dtype=np.uint32), 8)
+    mv4 = (centre[:, None, :] + pattern[None]).reshape(-1, 2)
+    c4["mv_row"], c4["mv_col"] = mv4[:, 0], mv4[:, 1]
+    d_c4 = torch.from_numpy(c4.view(np.uint8)).cuda()
+    d_o4 = torch.from_numpy((np.arange(nb + 1, dtype=np.uint32) * 8).view(np.uint8)).cuda()
+    d_b4 = torch.empty(nb * 16, dtype=torch.uint8, device="cuda")
+    d_k4 = torch.empty(nb * 256, dtype=torch.int32, device="cuda")
+    p_c4 = B.me_params(BW, BH, W, H, LAMBDA, allow_hp=True, use_satd=True, bit_depth=10)
+
+    def cfg4_only():
+        ctx.subpel_rdo_dev(p10[0], p10[1], d_blocks, nb, d_c4, nb * 8, d_o4, p_c4, 0, 2, 0, None, None, None, d_b4, d_k4)
+    cfg4_only()
+    ms_c4 = timed(cfg4_only, max(2, args.steps // 2)) / max(2, args.steps // 2)
+    for pl in p10:
+        ctx.plane_free(pl)
     w_in_b, h_in_b = 2 * ((W + 7) >> 3), 2 * ((H + 7) >> 3)
     bx, by = blocks["x"].astype(np.int64), blocks["y"].astype(np.int64)
     mvx_min = np.maximum(-(bx // 4) * 32 - (128 + BW * 8), -(1 << 14) + 1)
@@ -404,12 +429,31 @@ def run_b200(args, rank, world, local_rank):
                            "what": "me_full_search (+-192 x +-64 px, step 4) for every 16x16 block of one frame; "
                                    "not part of `value` (speed 6 disables full search)",
                            "positions_per_launch": fs_positions, "launch_ms": ms_fs,
-                           "candidates_per_s": fs_positions / (ms_fs * 1e-3)}}},
+                           "candidates_per_s": fs_positions / (ms_fs * 1e-3)},
+                           "config3_subpel_fused_10bit": {
+                               "what": "BASELINE configs[3]: 1080p 10-bit, per 16x16 block 8 sub-pel vectors -> put_8tap(REGULAR) "
+                                       "-> SATD + cost -> first minimum -> residual -> DCT_DCT 16x16 in ONE kernel "
+                                       "(b200_subpel_rdo_dev); not part of `value`",
+                               "blocks_per_launch": nb, "candidates_per_launch": nb * 8, "launch_ms": ms_c4,
+                               "blocks_per_s": nb / (ms_c4 * 1e-3), "candidates_per_s": nb * 8 / (ms_c4 * 1e-3),
+                               "algorithmic_bytes_per_block": 8 * 23 * 23 * 2 + 256 * 2 + 256 * 4 + 16,
+                               "algorithmic_GBps": nb * (8 * 23 * 23 * 2 + 256 * 2 + 256 * 4 + 16) / (ms_c4 * 1e-3) / 1e9}}},
             "roofline": {"kernel": "me_cand_group_u8<16,16,SAD> (candidate-list SAD + cost + argmin)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "traffic_source": "static: ncu dram__bytes of the same 32-pair launch recorded in "
+                                           "profiles/traffic.json (not re-measured in this run)",
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "launch_ms": ms_sad},
+                         "launch_ms": ms_sad,
+                         # what actually binds this kernel (ncu: DRAM traffic is 0.08x the algorithmic bytes):
+                         # warp-instruction issue.  Floor per candidate in the cooperative loop: 1 LDS.128
+                         # (parameters) + 4 LDS.32 + 2 funnel shifts + 2 VABSDIFF4.ACC + 1 REDUX = 10.
+                         "issue_roof": {"floor_warp_instr_per_candidate": 10,
+                                        "peak_candidates_per_s": 148 * 4 * 1.965e9 / 10,
+                                        "achieved_candidates_per_s": n_sad * pairs_per_launch / (ms_sad * 1e-3),
+                                        "frac": n_sad * pairs_per_launch / (ms_sad * 1e-3) / (148 * 4 * 1.965e9 / 10),
+                                        "note": "148 SMs x 4 schedulers x 1 warp instruction per clock at 1965 MHz; "
+                                                "the measured kernel issues ~35 per candidate (profiles/NOTES_r1.md)"}},
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
         }
         print(json.dumps(out))

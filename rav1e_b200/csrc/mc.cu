@@ -9,7 +9,7 @@
 // get_mv_params (predict.rs:284-297), so one launch predicts thousands of blocks.
 #include <mutex>
 
-#include "mc_filters.cuh"
+#include "mc_dev.cuh"
 
 namespace {
 
@@ -146,6 +146,57 @@ __global__ void mc_avg_kernel(const short *t1, const short *t2, T *dst, size_t t
     dst[i] = (T)min(max(rshift_round((int)t1[i] + (int)t2[i] + bias, ib + 1), 0), maxv);
 }
 
+// `put` for the square sizes the RDO loop predicts most (8x8 .. 64x64): the packed-word path of
+// mc_dev.cuh (IDP.4A / IDP.2A, four outputs per task), one warp per block, predictions written
+// straight to their packed slots.
+template <typename T, int W, int H>
+__global__ void __launch_bounds__(256) mc_put_fast_kernel(McArgs a, int smem_per_warp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using ML = McLayout<T, W, H>;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  T *tile = (T *)(smem_raw + (size_t)wid * smem_per_warp);
+  short *inter = (short *)((unsigned char *)tile + ML::TILE_BYTES);
+  const int xb = filter_bank(a.mode_x, W), yb = filter_bank(a.mode_y, H);
+  for (size_t blk = (size_t)blockIdx.x * nw + wid; blk < a.n; blk += (size_t)gridDim.x * nw) {
+    b200_block b;
+    int mvr, mvc;
+    if (a.cands) {
+      const b200_cand c = a.cands[blk];
+      b = a.blocks[c.block];
+      mvr = c.mv_row, mvc = c.mv_col;
+    } else {
+      b = a.blocks[blk];
+      mvr = a.mvs ? a.mvs[2 * blk] : 0;
+      mvc = a.mvs ? a.mvs[2 * blk + 1] : 0;
+    }
+    // predict.rs:284-297 get_mv_params
+    const int y0 = b.y + (mvr >> (3 + a.ydec)), x0 = b.x + (mvc >> (3 + a.xdec));
+    const int row_frac = (int)(((unsigned)mvr << (1 - a.ydec)) & 0xf), col_frac = (int)(((unsigned)mvc << (1 - a.xdec)) & 0xf);
+    const T *src = (const T *)a.ref + (long long)(y0 - 3) * a.ref_stride + (x0 - 3);
+    __syncwarp();
+    mc_stage_tile<T, W, H>(tile, src, a.ref_stride, lane);
+    __syncwarp();
+    mc_put_warp<T, W, H>(tile, inter, (T *)a.out + blk * (size_t)(W * H), xb, col_frac, yb, row_frac, a.bit_depth, lane);
+  }
+}
+
+template <typename T, int N>
+int launch_mc_fast(b200_ctx *ctx, const McArgs &a) {
+  using ML = McLayout<T, N, N>;
+  const size_t per_warp = b200_align_up(ML::TILE_BYTES + ML::INTER_BYTES, 16);
+  const int wpc = (int)std::min<size_t>(8, std::max<size_t>(1, (128 * 1024) / per_warp));
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    err = cudaFuncSetAttribute(mc_put_fast_kernel<T, N, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  });
+  B200_CUDA(ctx, err);
+  const int grid = (int)std::min<size_t>((a.n + wpc - 1) / wpc, (size_t)ctx->num_sms * 16);
+  mc_put_fast_kernel<T, N, N><<<grid, wpc * 32, per_warp * wpc, ctx->stream>>>(a, (int)per_warp);
+  B200_LAUNCH_CHECK(ctx);
+  return B200_OK;
+}
+
 int check_mc(b200_ctx *ctx, int w, int h, int mode_x, int mode_y, int bit_depth) {
   // mc.rs:256-257: the asm only supports even heights and power-of-two widths 2..128
   B200_REQUIRE(ctx, (h & 1) == 0 && h > 0 && h <= 128, "height %d must be even and <= 128", h);
@@ -156,6 +207,15 @@ int check_mc(b200_ctx *ctx, int w, int h, int mode_x, int mode_y, int bit_depth)
 }
 
 int launch_mc(b200_ctx *ctx, const McArgs &a, int bpp) {
+  if (a.kind == 0 && !a.explicit_frac && a.w == a.h && !getenv("B200_MC_GENERIC")) {
+#define B200_MCF(N) \
+  if (a.w == N) return bpp == 1 ? launch_mc_fast<uint8_t, N>(ctx, a) : launch_mc_fast<uint16_t, N>(ctx, a);
+    B200_MCF(8)
+    B200_MCF(16)
+    B200_MCF(32)
+    B200_MCF(64)
+#undef B200_MCF
+  }
   const size_t tile_elems = (size_t)(a.w + 7) * (a.h + 7);
   const size_t per_warp = b200_align_up((tile_elems + (tile_elems & 1)) * bpp + (size_t)(a.h + 7) * a.w * 2, 16);
   // warps (= blocks in flight) per CTA: as many as fit ~96 KB, at most 8

@@ -1142,15 +1142,17 @@ __global__ void __launch_bounds__(256, SATD ? B200_WARP_SATD_MINBLOCKS : 1) me_c
 #ifndef B200_SATD_SPARSE_MINBLOCKS
 #define B200_SATD_SPARSE_MINBLOCKS 2
 #endif
-template <int W, int H>
+template <typename T, int W, int H>
 struct SatdSparseCfg {
+  static constexpr int BPP = (int)sizeof(T);
   static constexpr int CW = W / 8, CH = H / 8, NCH = CW * CH;
-  static constexpr int CPP = 32 / NCH;              // candidates per batch
-  static constexpr int NSEG = (W + 30) / 16;        // 16-byte segments covering W + 15 bytes
-  static constexpr int ROWW = NSEG * 4;             // words per staged row
-  static constexpr int CANDW0 = H * ROWW + 4 * CH;  // + one 16-byte pad per chunk row (bank spread)
+  static constexpr int CPP = 32 / NCH;                    // candidates per batch
+  static constexpr int NSEG = (W * BPP + 30) / 16;        // 16-byte segments covering a row + 15 bytes
+  static constexpr int ROWW = NSEG * 4;                   // words per staged row
+  static constexpr int CANDW0 = H * ROWW + 4 * CH;        // + one 16-byte pad per chunk row (bank spread)
   static constexpr int CANDW = CANDW0 + ((8 - CANDW0 % 32 + 32) % 32);  // == 8 (mod 32), 16-byte multiple
-  static constexpr int ORGW = NCH * 16;             // org words: [chunk][row][2]
+  static constexpr int CHW = 2 * BPP;                     // words of one chunk row (8 pixels)
+  static constexpr int ORGW = NCH * 8 * CHW;              // org words: [chunk][row][CHW]
   static constexpr int BUFW = CPP * CANDW + ORGW;   // one half of the double buffer
   static constexpr int WARP_WORDS = 2 * BUFW;
   static constexpr int WARPS = 8;
@@ -1174,10 +1176,11 @@ struct SatdLane {  // this lane's candidate of a batch and what staging derived 
   bool inr;  // in the block's mv range (evaluated and reported)
 };
 
-template <int W, int H>
+template <typename T, int W, int H, bool SATD>
 __global__ void __launch_bounds__(256, B200_SATD_SPARSE_MINBLOCKS)
-    me_satd_sparse_u8(const __grid_constant__ MeArgs a) {
-  using C = SatdSparseCfg<W, H>;
+    me_chunk_lists(const __grid_constant__ MeArgs a) {
+  using C = SatdSparseCfg<T, W, H>;
+  constexpr int BPP = C::BPP, CHW = C::CHW;
   constexpr int CW = C::CW, NCH = C::NCH, CPP = C::CPP, NSEG = C::NSEG, ROWW = C::ROWW, CANDW = C::CANDW,
                 BUFW = C::BUFW;
   extern __shared__ __align__(128) uint32_t smem[];
@@ -1238,7 +1241,7 @@ __global__ void __launch_bounds__(256, B200_SATD_SPARSE_MINBLOCKS)
                                      c.mv_row > r.y_max);
       // byte offset of the candidate's first pixel from pixel (0,0) of the reference plane (planes
       // are far smaller than 2 GB), split into its 16-byte aligned part and the misalignment
-      const int off = (h.b.y + c.mv_row / 8) * ref.stride + h.b.x + c.mv_col / 8;
+      const int off = ((h.b.y + c.mv_row / 8) * ref.stride + h.b.x + c.mv_col / 8) * BPP;
       L.mis = (int)(((uintptr_t)ref.data + (unsigned)off) & 15);
       const int segoff = L.inr ? off - L.mis : kNoCand;
       const uint32_t dst0 = wbuf_s + (uint32_t)(half * BUFW) * 4u;
@@ -1246,31 +1249,39 @@ __global__ void __launch_bounds__(256, B200_SATD_SPARSE_MINBLOCKS)
 #pragma unroll
       for (int k = 0; k < NSTEP; k++) {
         const int so = __shfl_sync(0xffffffffu, segoff, st_lane[k]);
-        if (so != kNoCand) cp_async16(dst0 + (uint32_t)st_dst[k], rbase + (so + st_row[k] * ref.stride + st_src[k]));
+        if (so != kNoCand) cp_async16(dst0 + (uint32_t)st_dst[k], rbase + (so + st_row[k] * ref.stride * BPP + st_src[k]));
       }
-      if (with_org) {  // org rows as [chunk][row][2 words]
-        const uint8_t *op = px<uint8_t>(cur, h.b.x, h.b.y);
+      if (with_org) {  // org rows as [chunk][row][8 pixels]
+        const uint8_t *op = (const uint8_t *)px<T>(cur, h.b.x, h.b.y);
         const uint32_t odst = dst0 + (uint32_t)(CPP * CANDW) * 4u;
-        const int al = (int)((uintptr_t)op | (uintptr_t)(unsigned)cur.stride) & 7;
+        const int al = (int)((uintptr_t)op | (uintptr_t)(unsigned)(cur.stride * BPP)) & (8 * BPP - 1);
 #pragma unroll
         for (int t0 = 0; t0 < NCH * 8; t0 += 32) {
           const int t = t0 + lane;  // unit t = (chunk, row): 8 pixels
           if ((NCH * 8) % 32 == 0 || t < NCH * 8) {
             const int ch = t >> 3, row = t & 7;
             const int ocy = ch / CW, ocx = ch - ocy * CW;
-            const uint8_t *q = op + (ocy * 8 + row) * cur.stride + ocx * 8;
+            const uint8_t *q = op + ((ocy * 8 + row) * cur.stride + ocx * 8) * BPP;
+            const uint32_t d = odst + (uint32_t)t * (8u * BPP);
             if (al == 0) {
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(odst + (uint32_t)t * 8u), "l"(q) : "memory");
+              if (BPP == 1)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(q) : "memory");
+              else
+                cp_async16(d, q);
             } else if ((al & 3) == 0) {
-              cp_async4(odst + (uint32_t)t * 8u, q);
-              cp_async4(odst + (uint32_t)t * 8u + 4u, q + 4);
-            } else {  // rare: byte-aligned blocks take the synchronous way
+#pragma unroll
+              for (int k = 0; k < CHW; k++) cp_async4(d + 4u * k, q + 4 * k);
+            } else {  // rare: blocks on odd byte addresses take the synchronous way
               const int osh = (int)((uintptr_t)q & 3);
               const uint32_t *qw = (const uint32_t *)(q - osh);
-              const uint32_t o0 = __ldg(qw), o1 = __ldg(qw + 1), o2 = __ldg(qw + 2);
-              uint32_t *d = wbuf + half * BUFW + CPP * CANDW + 2 * t;
-              d[0] = __funnelshift_r(o0, o1, osh * 8);
-              d[1] = __funnelshift_r(o1, o2, osh * 8);
+              uint32_t *dw = wbuf + half * BUFW + CPP * CANDW + CHW * t;
+              uint32_t lo = __ldg(qw);
+#pragma unroll
+              for (int k = 0; k < CHW; k++) {
+                const uint32_t hi = __ldg(qw + k + 1);
+                dw[k] = __funnelshift_r(lo, hi, osh * 8);
+                lo = hi;
+              }
             }
           }
         }
@@ -1282,49 +1293,128 @@ __global__ void __launch_bounds__(256, B200_SATD_SPARSE_MINBLOCKS)
   // evaluate this thread's chunk of its candidate from half `half`; every lane of a candidate
   // returns the candidate's SATD
   auto evaluate = [&](int half, int mis) -> uint32_t {
-    const int off = mis + cx * 8;
+    const int off = mis + cx * 8 * BPP;
     const uint32_t *rowp = wbuf + half * BUFW + myc * CANDW + (cy * 8) * ROWW + 4 * cy + (off >> 2);
-    const uint2 *orgp = (const uint2 *)(wbuf + half * BUFW + CPP * CANDW + chunk * 16);
+    const uint32_t *orgp = wbuf + half * BUFW + CPP * CANDW + chunk * 8 * CHW;
     const int sh = (off & 3) * 8;
-    int t[8][8];
+    uint32_t acc;
+    if constexpr (BPP == 1 && SATD) {
+      int t[8][8];
 #pragma unroll
-    for (int y = 0; y < 8; y++) {
-      const uint32_t w0 = rowp[y * ROWW], w1 = rowp[y * ROWW + 1], w2 = rowp[y * ROWW + 2];
-      const uint32_t q0 = __funnelshift_r(w0, w1, sh), q1 = __funnelshift_r(w1, w2, sh);
-      const uint2 o = orgp[y];
-      // t = H.org - H.ref for the row: Hadamard rows on the org bytes, negated ones on the
-      // reference bytes; outputs 4..7 take the second word of each with the opposite sign
-      t[y][0] = dp4a_us(q1, 0xFFFFFFFFu, dp4a_us(q0, 0xFFFFFFFFu, dp4a_us(o.y, 0x01010101u, dp4a_us(o.x, 0x01010101u, 0))));
-      t[y][1] = dp4a_us(q1, 0x01FF01FFu, dp4a_us(q0, 0x01FF01FFu, dp4a_us(o.y, 0xFF01FF01u, dp4a_us(o.x, 0xFF01FF01u, 0))));
-      t[y][2] = dp4a_us(q1, 0x0101FFFFu, dp4a_us(q0, 0x0101FFFFu, dp4a_us(o.y, 0xFFFF0101u, dp4a_us(o.x, 0xFFFF0101u, 0))));
-      t[y][3] = dp4a_us(q1, 0xFF0101FFu, dp4a_us(q0, 0xFF0101FFu, dp4a_us(o.y, 0x01FFFF01u, dp4a_us(o.x, 0x01FFFF01u, 0))));
-      t[y][4] = dp4a_us(q1, 0x01010101u, dp4a_us(q0, 0xFFFFFFFFu, dp4a_us(o.y, 0xFFFFFFFFu, dp4a_us(o.x, 0x01010101u, 0))));
-      t[y][5] = dp4a_us(q1, 0xFF01FF01u, dp4a_us(q0, 0x01FF01FFu, dp4a_us(o.y, 0x01FF01FFu, dp4a_us(o.x, 0xFF01FF01u, 0))));
-      t[y][6] = dp4a_us(q1, 0xFFFF0101u, dp4a_us(q0, 0x0101FFFFu, dp4a_us(o.y, 0x0101FFFFu, dp4a_us(o.x, 0xFFFF0101u, 0))));
-      t[y][7] = dp4a_us(q1, 0x01FFFF01u, dp4a_us(q0, 0xFF0101FFu, dp4a_us(o.y, 0xFF0101FFu, dp4a_us(o.x, 0x01FFFF01u, 0))));
+      for (int y = 0; y < 8; y++) {
+        const uint32_t w0 = rowp[y * ROWW], w1 = rowp[y * ROWW + 1], w2 = rowp[y * ROWW + 2];
+        const uint32_t q0 = __funnelshift_r(w0, w1, sh), q1 = __funnelshift_r(w1, w2, sh);
+        const uint2 o = ((const uint2 *)orgp)[y];
+        // t = H.org - H.ref for the row: Hadamard rows on the org bytes, negated ones on the
+        // reference bytes; outputs 4..7 take the second word of each with the opposite sign
+        t[y][0] = dp4a_us(q1, 0xFFFFFFFFu, dp4a_us(q0, 0xFFFFFFFFu, dp4a_us(o.y, 0x01010101u, dp4a_us(o.x, 0x01010101u, 0))));
+        t[y][1] = dp4a_us(q1, 0x01FF01FFu, dp4a_us(q0, 0x01FF01FFu, dp4a_us(o.y, 0xFF01FF01u, dp4a_us(o.x, 0xFF01FF01u, 0))));
+        t[y][2] = dp4a_us(q1, 0x0101FFFFu, dp4a_us(q0, 0x0101FFFFu, dp4a_us(o.y, 0xFFFF0101u, dp4a_us(o.x, 0xFFFF0101u, 0))));
+        t[y][3] = dp4a_us(q1, 0xFF0101FFu, dp4a_us(q0, 0xFF0101FFu, dp4a_us(o.y, 0x01FFFF01u, dp4a_us(o.x, 0x01FFFF01u, 0))));
+        t[y][4] = dp4a_us(q1, 0x01010101u, dp4a_us(q0, 0xFFFFFFFFu, dp4a_us(o.y, 0xFFFFFFFFu, dp4a_us(o.x, 0x01010101u, 0))));
+        t[y][5] = dp4a_us(q1, 0xFF01FF01u, dp4a_us(q0, 0x01FF01FFu, dp4a_us(o.y, 0x01FF01FFu, dp4a_us(o.x, 0xFF01FF01u, 0))));
+        t[y][6] = dp4a_us(q1, 0xFFFF0101u, dp4a_us(q0, 0x0101FFFFu, dp4a_us(o.y, 0x0101FFFFu, dp4a_us(o.x, 0xFFFF0101u, 0))));
+        t[y][7] = dp4a_us(q1, 0x01FFFF01u, dp4a_us(q0, 0xFF0101FFu, dp4a_us(o.y, 0xFF0101FFu, dp4a_us(o.x, 0x01FFFF01u, 0))));
+      }
+      uint32_t s = 0;
+#pragma unroll
+      for (int col = 0; col < 8; col++) {
+        int v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = t[k][col];
+        bfly(v[0], v[1]);
+        bfly(v[2], v[3]);
+        bfly(v[4], v[5]);
+        bfly(v[6], v[7]);
+        bfly(v[0], v[2]);
+        bfly(v[1], v[3]);
+        bfly(v[4], v[6]);
+        bfly(v[5], v[7]);
+        // last stage pairs (k, k + 4): |x + y| + |x - y| = 2 max(|x|, |y|)
+#pragma unroll
+        for (int k = 0; k < 4; k++) s += (uint32_t)max(abs(v[k]), abs(v[k + 4]));
+      }
+      acc = 2u * s;
+    } else if constexpr (SATD) {  // 16-bit pixels: differences unpacked, butterflies in both directions
+      int t[8][8];
+#pragma unroll
+      for (int y = 0; y < 8; y++) {
+        uint32_t w[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) w[k] = rowp[y * ROWW + k];
+        const uint4 o = ((const uint4 *)orgp)[y];
+        const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+        int d[8];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t r = __funnelshift_r(w[k], w[k + 1], sh);
+          d[2 * k] = (int)(ow[k] & 0xffffu) - (int)(r & 0xffffu);
+          d[2 * k + 1] = (int)(ow[k] >> 16) - (int)(r >> 16);
+        }
+        bfly(d[0], d[1]);
+        bfly(d[2], d[3]);
+        bfly(d[4], d[5]);
+        bfly(d[6], d[7]);
+        bfly(d[0], d[2]);
+        bfly(d[1], d[3]);
+        bfly(d[4], d[6]);
+        bfly(d[5], d[7]);
+        bfly(d[0], d[4]);
+        bfly(d[1], d[5]);
+        bfly(d[2], d[6]);
+        bfly(d[3], d[7]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) t[y][k] = d[k];
+      }
+      uint32_t s = 0;
+#pragma unroll
+      for (int col = 0; col < 8; col++) {
+        int v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = t[k][col];
+        bfly(v[0], v[1]);
+        bfly(v[2], v[3]);
+        bfly(v[4], v[5]);
+        bfly(v[6], v[7]);
+        bfly(v[0], v[2]);
+        bfly(v[1], v[3]);
+        bfly(v[4], v[6]);
+        bfly(v[5], v[7]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) s += (uint32_t)max(abs(v[k]), abs(v[k + 4]));
+      }
+      acc = 2u * s;
+    } else if constexpr (BPP == 1) {  // SAD, 8-bit: VABSDIFF4 with the accumulator fused
+      acc = 0;
+#pragma unroll
+      for (int y = 0; y < 8; y++) {
+        const uint32_t w0 = rowp[y * ROWW], w1 = rowp[y * ROWW + 1], w2 = rowp[y * ROWW + 2];
+        const uint2 o = ((const uint2 *)orgp)[y];
+        acc = sad4_acc(__funnelshift_r(w0, w1, sh), o.x, acc);
+        acc = sad4_acc(__funnelshift_r(w1, w2, sh), o.y, acc);
+      }
+    } else {  // SAD, 16-bit: |a - b| per u16 lane = max - min, lanes summed packed (8 rows x 4095 < 2^16)
+      uint32_t pk[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int y = 0; y < 8; y++) {
+        uint32_t w[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) w[k] = rowp[y * ROWW + k];
+        const uint4 o = ((const uint4 *)orgp)[y];
+        const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t r = __funnelshift_r(w[k], w[k + 1], sh);
+          pk[k] += __vmaxu2(ow[k], r) - __vminu2(ow[k], r);
+        }
+      }
+      acc = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) acc += (pk[k] & 0xffffu) + (pk[k] >> 16);
     }
-    uint32_t s = 0;
-#pragma unroll
-    for (int col = 0; col < 8; col++) {
-      int v[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) v[k] = t[k][col];
-      bfly(v[0], v[1]);
-      bfly(v[2], v[3]);
-      bfly(v[4], v[5]);
-      bfly(v[6], v[7]);
-      bfly(v[0], v[2]);
-      bfly(v[1], v[3]);
-      bfly(v[4], v[6]);
-      bfly(v[5], v[7]);
-      // last stage pairs (k, k + 4): |x + y| + |x - y| = 2 max(|x|, |y|)
-#pragma unroll
-      for (int k = 0; k < 4; k++) s += (uint32_t)max(abs(v[k]), abs(v[k + 4]));
-    }
-    uint32_t acc = 2u * s;
 #pragma unroll
     for (int o = NCH >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    return (acc + 4u) >> 3;  // dist.rs:219-220, single final rounding (8x8: ln = 3)
+    return SATD ? (acc + 4u) >> 3 : acc;  // dist.rs:219-220: one final rounding (8x8 chunks: ln = 3)
   };
 
   // ---- prologue: headers of blocks 0..2, records of 0..1, block 0 staged
@@ -1681,6 +1771,29 @@ bool tma_plane_map(const b200_plane &p, uint32_t bw, uint32_t bh, CUtensorMap *o
   return true;
 }
 
+// The staged chunk kernel needs 16-byte aligned reference rows (whole aligned segments are copied).
+bool chunk_lists_ok(const MeArgs &a) {
+  for (int k = 0; k < a.pr.n; k++)
+    if ((a.pr.ref[k].stride & 15) || ((uintptr_t)a.pr.ref[k].data & 15)) return false;
+  return true;
+}
+
+template <typename T, int W, int H, bool SATD>
+int launch_chunk_lists(b200_ctx *ctx, const MeArgs &a) {
+  using C = SatdSparseCfg<T, W, H>;
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    err = cudaFuncSetAttribute(me_chunk_lists<T, W, H, SATD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+  });
+  B200_CUDA(ctx, err);
+  const int wpc = C::WARPS;
+  const int grid = (int)std::min<size_t>((a.nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms * 16);
+  me_chunk_lists<T, W, H, SATD><<<grid, wpc * 32, C::SMEM, ctx->stream>>>(a);
+  B200_LAUNCH_CHECK(ctx);
+  return B200_OK;
+}
+
 template <int W, int H, bool SATD>
 int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px, const b200_plane *refs) {
   // opt in to the largest dynamic shared memory this kernel may be launched with, once
@@ -1704,23 +1817,7 @@ int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px, const b200_pl
       const int wpc = 8;
       if constexpr (SATD && W >= 8 && H >= 8 && (W / 8) * (H / 8) <= 32) {
         // 8x8-chunk SATD: footprints staged per warp with cp.async, thread per (candidate, chunk)
-        bool ref16 = true;  // 16-byte segments need 16-byte aligned rows
-        for (int k = 0; k < a.pr.n; k++)
-          ref16 = ref16 && (a.pr.ref[k].stride & 15) == 0 && ((uintptr_t)a.pr.ref[k].data & 15) == 0;
-        if (ref16 && !getenv("B200_OLD_SATD")) {
-          using C = SatdSparseCfg<W, H>;
-          static std::once_flag once;
-          static cudaError_t err = cudaSuccess;
-          std::call_once(once, [] {
-            err = cudaFuncSetAttribute(me_satd_sparse_u8<W, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)C::SMEM);
-          });
-          B200_CUDA(ctx, err);
-          const int grid = (int)std::min<size_t>((a.nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms * 16);
-          me_satd_sparse_u8<W, H><<<grid, wpc * 32, C::SMEM, ctx->stream>>>(a);
-          B200_LAUNCH_CHECK(ctx);
-          return B200_OK;
-        }
+        if (chunk_lists_ok(a) && !getenv("B200_OLD_SATD")) return launch_chunk_lists<uint8_t, W, H, true>(ctx, a);
       }
       const int grid = (int)std::min<size_t>((a.nblocks + wpc - 1) / wpc, (size_t)ctx->num_sms * 16);
       me_cand_warp_u8<W, H, SATD><<<grid, wpc * 32, 0, ctx->stream>>>(a);
@@ -1922,6 +2019,45 @@ int me_candidates_pairs(b200_ctx *ctx, size_t npairs, const b200_plane *curs, co
         if (int st = launch(ctx, a, p->window_hint_px, refs + k0)) return st;
       }
       return B200_OK;
+    }
+  }
+
+  // High bit depth: candidate lists grouped by block, block sides multiples of 8 (at most 32 8x8 chunks):
+  // the staged chunk kernel (16-bit lanes: max - min absolute differences, unpacked Hadamard).
+  // The reference's counterpart is its AVX2 HBD SAD / SATD (asm/x86/dist/mod.rs:96-182, satd16_avx2.asm).
+  if (curs[0].bpp == 2 && d_cand_offsets && nblocks > 0 && !getenv("B200_HBD_GENERIC")) {
+    int (*launch)(b200_ctx *, const MeArgs &) = nullptr;
+#define B200_CASE(W_, H_)       \
+  if (p->w == W_ && p->h == H_) \
+    launch = p->use_satd ? launch_chunk_lists<uint16_t, W_, H_, true> : launch_chunk_lists<uint16_t, W_, H_, false>;
+    B200_CASE(8, 8)
+    B200_CASE(16, 16)
+    B200_CASE(32, 32)
+    B200_CASE(8, 16)
+    B200_CASE(16, 8)
+    B200_CASE(16, 32)
+    B200_CASE(32, 16)
+#undef B200_CASE
+    if (launch) {
+      bool ok = true;
+      for (size_t k = 0; k < npairs; k++)
+        ok = ok && (refs[k].stride * 2 % 16 == 0) && ((uintptr_t)refs[k].data & 15) == 0 && (curs[k].stride & 1) == 0;
+      if (ok) {
+        for (size_t k0 = 0; k0 < npairs; k0 += kMaxPairs) {
+          const int n = (int)std::min<size_t>(kMaxPairs, npairs - k0);
+          a.pr.n = n;
+          a.pr.block_begin = k0 ? block_end[k0 - 1] : 0;
+          for (int k = 0; k < n; k++) {
+            a.pr.block_end[k] = block_end[k0 + k];
+            a.pr.cur[k] = {curs[k0 + k].data, curs[k0 + k].stride};
+            a.pr.ref[k] = {refs[k0 + k].data, refs[k0 + k].stride};
+          }
+          a.nblocks = a.pr.block_end[n - 1] - a.pr.block_begin;
+          if (a.nblocks == 0) continue;
+          if (int st = launch(ctx, a)) return st;
+        }
+        return B200_OK;
+      }
     }
   }
 

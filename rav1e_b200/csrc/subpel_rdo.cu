@@ -23,7 +23,7 @@
 #include <mutex>
 
 #include "fwd_txfm_dev.cuh"
-#include "mc_filters.cuh"
+#include "mc_dev.cuh"
 
 namespace {
 
@@ -124,19 +124,15 @@ template <typename T, int W, int H>
 __global__ void __launch_bounds__(256) subpel_rdo_kernel(const __grid_constant__ SrdoArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using CoefT = typename std::conditional<sizeof(T) == 1, int16_t, int32_t>::type;
-  constexpr int TW = W + 7, TH = H + 7;
-  constexpr int TILE_E = TH * TW + ((TH * TW) & 1);
+  using ML = McLayout<T, W, H>;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   unsigned char *base = smem_raw + (size_t)wid * a.smem_per_warp;
-  T *tile = (T *)base;                                  // [TH][TW] source footprint
-  short *inter = (short *)(tile + TILE_E);              // [TH][W] i16 intermediate
+  T *tile = (T *)base;                                  // [H+7][W+8] source footprint
+  short *inter = (short *)(base + ML::TILE_BYTES);      // [W][H+8] transposed i16 intermediate
   T *pred0 = (T *)(base + a.pred_off);                  // two W x H predictions: current / best so far
   T *pred1 = pred0 + W * H;
   int *txtile = (int *)base;                            // aliases tile + inter once the list is done
-  const int ib = 4 - (a.bit_depth == 12 ? 2 : 0);
-  const int maxv = (1 << a.bit_depth) - 1;
   const int xb = filter_bank(a.mode, W), yb = filter_bank(a.mode, H);
-  constexpr int wlog2 = W == 8 ? 3 : W == 16 ? 4 : 5;
 
   for (size_t blk = (size_t)blockIdx.x * nw + wid; blk < a.nblocks; blk += (size_t)gridDim.x * nw) {
     const b200_block b = a.blocks[blk];
@@ -159,55 +155,11 @@ __global__ void __launch_bounds__(256) subpel_rdo_kernel(const __grid_constant__
       // predict.rs:284-297 get_mv_params (luma)
       const int y0 = b.y + (mv_row >> 3), x0 = b.x + (mv_col >> 3);
       const int row_frac = (int)(((unsigned)mv_row << 1) & 0xf), col_frac = (int)(((unsigned)mv_col << 1) & 0xf);
-      const T *src = (const T *)a.ref + (long long)y0 * a.ref_stride + x0;
-      int xf[8], yf[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        xf[k] = kSubpel[xb][col_frac][k];
-        yf[k] = kSubpel[yb][row_frac][k];
-      }
+      const T *src = (const T *)a.ref + (long long)(y0 - 3) * a.ref_stride + (x0 - 3);
       __syncwarp();
-      for (int r = 0; r < TH; r++) {
-        const T *srow = src + (long long)(r - 3) * a.ref_stride - 3;
-        for (int cc = lane; cc < TW; cc += 32) tile[r * TW + cc] = srow[cc];
-      }
+      mc_stage_tile<T, W, H>(tile, src, a.ref_stride, lane);
       __syncwarp();
-      // put_8tap, mc.rs:250-353: the four cases
-      if (col_frac != 0 && row_frac != 0) {
-        for (int k = lane; k < TH * W; k += 32) {
-          const int r = k >> wlog2, cc = k & (W - 1);
-          int acc = 0;
-#pragma unroll
-          for (int t = 0; t < 8; t++) acc += xf[t] * (int)tile[r * TW + cc + t];
-          inter[k] = (short)rshift_round(acc, 7 - ib);  // `as i16`, mc.rs:323
-        }
-        __syncwarp();
-        for (int k = lane; k < H * W; k += 32) {
-          int acc = 0;
-#pragma unroll
-          for (int t = 0; t < 8; t++) acc += yf[t] * (int)inter[k + t * W];
-          pcur[k] = (T)min(max(rshift_round(acc, 7 + ib), 0), maxv);
-        }
-      } else {
-        for (int k = lane; k < H * W; k += 32) {
-          const int r = k >> wlog2, cc = k & (W - 1);
-          int v;
-          if (col_frac == 0 && row_frac == 0) {
-            v = (int)tile[(r + 3) * TW + cc + 3];
-          } else if (col_frac == 0) {  // V only, mc.rs:277-296
-            int acc = 0;
-#pragma unroll
-            for (int t = 0; t < 8; t++) acc += yf[t] * (int)tile[(r + t) * TW + cc + 3];
-            v = min(max(rshift_round(acc, 7), 0), maxv);
-          } else {  // H only with its double rounding, mc.rs:297-311
-            int acc = 0;
-#pragma unroll
-            for (int t = 0; t < 8; t++) acc += xf[t] * (int)tile[(r + 3) * TW + cc + t];
-            v = min(max(rshift_round(rshift_round(acc, 7 - ib), ib), 0), maxv);
-          }
-          pcur[k] = (T)v;
-        }
-      }
+      mc_put_warp<T, W, H>(tile, inter, pcur, xb, col_frac, yb, row_frac, a.bit_depth, lane);
       __syncwarp();
       sad = a.use_satd ? warp_satd<T, W, H>(org, a.cur_stride, pcur, lane) : warp_sad<T, W, H>(org, a.cur_stride, pcur, lane);
       return b200_mv_cost(sad, mv_row, mv_col, p0r, p0c, p1r, p1c, a.lambda, a.allow_hp);
@@ -310,9 +262,8 @@ __global__ void __launch_bounds__(256) subpel_rdo_kernel(const __grid_constant__
 
 template <typename T, int W, int H>
 int launch_srdo(b200_ctx *ctx, SrdoArgs a) {
-  constexpr int TW = W + 7, TH = H + 7;
-  constexpr size_t tile_e = TH * TW + ((TH * TW) & 1);
-  const size_t mc_bytes = tile_e * sizeof(T) + (size_t)TH * W * 2;
+  using ML = McLayout<T, W, H>;
+  const size_t mc_bytes = b200_align_up(ML::TILE_BYTES, 4) + ML::INTER_BYTES;
   const size_t tx_bytes = (size_t)H * (W + 1) * 4;  // aliases the MC buffers
   // the predictions sit behind whichever of the two is larger
   const size_t pred_off = b200_align_up(std::max(mc_bytes, tx_bytes), 16);

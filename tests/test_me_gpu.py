@@ -87,6 +87,14 @@ CAND_CASES = [
     (32, 64, np.uint8, 8, True, 2, 60),
     (64, 32, np.uint8, 8, True, 3, 70),
     (8, 8, np.uint8, 8, True, 1, 70),
+    # high bit depth through the staged chunk kernel (16-bit lanes), dense and sparse, SAD and SATD
+    (8, 8, np.uint16, 10, False, 40, 30),
+    (8, 8, np.uint16, 12, True, 3, 30),
+    (16, 16, np.uint16, 12, False, 70, 50),
+    (16, 32, np.uint16, 10, True, 6, 40),
+    (32, 32, np.uint16, 10, False, 9, 60),
+    (32, 32, np.uint16, 12, True, 2, 60),
+    (8, 16, np.uint16, 10, False, 12, 30),
 ]
 
 
