@@ -478,13 +478,15 @@ int b200_inverse_transform_add_dev(b200_ctx *ctx, const void *d_coeffs, const b2
                                    const b200_block *d_blocks, size_t nblocks, int tx_size, int tx_type,
                                    int bd);
 
-/* encode_tx_block's numeric core (encoder.rs:1492-1655) for nblocks transform blocks in one call:
- * residual against `ref` displaced by d_mv_src (NULL: zero motion) -> forward transform ->
- * quantize -> dequantize -> raw tx-domain distortion, and, when need_recon_pixel, the inverse
- * transform added into `rec` (which must already hold the prediction in the blocks' areas).
- * d_coeffs: nblocks x w*h scratch/outputs (i16, or i32 for HBD); d_qcoeffs, d_rcoeffs: nblocks x
- * b200_coded_tx_area(tx_size); d_eob / d_tx_dist may be NULL.  Entropy coding of d_qcoeffs and the
- * rate / bias terms stay with the caller. */
+/* encode_tx_block's numeric core (encoder.rs:1492-1655) for nblocks transform blocks in ONE kernel - the
+ * coefficients of a block stay in shared memory from the forward transform to the reconstruction:
+ * residual against `ref` displaced by d_mv_src (NULL: zero motion) -> forward transform -> quantize ->
+ * dequantize -> raw tx-domain distortion, and, when need_recon_pixel, the inverse transform added into
+ * `rec` (which must already hold the prediction in the blocks' areas).
+ * d_qcoeffs: nblocks x b200_coded_tx_area(tx_size) (required; i16, or i32 for HBD).  Optional outputs (each
+ * may be NULL): d_coeffs nblocks x w*h raw coefficients, d_rcoeffs dequantized ones (coded area), d_eob,
+ * d_tx_dist.  Entropy coding of d_qcoeffs and the rate / bias terms stay with the caller.  Results are
+ * identical to b200_fwd_txfm_residual_dev + b200_quantize_dev + b200_inverse_transform_add_dev. */
 int b200_encode_tx_blocks_dev(b200_ctx *ctx, const b200_plane *cur, const b200_plane *ref,
                               const b200_plane *rec, const b200_block *d_blocks, size_t nblocks,
                               const b200_me_result *d_mv_src, int tx_size, int tx_type, int bd,

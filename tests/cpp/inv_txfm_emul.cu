@@ -35,7 +35,7 @@ void emulate(const InvArgs &a) {
 extern "C" int emul_inverse_transform_add(const void *coeffs, void *dst, int dst_stride, int bpp,
                                           const b200_block *blocks, size_t n, int tx_size, int tx_type,
                                           int bd) {
-  const int w = kTxW[tx_size], h = kTxH[tx_size];
+  const int w = kItxW[tx_size], h = kItxH[tx_size];
   if (!inv_1d_exists(kTx1D[tx_type][1], w) || !inv_1d_exists(kTx1D[tx_type][0], h)) return -1;
   InvArgs a{};
   a.coeffs = coeffs;

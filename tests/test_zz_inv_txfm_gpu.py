@@ -98,30 +98,51 @@ def test_encode_tx_block_chain_on_device():
         c.plane_free(pl)
 
 
-def test_encode_tx_blocks_one_call_equals_the_three_steps():
-    """b200_encode_tx_blocks_dev == b200_fwd_txfm_residual_dev + b200_quantize_dev +
-    b200_inverse_transform_add_dev called one after the other."""
+@pytest.mark.parametrize("ts,tt,bd", [(2, 0, 8), (1, 3, 8), (0, 1, 8), (3, 0, 10), (4, 0, 8), (9, 0, 8), (13, 1, 10),
+                                      (5, 9, 8), (16, 10, 12), (11, 0, 10)])
+def test_encode_tx_blocks_one_call_equals_the_three_steps(ts, tt, bd):
+    """the fused kernel (b200_encode_tx_blocks_dev: coefficients stay on the SM) == b200_fwd_txfm_residual_dev +
+    b200_quantize_dev + b200_inverse_transform_add_dev called one after the other, every output, with
+    motion-displaced predictions."""
     import torch
     c = G.ctx()
-    W, H, PAD = 192, 128, 64
-    cur, ref = G.make_planes(W, H, PAD, np.uint8, seed=44)
+    W, H, PAD = 256, 192, 64
+    dtype = np.uint8 if bd == 8 else np.uint16
+    cur, ref = G.make_planes(W, H, PAD, dtype, seed=44 + ts, bit_depth=bd)
     _, dcur = G.both_planes(cur, PAD)
     _, dref = G.both_planes(ref, PAD)
-    blocks = G.grid_blocks(W, H, 16, 16)
+    w, h = O.TX_SIZES[ts]
+    blocks = G.grid_blocks(W, H, w, h)
     n = len(blocks)
     d_blocks = G.to_dev(blocks)
-    mk = lambda: torch.empty((n, 256), dtype=torch.int16, device="cuda")
-    co1, q1, r1, co2, q2, r2 = mk(), mk(), mk(), mk(), mk(), mk()
+    rng = np.random.default_rng(ts)
+    mv = np.zeros(n, B.ME_RESULT_DTYPE)
+    mv["cost"] = 1
+    mv["cost"][::7] = np.uint64(2**64 - 1)                  # empty results: zero motion
+    mv["mv_row"], mv["mv_col"] = rng.integers(-5, 6, n) * 8, rng.integers(-5, 6, n) * 8
+    d_mv = G.to_dev(mv)
+    ct = torch.int16 if bd == 8 else torch.int32
+    coded = c.L.b200_coded_tx_area(ts)
+    mk = lambda k: torch.empty((n, k), dtype=ct, device="cuda")
+    co1, q1, r1, co2, q2, r2 = mk(w * h), mk(coded), mk(coded), mk(w * h), mk(coded), mk(coded)
     e1, e2 = (torch.zeros(n, dtype=torch.int16, device="cuda") for _ in range(2))
     d1, d2 = (torch.zeros(n, dtype=torch.int64, device="cuda") for _ in range(2))
     rec1, rec2 = c.plane_from_host(ref, 0), c.plane_from_host(ref, 0)
-    c.fwd_txfm_residual_dev(dcur, dref, d_blocks, n, None, co1, 2, 0, 8)
-    c.quantize_dev(co1, n, 2, 0, 70, 60, False, False, q1, r1, e1, d1)
-    c.inverse_transform_add_dev(r1, rec1, d_blocks, n, 2, 0, 8)
-    c.encode_tx_blocks_dev(dcur, dref, rec2, d_blocks, n, None, 2, 0, 8, 70, 60, False, True, co2, q2, r2, e2, d2)
+    dcq, acq = 70 << (bd - 8), 60 << (bd - 8)
+    c.fwd_txfm_residual_dev(dcur, dref, d_blocks, n, d_mv, co1, ts, tt, bd)
+    c.quantize_dev(co1, n, ts, tt, dcq, acq, False, bd > 8, q1, r1, e1, d1)
+    c.inverse_transform_add_dev(r1, rec1, d_blocks, n, ts, tt, bd)
+    c.encode_tx_blocks_dev(dcur, dref, rec2, d_blocks, n, d_mv, ts, tt, bd, dcq, acq, False, True, co2, q2, r2, e2, d2)
     c.synchronize()
     for a, b in ((co1, co2), (q1, q2), (r1, r2), (e1, e2), (d1, d2)):
         assert torch.equal(a, b)
     np.testing.assert_array_equal(download(c, rec1, ref), download(c, rec2, ref))
-    for pl in (dcur, dref, rec1, rec2):
+    # optional outputs left out: nothing else changes
+    q3 = mk(coded)
+    rec3 = c.plane_from_host(ref, 0)
+    c.encode_tx_blocks_dev(dcur, dref, rec3, d_blocks, n, d_mv, ts, tt, bd, dcq, acq, False, True, None, q3, None, None, None)
+    c.synchronize()
+    assert torch.equal(q3, q1)
+    np.testing.assert_array_equal(download(c, rec3, ref), download(c, rec1, ref))
+    for pl in (dcur, dref, rec1, rec2, rec3):
         c.plane_free(pl)
