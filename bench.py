@@ -717,7 +717,9 @@ def run_e2e(ctx0, blocks, args, world=1, dist=None):
     from rav1e_b200 import backend as B
     nb = len(blocks)
     NCTX = int(os.environ.get("B200_E2E_CONTEXTS", "4"))
-    Fe = 4 * NCTX
+    # frames per step: the contexts run dry at every step boundary (the clock stops on a full
+    # synchronisation), so a step holds enough frames per context for the pipeline to be mostly full
+    Fe = int(os.environ.get("B200_E2E_FRAMES_PER_CTX", "8")) * NCTX
     pinned = lambda n, dt=np.uint8: torch.empty(n, dtype=torch.uint8).pin_memory().numpy().view(dt)
     ctxs = [B.Context(ctx0.device) for _ in range(NCTX)]
     pipes = []
@@ -803,12 +805,37 @@ def run_e2e(ctx0, blocks, args, world=1, dist=None):
         torch.cuda.synchronize()
         return 4 * big.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9
     h2d_gbs, d2h_gbs = link(dbig, big), link(big, dbig)
+
+    def link_bidir():
+        """both directions at once, in the e2e's own proportion of bytes (what the pipes ask of the link)"""
+        big2 = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+        dbig2 = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        n_up = 192 << 20
+        n_dn = min(int(n_up * (d2h / max(h2d, 1))), 256 << 20)
+        su, sd = torch.cuda.Stream(), torch.cuda.Stream()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        with torch.cuda.stream(su):
+            ev[0].record()
+            for _ in range(4):
+                dbig[:n_up].copy_(big[:n_up], non_blocking=True)
+            ev[1].record()
+        with torch.cuda.stream(sd):
+            ev[2].record()
+            for _ in range(4):
+                big2[:n_dn].copy_(dbig2[:n_dn], non_blocking=True)
+            ev[3].record()
+        torch.cuda.synchronize()
+        return (4 * n_up / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9, 4 * n_dn / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9)
+    h2d_bi, d2h_bi = link_bidir()
     del big, dbig
     res = {"value": units * reps / dt_job, "unit": "blocks/s", "h2d_bytes_per_step": int(h2d) * world,
            "d2h_bytes_per_step": int(d2h) * world, "frames_per_step": Fe * world,
            "kernel_launches_per_step": launches // reps * world,
            "h2d_GBps_achieved": h2d * reps / dt / 1e9, "d2h_GBps_achieved": d2h * reps / dt / 1e9,
-           "h2d_GBps_link_measured": h2d_gbs, "d2h_GBps_link_measured": d2h_gbs, "ranks": world,
+           "h2d_GBps_link_measured": h2d_gbs, "d2h_GBps_link_measured": d2h_gbs,
+           "h2d_GBps_link_bidirectional": h2d_bi, "d2h_GBps_link_bidirectional": d2h_bi,
+           "link_frac": max(h2d * reps / dt / 1e9 / h2d_bi, d2h * reps / dt / 1e9 / d2h_bi), "ranks": world,
            "workload": "1080p-8bit-speed6-me16x16 frames, one stream of frames per rank (per-GPU work fixed)",
            "api": "per frame: ONE b200_frame_pipe_push (frame uploaded once - the previous frame is the reference; "
                   "candidate lists as 2-byte full-pel offsets; SAD winners -> residual + 16x16 DCT on the device; "

@@ -30,6 +30,9 @@
 #ifndef B200_SAD_THREADS
 #define B200_SAD_THREADS 256  // CTA size of the SAD instantiations of the grouped kernel
 #endif
+#ifndef B200_SAD_GROUP_DEFAULT
+#define B200_SAD_GROUP_DEFAULT 8  // blocks per group of the cooperative SAD kernel (measured: profiles/NOTES_r2.md)
+#endif
 #ifndef B200_SAD16_MINBLOCKS
 // Resident CTAs per SM the 16x16 SAD kernel is register-capped for: 4 (64 registers, no spills)
 // measured 0.850 ms per 32-pair launch against 0.931 ms at 5 (48 registers, 66 B of spills).
@@ -499,7 +502,7 @@ __device__ __forceinline__ uint32_t chunk_satd_u8(const uint32_t *wrow, int pitc
 }
 
 constexpr int kCandSmemBytes = 160 * 1024;  // upper bound of the dynamic smem (window + org)
-constexpr int kMaxGroup = 8;                // blocks sharing one staged window
+constexpr int kMaxGroup = 16;               // blocks sharing one staged window
 constexpr int kKeyIdxBits = 24;             // packed argmin key: cost << 24 | index in block
 
 // cost < 2^39 always (256*sad <= 2^34 for 128x128x12 bit, rate <= 61, lambda < 2^32), so
@@ -548,22 +551,25 @@ __global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 
   const bool tma_on = COOP && tm.enabled;
   const uint32_t mbar = smem_u32(&s_mbar);
   uint32_t tma_parity = 0;
-  if (tma_on) {
-    if (threadIdx.x == 0) mbar_init(mbar, 1);
-    __syncthreads();
-  }
+  __shared__ uint32_t s_gend[kMaxPairs];
+  if (threadIdx.x < a.pr.n) s_gend[threadIdx.x] = a.pr.group_end[threadIdx.x];
+  if (tma_on && threadIdx.x == 0) mbar_init(mbar, 1);
+  __syncthreads();
 
   for (size_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     int pi = 0;
     uint32_t g0 = 0, pb0 = a.pr.block_begin;
     if (a.pr.n > 1) {
-      pi = pair_lookup(a.pr.group_end, a.pr.n, (uint32_t)grp);
-      if (pi) g0 = a.pr.group_end[pi - 1], pb0 = a.pr.block_end[pi - 1];
+      // first pair whose group_end exceeds grp: one lane per pair, a ballot instead of a search
+      const uint32_t e = lane < a.pr.n ? s_gend[lane] : 0xffffffffu;
+      pi = __ffs(__ballot_sync(0xffffffffu, (uint32_t)grp < e)) - 1;
+      if (pi) g0 = s_gend[pi - 1], pb0 = a.pr.block_end[pi - 1];
     }
     const PlaneView cur = a.pr.cur[pi], ref = a.pr.ref[pi];
     const size_t gb0 = pb0 + (grp - g0) * G, gb1 = min(gb0 + (size_t)G, (size_t)a.pr.block_end[pi]);
-    // pass 0 tries the whole group; if its window does not fit, passes 1.. take one block each
-    bool whole = true;
+    // A pass takes `chunk` blocks; it starts as the whole group and halves whenever a window does not
+    // fit (e.g. a group that straddles the end of a block row), down to single blocks.
+    int chunk = G;
     bool force_bbox = false;  // set when a hinted window turned out too small for the candidates
     size_t b0 = gb0, b1 = gb1;
     while (b0 < gb1) {
@@ -602,15 +608,20 @@ __global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 
       pre.mv_col = 0;
       if (hinted && lo + threadIdx.x < hi) pre = a.cands[lo + threadIdx.x];
       if (hinted) {
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) {  // warp 0: a lane per block, never beyond what get_mv_range allows (plane padding)
           int x0 = INT_MAX, x1 = INT_MIN, y0 = INT_MAX, y1 = INT_MIN;
-          for (int k = 0; k < nb; k++) {  // never beyond what get_mv_range allows (plane padding)
-            const MvRange r = s_rng[k];
-            x0 = min(x0, s_blk[k].x + max(-a.hint_px, r.x_min / 8));
-            x1 = max(x1, s_blk[k].x + min(a.hint_px, r.x_max / 8));
-            y0 = min(y0, s_blk[k].y + max(-a.hint_px, r.y_min / 8));
-            y1 = max(y1, s_blk[k].y + min(a.hint_px, r.y_max / 8));
+          if (lane < nb) {
+            const MvRange r = s_rng[lane];
+            x0 = s_blk[lane].x + max(-a.hint_px, r.x_min / 8);
+            x1 = s_blk[lane].x + min(a.hint_px, r.x_max / 8);
+            y0 = s_blk[lane].y + max(-a.hint_px, r.y_min / 8);
+            y1 = s_blk[lane].y + min(a.hint_px, r.y_max / 8);
           }
+          x0 = __reduce_min_sync(0xffffffffu, x0);
+          x1 = __reduce_max_sync(0xffffffffu, x1);
+          y0 = __reduce_min_sync(0xffffffffu, y0);
+          y1 = __reduce_max_sync(0xffffffffu, y1);
+        if (lane == 0) {
           s_box[0] = x0;
           s_box[1] = x1;
           s_box[2] = y0;
@@ -630,6 +641,7 @@ __global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 
             }
           }
           s_box[4] = by_tma;
+        }
         }
       } else {
         int bx0 = INT_MAX, bx1 = INT_MIN, by0 = INT_MAX, by1 = INT_MIN;
@@ -678,8 +690,9 @@ __global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 
         continue;
       }
       if (!fits && nb > 1) {  // uniform: derived from shared state
-        whole = false;
-        b1 = b0 + 1;
+        chunk = (nb + 1) >> 1;
+        b1 = b0 + chunk;
+        force_bbox = false;
         continue;
       }
       // Sparse candidate sets (few candidates per block, e.g. the sub-pel / mode-pruning SATD
@@ -977,9 +990,8 @@ __global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 
         }
       }
       // next pass
-      if (whole) break;
       b0 = b1;
-      b1 = b0 + 1;
+      b1 = min(b0 + (size_t)chunk, gb1);
       force_bbox = false;
     }
   }
@@ -1832,6 +1844,13 @@ int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px, const b200_pl
   constexpr int TPC = NCH < 32 ? NCH : 32;
   const int threads = SATD ? 128 : B200_SAD_THREADS;  // SATD holds a 64-entry chunk per thread: smaller CTAs, more of them
   int G = (int)std::min<size_t>(kMaxGroup, std::max<size_t>(1, (threads / TPC) / std::max<size_t>(avg, 1)));
+  // Cooperative SAD: the per-group work (descriptors, window geometry, TMA issue, barriers) is paid per
+  // group whatever its size, and a wider group re-uses more of its window: take more blocks per group
+  // than one round of the CTA needs (B200_SAD_GROUP overrides, for A/B runs).
+  if (!SATD && W >= 16 && window_hint_px > 0) {
+    static const int env_g = getenv("B200_SAD_GROUP") ? atoi(getenv("B200_SAD_GROUP")) : 0;
+    G = std::max(G, env_g > 0 ? std::min(env_g, kMaxGroup) : B200_SAD_GROUP_DEFAULT);
+  }
   G = std::max(1, std::min(G, 16384 / (W * H)));  // org tiles <= 16 KB
   // Shared window sized from the caller's search-range hint (+ the group's extent along x);
   // groups/blocks that do not fit degrade inside the kernel, never fail.
