@@ -65,6 +65,9 @@ class ClockSampler:
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.perf_counter()       # nvidia-smi takes a few 100 ms to start: the first sample
+            while not self.lines and time.perf_counter() - t0 < 5.0:   # must exist before the load begins
+                time.sleep(0.01)
         except OSError:
             self.proc = None
 
@@ -318,6 +321,9 @@ def run_b200(args, rank, world, local_rank):
     l0 = ctx.launches
     ms = timed(step, args.steps)
     launches = ctx.launches - l0
+    for _ in range(int(min(2000, max(0, 250.0 / max(ms / args.steps, 1e-3) - args.steps)))):   # ~0.25 s more of the
+        step()                                                   # same steps (untimed): clock samples under load
+    torch.cuda.synchronize()
     units_per_step = world * F * (n_sad + n_satd + nb)
     value = units_per_step * args.steps / (ms * 1e-3)
 
@@ -457,9 +463,25 @@ def run_b200(args, rank, world, local_rank):
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
         }
         print(json.dumps(out))
-    if world > 1:
+    finish(world, dist)
+
+
+def finish(world, dist):
+    """N > 1: leave through a barrier, give destroy_process_group 20 s, then exit the process for good - a
+    teardown that hangs after the result line is printed would stall the whole launch."""
+    sys.stdout.flush()
+    if world <= 1:
+        return
+    try:
         dist.barrier()
-        dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        pass
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(20)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 # ----------------------------------------------------------------------------- B200 arm, 4K tiles
@@ -608,7 +630,9 @@ def run_b200_tiles(args, rank, world, local_rank):
         step_body()
     torch.cuda.synchronize()
     graph = None
-    if not args.no_graph:
+    # NCCL inside a captured graph works, but tearing such a process group down has hung a 2-rank run
+    # (and the graph buys ~0: the step is GPU-bound): eager at N > 1 unless --graph asks for it
+    if not args.no_graph and (world == 1 or args.graph):
         try:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=stream):
@@ -652,6 +676,9 @@ def run_b200_tiles(args, rank, world, local_rank):
     ms = timed(step, args.steps)
     if launches_per_step is None:
         launches_per_step = (ctx.launches - l0) // args.steps
+    for _ in range(int(min(2000, max(0, 250.0 / max(ms / args.steps, 1e-3) - args.steps)))):   # ~0.25 s more of the
+        step()                                                   # same steps (untimed): clock samples under load
+    torch.cuda.synchronize()
     units_per_step = F * nb_all * (CAND_SAD + CAND_SATD + 1)        # the whole job, every tile
     value = units_per_step * args.steps / (ms * 1e-3)
     legs = {}
@@ -699,9 +726,9 @@ def run_b200_tiles(args, rank, world, local_rank):
             "gpu_launches": int(launches_per_step * args.steps),
         }
         print(json.dumps(out))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    graph = step = None          # a captured NCCL node must not outlive its communicator
+    torch.cuda.synchronize()
+    finish(world, dist)
 
 
 def run_e2e(ctx0, blocks, args, world=1, dist=None):
@@ -884,12 +911,15 @@ def main():
                          "configs[4] (4K, 8 tiles sharded over the ranks, total work fixed) on several")
     ap.add_argument("--frames-4k", type=int, default=16, help="4K frame pairs of the tile workload")
     ap.add_argument("--no-graph", action="store_true", help="4k-tiles: launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--graph", action="store_true", help="4k-tiles at N > 1: capture the step (incl. the NCCL all-gather) in a CUDA graph")
     ap.add_argument("--pairs-per-launch", type=int, default=32,
                     help="frame pairs served by one launch of each leg (b200_*_multi_dev); 1 = a launch per pair")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: NCCL's own log (the version banner included) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         run_reference(args, rank, world)
     elif args.workload == "4k-tiles" or (args.workload == "auto" and world > 1):

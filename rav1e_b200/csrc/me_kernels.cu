@@ -501,6 +501,16 @@ __device__ __forceinline__ uint32_t chunk_satd_u8(const uint32_t *wrow, int pitc
   }
 }
 
+// sad = tot on lane `which`, one compare + one predicated move where they stand: written as `if (lane ==
+// sidx) sad = tot` in a fully unrolled loop the compiler hoists all 32 compares out of the loop and packs
+// the predicates into a bit mask (130 instructions per 32 candidates, ncu r2j)
+__device__ __forceinline__ void keep_if_lane(uint32_t &sad, uint32_t tot, int lane, int which) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\t@p mov.u32 %0, %3;\n\t}"
+      : "+r"(sad)
+      : "r"(lane), "r"(which), "r"(tot));
+}
+
 constexpr int kCandSmemBytes = 160 * 1024;  // upper bound of the dynamic smem (window + org)
 constexpr int kMaxGroup = 16;               // blocks sharing one staged window
 constexpr int kKeyIdxBits = 24;             // packed argmin key: cost << 24 | index in block
@@ -561,9 +571,14 @@ __global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 
     uint32_t g0 = 0, pb0 = a.pr.block_begin;
     if (a.pr.n > 1) {
       // first pair whose group_end exceeds grp: one lane per pair, a ballot instead of a search
+#ifdef B200_V_OLD_LOOKUP
+      pi = pair_lookup(a.pr.group_end, a.pr.n, (uint32_t)grp);
+      if (pi) g0 = a.pr.group_end[pi - 1], pb0 = a.pr.block_end[pi - 1];
+#else
       const uint32_t e = lane < a.pr.n ? s_gend[lane] : 0xffffffffu;
       pi = __ffs(__ballot_sync(0xffffffffu, (uint32_t)grp < e)) - 1;
       if (pi) g0 = s_gend[pi - 1], pb0 = a.pr.block_end[pi - 1];
+#endif
     }
     const PlaneView cur = a.pr.cur[pi], ref = a.pr.ref[pi];
     const size_t gb0 = pb0 + (grp - g0) * G, gb1 = min(gb0 + (size_t)G, (size_t)a.pr.block_end[pi]);
@@ -608,6 +623,18 @@ __global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 
       pre.mv_col = 0;
       if (hinted && lo + threadIdx.x < hi) pre = a.cands[lo + threadIdx.x];
       if (hinted) {
+#ifdef B200_V_OLD_EXTENT
+        if (threadIdx.x == 0) {
+          int x0 = INT_MAX, x1 = INT_MIN, y0 = INT_MAX, y1 = INT_MIN;
+          for (int k = 0; k < nb; k++) {
+            const MvRange r = s_rng[k];
+            x0 = min(x0, s_blk[k].x + max(-a.hint_px, r.x_min / 8));
+            x1 = max(x1, s_blk[k].x + min(a.hint_px, r.x_max / 8));
+            y0 = min(y0, s_blk[k].y + max(-a.hint_px, r.y_min / 8));
+            y1 = max(y1, s_blk[k].y + min(a.hint_px, r.y_max / 8));
+          }
+        {
+#else
         if (threadIdx.x < 32) {  // warp 0: a lane per block, never beyond what get_mv_range allows (plane padding)
           int x0 = INT_MAX, x1 = INT_MIN, y0 = INT_MAX, y1 = INT_MIN;
           if (lane < nb) {
@@ -622,6 +649,7 @@ __global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 
           y0 = __reduce_min_sync(0xffffffffu, y0);
           y1 = __reduce_max_sync(0xffffffffu, y1);
         if (lane == 0) {
+#endif
           s_box[0] = x0;
           s_box[1] = x1;
           s_box[2] = y0;
@@ -635,7 +663,7 @@ __global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 
             const int wx = cx - tm.ox[pi];
             by_tma = dense0 && x1 - wx + W + 4 <= tm.box_w && y1 - y0 + H <= tm.box_h;
             if (by_tma) {
-              tma_load_window(smem_u32(win), &tm.map[pi], cx, y0 + tm.oy[pi], mbar,
+              tma_load_window(smem_u32(win), &tm.map[pi], cx >> 2, y0 + tm.oy[pi], mbar,
                               (uint32_t)(tm.box_w * tm.box_h));
               s_box[0] = wx;
             }
@@ -805,7 +833,7 @@ __global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 
                 wa += pstep;
               }
               const uint32_t tot = __reduce_add_sync(0xffffffffu, part);
-              if (lane == sidx) sad = tot;
+              keep_if_lane(sad, tot, lane, sidx);
             }
           } else {
 #pragma unroll
@@ -827,7 +855,7 @@ __global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 
                 wa += pstep;
               }
               const uint32_t tot = __reduce_add_sync(0xffffffffu, part);
-              if (lane == sidx) sad = tot;
+              keep_if_lane(sad, tot, lane, sidx);
             }
           }
           unsigned long long cost = kEmptyCost, key = ~0ull;
@@ -1434,8 +1462,11 @@ __global__ void __launch_bounds__(256, B200_SATD_SPARSE_MINBLOCKS)
   SatdHdr h0 = fetch_hdr(blk), h1 = fetch_hdr(blk + nwarps), h2 = fetch_hdr(blk + 2 * nwarps);
   b200_cand c0 = fetch_cand(h0, h0.lo), c1 = fetch_cand(h1, h1.lo);
   // plane pair of a block: the warp's blocks come in ascending order, the pair index only grows
+  uint32_t pair_end = a.pr.block_end[0];  // end of the pair the newest staged block belongs to
   auto advance_pair = [&](int pi, size_t b) {
+    if ((uint32_t)b < pair_end) return pi;  // the usual case costs one compare
     while (pi + 1 < a.pr.n && (uint32_t)b >= a.pr.block_end[pi]) pi++;
+    pair_end = a.pr.block_end[pi];
     return pi;
   };
   int pi0 = advance_pair(0, blk);
@@ -1456,6 +1487,8 @@ __global__ void __launch_bounds__(256, B200_SATD_SPARSE_MINBLOCKS)
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncwarp();
     unsigned long long best = ~0ull;
+    uint32_t best_sad = kEmptySad;  // this lane's best candidate so far: the lane that owns the block's
+    short best_row = 0, best_col = 0;  // first minimum writes the record itself
     SatdLane L = L0;
     for (uint32_t base = h0.lo;;) {
       const uint32_t i = base + myc;
@@ -1471,7 +1504,7 @@ __global__ void __launch_bounds__(256, B200_SATD_SPARSE_MINBLOCKS)
         if (a.out_sad) a.out_sad[i] = sad;
         if (a.out_cost) a.out_cost[i] = cost;
       }
-      best = key < best ? key : best;
+      if (key < best) best = key, best_sad = sad, best_row = L.c.mv_row, best_col = L.c.mv_col;
       base += CPP;
       if (base >= h0.hi) break;
       // further batches of a long list, in place: this half is free once every lane has evaluated
@@ -1485,25 +1518,15 @@ __global__ void __launch_bounds__(256, B200_SATD_SPARSE_MINBLOCKS)
       const uint32_t mh = __reduce_min_sync(0xffffffffu, khi);
       const uint32_t klo = khi == mh ? (uint32_t)best : 0xffffffffu;
       const uint32_t ml = __reduce_min_sync(0xffffffffu, klo);
-      if (lane == 0) {
-        const unsigned long long key = ((unsigned long long)mh << 32) | ml;
+      // keys are unique (they carry the candidate's index), so exactly one lane holds the minimum;
+      // with no candidate in range every key is ~0 and lane 0 writes MotionSearchResult::empty()
+      const unsigned long long key = ((unsigned long long)mh << 32) | ml;
+      if (key == ~0ull ? lane == 0 : best == key) {
         b200_me_result res;
-        res.cost = kEmptyCost;
-        res.sad = kEmptySad;
-        res.mv_row = 0;
-        res.mv_col = 0;
-        if (key != ~0ull) {
-          const uint32_t idx = (uint32_t)(key & ((1u << kKeyIdxBits) - 1));
-          const unsigned long long cost = key >> kKeyIdxBits;
-          const b200_cand c = a.cands[h0.lo + idx];
-          const uint32_t r1 = b200_mv_rate(c.mv_row, c.mv_col, p0r, p0c, a.allow_hp);
-          const uint32_t r2 = b200_mv_rate(c.mv_row, c.mv_col, p1r, p1c, a.allow_hp) + 1;
-          const uint32_t rate = r1 < r2 ? r1 : r2;
-          res.cost = cost;
-          res.sad = (uint32_t)((cost - (unsigned long long)rate * a.lambda) >> 8);
-          res.mv_row = c.mv_row;
-          res.mv_col = c.mv_col;
-        }
+        res.cost = key == ~0ull ? kEmptyCost : key >> kKeyIdxBits;
+        res.sad = best_sad;
+        res.mv_row = best_row;
+        res.mv_col = best_col;
         a.out_best[blk] = res;
       }
     }
@@ -1746,7 +1769,9 @@ struct TmaKeyHash {
 // False when the plane cannot be described (unaligned base / pitch): the caller stages by hand.
 bool tma_plane_map(const b200_plane &p, uint32_t bw, uint32_t bh, CUtensorMap *out, short *ox, short *oy) {
   EncodeTiledFn enc = tma_encoder();
-  if (!enc || p.bpp != 1 || p.pad < 0 || p.pad > 16384 || (p.stride & 15) || bw > 256 || bh > 256 ||
+  // the map counts 4-byte elements (box dimensions are limited to 256 ELEMENTS: a byte map would cap the
+  // window at 256 pixels), so x coordinates are pixel columns / 4
+  if (!enc || p.bpp != 1 || p.pad < 0 || p.pad > 16384 || (p.stride & 15) || bw > 1024 || bh > 256 ||
       (bw & 15))
     return false;
   // origin: the allocation's first column when known (b200_plane_alloc keeps it 256-byte
@@ -1765,12 +1790,12 @@ bool tma_plane_map(const b200_plane &p, uint32_t bw, uint32_t bh, CUtensorMap *o
   auto it = cache.find(key);
   if (it == cache.end()) {
     CUtensorMap m;
-    const cuuint64_t dims[2] = {key.w, key.h};
+    const cuuint64_t dims[2] = {(key.w + 3) / 4, key.h};  // the row pitch is a multiple of 16: still inside the row
     const cuuint64_t strides[1] = {key.stride};
-    const cuuint32_t box[2] = {bw, bh};
+    const cuuint32_t box[2] = {bw / 4, bh};
     const cuuint32_t estr[2] = {1, 1};
     if (key.w > key.stride ||
-        enc(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)base, dims, strides, box, estr,
+        enc(&m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *)base, dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return false;

@@ -99,7 +99,7 @@ def test_encode_tx_block_chain_on_device():
 
 
 @pytest.mark.parametrize("ts,tt,bd", [(2, 0, 8), (1, 3, 8), (0, 1, 8), (3, 0, 10), (4, 0, 8), (9, 0, 8), (13, 1, 10),
-                                      (5, 9, 8), (16, 10, 12), (11, 0, 10)])
+                                      (5, 9, 8), (16, 9, 12), (11, 0, 10), (8, 10, 8)])
 def test_encode_tx_blocks_one_call_equals_the_three_steps(ts, tt, bd):
     """the fused kernel (b200_encode_tx_blocks_dev: coefficients stay on the SM) == b200_fwd_txfm_residual_dev +
     b200_quantize_dev + b200_inverse_transform_add_dev called one after the other, every output, with
