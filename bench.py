@@ -140,7 +140,7 @@ def run_reference(args, rank, world):
         return
     from tests import oracle_lib as O
     threads = O.host_threads()
-    tiles_mode = args.workload == "4k-tiles" or (args.workload == "auto" and world > 1)
+    tiles_mode = args.workload == "4k-tiles"
     blocks = grid_blocks()
     cur_img, ref_img = synth_frame_pair(0)
     ocur, oref = O.Plane(W, H, PAD), O.Plane(W, H, PAD)
@@ -286,14 +286,23 @@ def run_b200(args, rank, world, local_rank):
                                         d_coef[f0 * nb * BW * BH:], 2, 0, 8)
 
     NG = len(groups)
+    side = torch.cuda.Stream(device=local_rank)
+    ev_sad, ev_comm = torch.cuda.Event(), torch.cuda.Event()
 
     def step():
         for g in range(NG):
             sad_launch(g)
+        if world > 1:   # winners to every rank (the entropy-coder owner): on a side stream as soon as the
+            ev_sad.record(stream)        # SAD legs are done, under the SATD and transform legs
+            with torch.cuda.stream(side):
+                side.wait_event(ev_sad)
+                dist.all_gather_into_tensor(gathered, d_best)
+                ev_comm.record(side)
+        for g in range(NG):
             satd_launch(g)
             txfm_launch(g)
-        if world > 1:   # per-tile/frame winners to every rank (the entropy-coder owner)
-            dist.all_gather_into_tensor(gathered, d_best)
+        if world > 1:
+            stream.wait_event(ev_comm)   # the step ends when the winners have arrived everywhere
 
     def timed(fn, reps):
         if world > 1:
@@ -411,6 +420,13 @@ def run_b200(args, rank, world, local_rank):
     out = None
     # ---- e2e: same metric through the host-buffer C ABI (H2D + kernels + D2H per frame), on every rank
     e2e = run_e2e(ctx, blocks, args, world, dist if world > 1 else None)
+    # ---- the 4K tile workload (BASELINE configs[4]) on the same ranks: strong scaling, reported beside the
+    # headline so that the N = 1, 2, 4, 8 lines of one series carry both (auto mode; --workload 1080p skips it)
+    tiles4k = None
+    if args.workload == "auto":
+        torch.cuda.synchronize()
+        tiles4k = run_b200_tiles(args, rank, world, local_rank, embedded=True)
+        torch.cuda.set_stream(stream)
     if rank == 0:
         cpu = run_cpu_baseline(blocks)
         out = {
@@ -459,9 +475,12 @@ def run_b200(args, rank, world, local_rank):
                                         "achieved_candidates_per_s": n_sad * pairs_per_launch / (ms_sad * 1e-3),
                                         "frac": n_sad * pairs_per_launch / (ms_sad * 1e-3) / (148 * 4 * 1.965e9 / 10),
                                         "note": "148 SMs x 4 schedulers x 1 warp instruction per clock at 1965 MHz; "
-                                                "the measured kernel issues ~35 per candidate (profiles/NOTES_r1.md)"}},
+                                                "the measured kernel issues ~29 per candidate, issue slots 68 % busy, L1TEX 73 % "
+                                                "(ncu, profiles/prof_r2l_sad_raw.csv, NOTES_r2.md)"}},
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
         }
+        if tiles4k is not None:
+            out["strong_scaling_4k_tiles"] = tiles4k
         print(json.dumps(out))
     finish(world, dist)
 
@@ -489,7 +508,7 @@ W4K, H4K = 3840, 2160
 TILE_COLS_LOG2, TILE_ROWS_LOG2 = 2, 1     # 4 x 2 tiles of 15 x 17 superblocks (BASELINE configs[4])
 
 
-def run_b200_tiles(args, rank, world, local_rank):
+def run_b200_tiles(args, rank, world, local_rank, embedded=False):
     """BASELINE configs[4]: 4K 8-bit, 8 tiles, speed-6 RDO legs + CDEF, tile t owned by rank t mod N
     (encoder.rs:3249-3257 runs one worker per tile; tiling/tiler.rs:97-132 lays the grid out).  STRONG
     scaling: the job - F 4K frame pairs, every tile of every frame - is the same at every N; a rank
@@ -506,8 +525,10 @@ def run_b200_tiles(args, rank, world, local_rank):
     from rav1e_b200 import backend as B
     from rav1e_b200 import shard
 
+    # embedded: called from run_b200 at the end of the 1080p measurement (same process group, own stream
+    # and context); returns the result instead of printing it, without the e2e / CPU legs
     torch.cuda.set_device(local_rank)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.Stream(device=local_rank)
     side = torch.cuda.Stream(device=local_rank)
@@ -663,7 +684,7 @@ def run_b200_tiles(args, rank, world, local_rank):
         return float(ms.item())
 
     clk = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not embedded:
         clk.start()
     for _ in range(max(args.warmup, 3)):
         step()
@@ -691,7 +712,26 @@ def run_b200_tiles(args, rank, world, local_rank):
         leg_comm()
     comm_alone()
     ms_comm = timed(comm_alone, max(2, args.steps // 2)) / max(2, args.steps // 2)
-    clocks = clk.stop() if rank == 0 else None
+    clocks = clk.stop() if rank == 0 and not embedded else None
+    if embedded:
+        res = None
+        if rank == 0:
+            res = {"workload": "4k-8bit-speed6-8tiles (BASELINE configs[4])", "scaling": "strong",
+                   "value": value, "unit": "blocks/s", "ms_per_step": ms / args.steps, "n_gpus": world,
+                   "frame_pairs": F, "blocks_per_frame": nb_all, "tiles": NT,
+                   "parallelism": f"tile t -> rank t mod {world} ({len(mine)} tile(s) per rank); total work fixed; "
+                                  "the N=1 line of the same run series is the baseline",
+                   "legs": "64 SAD + 8 SATD candidates + residual/DCT per 16x16 block, cdef_find_dir + cdef_filter per tile "
+                           "(CDEF time is in the step, not in the unit count)",
+                   "collective": {"what": "NCCL all-gather of 8-byte winner records on a side stream behind the SAD leg",
+                                  "bytes_per_rank": int(rec_local.numel()), "ms_alone": ms_comm},
+                   "cuda_graph": graph is not None, "per_rank_leg_ms": legs,
+                   "gpu_launches": int(launches_per_step * args.steps)}
+        graph = step = None
+        torch.cuda.synchronize()
+        for pl in outs:
+            ctx.plane_free(pl)
+        return res
     # the same job on ONE GPU is the strong-scaling baseline: rank 0 cannot run it inside an N-rank
     # launch without the other ranks idling, so it is measured by `--gpus 1 --workload 4k-tiles`
     e2e = run_e2e(ctx, grid_blocks(), args, world, dist if world > 1 else None)
@@ -907,8 +947,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU)
     ap.add_argument("--workload", default="auto", choices=["auto", "1080p", "4k-tiles"],
-                    help="auto: BASELINE configs[1] (1080p lookahead batch, per-GPU work fixed) on 1 GPU, "
-                         "configs[4] (4K, 8 tiles sharded over the ranks, total work fixed) on several")
+                    help="auto: BASELINE configs[1] (1080p lookahead batch, per-GPU work fixed: weak scaling) as the "
+                         "line's metric at every N, plus configs[4] (4K, 8 tiles sharded over the ranks, total work "
+                         "fixed: strong scaling) in `strong_scaling_4k_tiles`; 1080p / 4k-tiles: only that one")
     ap.add_argument("--frames-4k", type=int, default=16, help="4K frame pairs of the tile workload")
     ap.add_argument("--no-graph", action="store_true", help="4k-tiles: launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--graph", action="store_true", help="4k-tiles at N > 1: capture the step (incl. the NCCL all-gather) in a CUDA graph")
@@ -922,7 +963,7 @@ def main():
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         run_reference(args, rank, world)
-    elif args.workload == "4k-tiles" or (args.workload == "auto" and world > 1):
+    elif args.workload == "4k-tiles":
         run_b200_tiles(args, rank, world, local_rank)
     else:
         run_b200(args, rank, world, local_rank)

@@ -30,9 +30,6 @@
 #ifndef B200_SAD_THREADS
 #define B200_SAD_THREADS 256  // CTA size of the SAD instantiations of the grouped kernel
 #endif
-#ifndef B200_SAD_GROUP_DEFAULT
-#define B200_SAD_GROUP_DEFAULT 8  // blocks per group of the cooperative SAD kernel (measured: profiles/NOTES_r2.md)
-#endif
 #ifndef B200_SAD16_MINBLOCKS
 // Resident CTAs per SM the 16x16 SAD kernel is register-capped for: 4 (64 registers, no spills)
 // measured 0.850 ms per 32-pair launch against 0.931 ms at 5 (48 registers, 66 B of spills).
@@ -713,11 +710,22 @@ __global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 
         pitch_words = (row_bytes >> 2) | 4;
       }
       const bool fits = (long long)rows * pitch_words * 4 <= (long long)win_bytes;
+      if (!fits && nb > 1) {  // uniform: derived from shared state
+        // a group that runs over the end of a block row: split it there (each part is a compact window again)
+        int brk = nb;
+        for (int k = nb - 1; k >= 1; k--)
+          if (s_blk[k].y != s_blk[0].y) brk = k;
+        if (brk < nb) {
+          b1 = b0 + brk;
+          force_bbox = false;
+          continue;
+        }
+      }
       if (!fits && hinted) {  // the exact bounding box may still fit
         force_bbox = true;
         continue;
       }
-      if (!fits && nb > 1) {  // uniform: derived from shared state
+      if (!fits && nb > 1) {
         chunk = (nb + 1) >> 1;
         b1 = b0 + chunk;
         force_bbox = false;
@@ -809,7 +817,9 @@ __global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 
           const unsigned live = __ballot_sync(0xffffffffu, inr);
           const uint32_t org0 = __shfl_sync(0xffffffffu, par.y, live ? __ffs(live) - 1 : 0);
           const bool one_block = __all_sync(0xffffffffu, !inr || par.y == org0);
-          if (one_block) {
+          if (!live) {
+            // nothing in range in this warp's 32 slots (the tail of a group's last round): skip the evaluation
+          } else if (one_block) {
             uint32_t orgr[P];
 #pragma unroll
             for (int p = 0; p < P; p++)
@@ -1872,9 +1882,20 @@ int launch_cand_group(b200_ctx *ctx, MeArgs a, int window_hint_px, const b200_pl
   // Cooperative SAD: the per-group work (descriptors, window geometry, TMA issue, barriers) is paid per
   // group whatever its size, and a wider group re-uses more of its window: take more blocks per group
   // than one round of the CTA needs (B200_SAD_GROUP overrides, for A/B runs).
-  if (!SATD && W >= 16 && window_hint_px > 0) {
+  if (!SATD && W >= 16 && W <= 64 && window_hint_px > 0) {
     static const int env_g = getenv("B200_SAD_GROUP") ? atoi(getenv("B200_SAD_GROUP")) : 0;
-    G = std::max(G, env_g > 0 ? std::min(env_g, kMaxGroup) : B200_SAD_GROUP_DEFAULT);
+    int want = env_g > 0 ? std::min(env_g, kMaxGroup) : 0;
+    if (!want) {
+      // the widest group (<= 12 blocks) whose window + org tiles leave room for three CTAs per SM (227 KB of
+      // shared memory, 1 KB reserved + ~5 KB static per CTA); measured on 16x16 / +-64 px, ms per 32-pair
+      // launch: 4: 0.728, 8: 0.622, 12: 0.594, 16: 0.669 (profiles/NOTES_r2.md)
+      const size_t budget = (size_t)227 * 1024 / 3 - 6 * 1024;
+      for (want = 12; want > 1; want--) {
+        const size_t bw = b200_align_up((size_t)(2 * window_hint_px + want * W + 4 + 15), 16) + 16;
+        if (bw * (size_t)(2 * window_hint_px + H) + (size_t)want * W * H <= budget) break;
+      }
+    }
+    G = std::max(G, want);
   }
   G = std::max(1, std::min(G, 16384 / (W * H)));  // org tiles <= 16 KB
   // Shared window sized from the caller's search-range hint (+ the group's extent along x);
