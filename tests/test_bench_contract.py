@@ -1,7 +1,7 @@
-"""The bench line's contract (driver-facing): the committed measurement of the final round-1 tree
-(profiles/bench_r1_final.json, written by `python bench.py` on a B200) carries every key the
-contract names, with sane types and internally consistent numbers.  Guards the output format
-against accidental edits to bench.py."""
+"""The bench line's contract (driver-facing): the committed measurements of the round-2 tree
+(profiles/bench_r2_final.json at N=1, bench_r2_n2.json at N=2, written by `python bench.py` on B200s; the
+round-1 lines stay under the same checks) carry every key the contract names, with sane types and internally
+consistent numbers.  Guards the output format against accidental edits to bench.py."""
 import json
 import os
 
@@ -17,7 +17,8 @@ def load(name):
     return json.loads(lines[0])
 
 
-@pytest.mark.parametrize("name,n", [("bench_r1_final.json", 1), ("bench_r1_final_2gpu.json", 2)])
+@pytest.mark.parametrize("name,n", [("bench_r1_final.json", 1), ("bench_r1_final_2gpu.json", 2),
+                                    ("bench_r2_final.json", 1), ("bench_r2_n2.json", 2)])
 def test_contract_keys(name, n):
     d = load(name)
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -48,6 +49,28 @@ def test_contract_keys(name, n):
     assert abs(d["value"] - units / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
 
 
-def test_two_gpus_scale_weakly():
-    one, two = load("bench_r1_final.json"), load("bench_r1_final_2gpu.json")
+@pytest.mark.parametrize("a,b", [("bench_r1_final.json", "bench_r1_final_2gpu.json"),
+                                 ("bench_r2_final.json", "bench_r2_n2.json")])
+def test_two_gpus_scale_weakly(a, b):
+    one, two = load(a), load(b)
     assert 1.7 < two["value"] / one["value"] <= 2.05
+
+
+@pytest.mark.parametrize("name,n", [("bench_r2_final.json", 1), ("bench_r2_n2.json", 2)])
+def test_strong_scaling_object(name, n):
+    """auto mode carries the 4K tile workload (BASELINE configs[4]) beside the headline: whole-job units over
+    the max-over-ranks step time, total work independent of N"""
+    t = load(name)["strong_scaling_4k_tiles"]
+    assert t["scaling"] == "strong" and t["n_gpus"] == n and t["tiles"] == 8
+    units = t["frame_pairs"] * t["blocks_per_frame"] * (64 + 8 + 1)
+    assert abs(t["value"] - units / (t["ms_per_step"] * 1e-3)) < 1e-6 * t["value"]
+    assert set(t["per_rank_leg_ms"]) == {"sad_cand", "satd_cand", "residual+fwd_txfm", "cdef_find_dir", "cdef_filter"}
+
+
+def test_strong_scaling_series():
+    one = load("bench_r2_final.json")["strong_scaling_4k_tiles"]
+    two = load("bench_r2_n2.json")["strong_scaling_4k_tiles"]
+    eight = load("bench_r2_tiles_n8.json")          # measured with --workload 4k-tiles (tiles as the line's metric)
+    assert eight["scaling"] == "strong" and eight["n_gpus"] == 8
+    assert two["value"] / one["value"] > 1.9
+    assert eight["value"] / one["value"] / 8 >= 0.9
