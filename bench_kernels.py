@@ -29,8 +29,15 @@ TX_SIZES = [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (4, 8), (8, 4), (8, 16
 
 
 def timed(fn, reps=20, warm=3):
-    for _ in range(warm):
+    """ms per launch, CUDA events.  The GPU idles (and clocks down) while a CPU-port leg runs between two GPU legs:
+    warm up until at least 3 launches AND 3 ms of back-to-back work have gone by."""
+    import time
+    t0, k = time.perf_counter(), 0
+    while k < warm or time.perf_counter() - t0 < 3e-3:
         fn()
+        k += 1
+        if k % 8 == 0:
+            torch.cuda.synchronize()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -92,7 +99,7 @@ def main():
         for tt in range(17):
             if not ctx.L.b200_valid_av1_transform(ts, tt):
                 continue
-            ms = timed(lambda: ctx.fwd_txfm_dev(resid, w * h, w, out, n, ts, tt, 8, False), reps=5)
+            ms = timed(lambda: ctx.fwd_txfm_dev(resid, w * h, w, out, n, ts, tt, 8, False), reps=10)
             sweep_ms += ms
             if tt == 0:
                 cpu = None
