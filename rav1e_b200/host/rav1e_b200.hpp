@@ -192,6 +192,37 @@ void dispatch_predict_intra(PredictionMode mode, PredictionVariant variant, Plan
                      plane_w, plane_h, dst_x, dst_y);
 }
 
+// rdo.rs:718-723: `compute_rd_cost(fi, rate, distortion)` with lambda = fi.lambda: one correctly rounded
+// f64 fma of rate / 8 (rate is in 1/8 bit units, OD_BITRES = 3).
+inline double compute_rd_cost(double lambda, std::uint32_t rate, std::uint64_t distortion, CpuFeatureLevel cpu) {
+  require_cuda(cpu);
+  return b200_compute_rd_cost(lambda, rate, distortion);
+}
+
+// ------------------------------------------------------------------------------------------
+// The lookahead-shaped call (b200_frame_pipe_*): one push per frame, the previous frame is the reference.
+// Host buffers in and out; winners of the SAD and SATD lists and the coefficients of the SAD winner's residual.
+class FramePipe {
+ public:
+  FramePipe(b200_ctx *ctx, const b200_frame_pipe_cfg &cfg) {
+    if (b200_frame_pipe_create(ctx, &cfg, &pipe_) != B200_OK) throw std::runtime_error(b200_last_error(ctx));
+  }
+  ~FramePipe() { b200_frame_pipe_destroy(pipe_); }
+  FramePipe(const FramePipe &) = delete;
+  FramePipe &operator=(const FramePipe &) = delete;
+  std::size_t nblocks() const { return b200_frame_pipe_nblocks(pipe_); }
+  // offsets: (row, col) full-pel int8 pairs per candidate; NULL outputs are skipped
+  int push(const void *frame, std::ptrdiff_t stride_bytes, const std::int8_t *sad_offsets,
+           const std::int8_t *satd_offsets, const std::int16_t *centers, b200_me_result *best_sad,
+           b200_me_result *best_satd, void *coeffs, std::uint16_t *eob = nullptr, std::uint64_t *tx_dist = nullptr) {
+    return b200_frame_pipe_push(pipe_, frame, stride_bytes, sad_offsets, satd_offsets, centers, best_sad, best_satd,
+                                coeffs, eob, tx_dist);
+  }
+
+ private:
+  b200_frame_pipe *pipe_ = nullptr;
+};
+
 // ------------------------------------------------------------------------------------------
 // Batched motion search helper: what me.rs's serial candidate loops become.  One call
 // evaluates every candidate of every block and returns per-block winners with the reference's

@@ -2,6 +2,7 @@
 // kernels: get_sad / get_satd on the closed-form planes of src/dist.rs:384-413 with the golden
 // values of :418-441 / :477-500, plus forward_transform / put_8tap smoke calls.  Built and run by
 // tests/test_host_mirror_gpu.py.  Exit code 0 = all good.
+#include <cmath>
 #include <cstdio>
 #include <vector>
 
@@ -54,6 +55,12 @@ int main() {
   for (int r = 0; r < 8; r++)
     for (int col = 0; col < 8; col++)
       if (dst[r * 8 + col] != org.data[(size_t)r * org.stride + col]) bad++;
+  // compute_rd_cost is the correctly rounded fma of rdo.rs:718-723
+  const double lam = 123.456789, want = std::fma(lam, 98765 / 8.0, (double)1234567890123ull);
+  if (compute_rd_cost(lam, 98765, 1234567890123ull, CpuFeatureLevel::CUDA_SM100) != want) {
+    std::printf("compute_rd_cost mismatch\n");
+    bad++;
+  }
   std::printf(bad ? "FAILED (%d)\n" : "host mirror ok\n", bad);
   return bad ? 1 : 0;
 }
