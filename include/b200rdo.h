@@ -425,6 +425,24 @@ int b200_frame_pipe_push(b200_frame_pipe *pipe, const void *frame, ptrdiff_t fra
                          const int8_t *sad_offsets, const int8_t *satd_offsets, const int16_t *centers,
                          b200_me_result *best_sad, b200_me_result *best_satd, void *coeffs, uint16_t *eob,
                          uint64_t *tx_dist);
+/* Resident candidate lists.  A search stage's pattern is an encoder constant, not per-frame data: upload the
+ * lists (same layout as for b200_frame_pipe_push; centers may be NULL) ONCE; the device keeps them expanded, and
+ * later pushes may pass NULL for sad_offsets / satd_offsets / centers - then only the frame crosses PCIe.
+ * Synchronous. */
+int b200_frame_pipe_set_lists(b200_frame_pipe *pipe, const int8_t *sad_offsets, const int8_t *satd_offsets,
+                              const int16_t *centers);
+/* A push whose results come back PACKED: what the entropy coder reads from a transform block is
+ * coeffs[scan[0 .. eob)] (src/context/block_unit.rs write_coeffs_lv_map walks the scan order up to eob), so
+ * a quantizing pipe (tx_size >= 0, ac_quant != 0) with resident lists returns, per block, its eob and tx-domain
+ * distortion and - block after block in `packed` - only those eob quantized coefficients in scan order
+ * (i16 for 8-bit frames, i32 for HBD).  *packed_count = total number of coefficients; when it exceeds
+ * packed_capacity (in coefficients) only the first packed_capacity were copied (the call still succeeds: the
+ * caller retries with a larger buffer).  best_sad / best_satd / eob / tx_dist may be NULL.  The call waits
+ * once for the device (the size of the packed copy is a result); in asynchronous mode the packed copy itself is
+ * still in flight when it returns.  The first push of a pipe only uploads: *packed_count = 0. */
+int b200_frame_pipe_push_packed(b200_frame_pipe *pipe, const void *frame, ptrdiff_t frame_stride_bytes,
+                                b200_me_result *best_sad, b200_me_result *best_satd, uint16_t *eob,
+                                uint64_t *tx_dist, void *packed, size_t packed_capacity, size_t *packed_count);
 
 /* ---------------------------------------------------------------- lookahead (api/lookahead.rs)
  * Plane::downsampled (v_frame 0.3.9; encoder.rs:476-477 builds the half / quarter resolution planes of

@@ -197,6 +197,8 @@ def lib():
     L.b200_frame_pipe_nblocks.argtypes = [vp]
     L.b200_frame_pipe_nblocks.restype = sz
     L.b200_frame_pipe_push.argtypes = [vp, vp, C.c_ssize_t] + [vp] * 8
+    L.b200_frame_pipe_set_lists.argtypes = [vp, vp, vp, vp]
+    L.b200_frame_pipe_push_packed.argtypes = [vp, vp, C.c_ssize_t] + [vp] * 5 + [sz, C.POINTER(sz)]
     L.b200_plane_downsample_dev.argtypes = [vp, pp, pp, i32, i32]
     L.b200_estimate_intra_costs_dev.argtypes = [vp, pp, i32, vp]
     L.b200_estimate_inter_costs_dev.argtypes = [vp, pp, pp, vp, vp, vp, vp]
@@ -539,6 +541,22 @@ class FramePipe:
         self.ctx.check(self.ctx.L.b200_frame_pipe_push(
             self.h, frame.ctypes.data, frame.strides[0], _np_ptr(sad_offsets), _np_ptr(satd_offsets), _np_ptr(centers),
             _np_ptr(best_sad), _np_ptr(best_satd), _np_ptr(coeffs), _np_ptr(eob), _np_ptr(tx_dist)))
+
+    def set_lists(self, sad_offsets, satd_offsets, centers=None):
+        """upload the candidate lists once: later pushes may leave them out (only the frame crosses PCIe)"""
+        self.ctx.check(self.ctx.L.b200_frame_pipe_set_lists(self.h, _np_ptr(sad_offsets), _np_ptr(satd_offsets),
+                                                            _np_ptr(centers)))
+
+    def push_packed(self, frame, best_sad=None, best_satd=None, eob=None, tx_dist=None, packed=None):
+        """quantizing pipe with resident lists: per block eob + tx-domain distortion, and in `packed` only the eob
+        quantized coefficients of each block in scan order, block after block.  Returns their total count (which may
+        exceed len(packed): then only len(packed) were copied)."""
+        n = C.c_size_t(0)
+        cap = 0 if packed is None else packed.size
+        self.ctx.check(self.ctx.L.b200_frame_pipe_push_packed(
+            self.h, frame.ctypes.data, frame.strides[0], _np_ptr(best_sad), _np_ptr(best_satd), _np_ptr(eob),
+            _np_ptr(tx_dist), _np_ptr(packed), cap, C.byref(n)))
+        return int(n.value)
 
     def close(self):
         if self.h:

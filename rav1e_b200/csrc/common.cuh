@@ -74,6 +74,8 @@ int b200_mc_cands_internal(b200_ctx *ctx, const b200_plane *ref, const b200_bloc
                            const b200_cand *d_cands, size_t ncands, int w, int h, int mode,
                            int bit_depth, void *d_out);
 int b200_plane_unpack_internal(b200_ctx *ctx, const b200_plane *p, const void *d_packed);
+// device copy of the scan order of (tx_size, tx_type) (scan_order.rs; owned by the context), quantize.cu
+int b200_scan_table_internal(b200_ctx *ctx, int tx_size, int tx_type, const uint16_t **d_scan);
 b200_ctx *b200_default_ctx();  // lazily created; aborts loudly if no device (no CPU fallback)
 
 #ifdef __CUDACC__

@@ -49,6 +49,11 @@ struct b200_frame_pipe {
   uint16_t *d_eob = nullptr;
   uint64_t *d_dist = nullptr;
   size_t coef_bytes = 0, q_bytes = 0;
+  // resident lists (b200_frame_pipe_set_lists) and packed output (b200_frame_pipe_push_packed)
+  bool lists_resident = false, centers_resident = false;
+  uint32_t *d_pack_offs = nullptr;  // [nblocks + 1] exclusive scan of eob; [nblocks] = total
+  void *d_packed = nullptr;         // worst case: every coefficient of every block
+  uint32_t *h_total = nullptr;      // pinned: the total, read by the host once per packed push
 };
 
 namespace {
@@ -70,6 +75,60 @@ __global__ void expand_offsets_kernel(const char2 *offs1, int per1, b200_cand *o
     r.mv_row = (short)(c.x + (short)(8 * o.x));
     r.mv_col = (short)(c.y + (short)(8 * o.y));
     (first ? out1 : out2)[i] = r;
+  }
+}
+
+// offs[i] = eob[0] + ... + eob[i - 1], offs[n] = total: one CTA walks the blocks 1024 at a time (a frame has
+// a few thousand transform blocks; the scan is a few microseconds)
+__global__ void __launch_bounds__(1024) eob_scan_kernel(const uint16_t *eob, uint32_t *offs, size_t n) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (size_t base = 0; base < n; base += blockDim.x) {
+    const size_t i = base + threadIdx.x;
+    const uint32_t v = i < n ? eob[i] : 0u;
+    uint32_t x = v;  // inclusive scan inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the warp totals
+      const uint32_t w = s_warp[lane];
+      uint32_t z = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
+        if (lane >= o) z += y;
+      }
+      s_warp[lane] = z - w;
+    }
+    __syncthreads();
+    const uint32_t excl = s_carry + s_warp[warp] + x - v;
+    if (i < n) offs[i] = excl;
+    __syncthreads();  // every thread has read s_carry and s_warp
+    if (threadIdx.x == blockDim.x - 1) s_carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offs[n] = s_carry;
+}
+
+// packed[offs[b] + k] = q[b * coded + scan[k]] for k < eob[b]: a warp per block
+template <typename CoefT>
+__global__ void __launch_bounds__(256) pack_gather_kernel(const CoefT *q, const uint16_t *eob, const uint32_t *offs,
+                                                          const uint16_t *scan, int coded, size_t n, CoefT *packed) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+  for (size_t b = warp0; b < n; b += nwarps) {
+    const int e = eob[b];
+    const CoefT *src = q + b * (size_t)coded;
+    CoefT *dst = packed + offs[b];
+    for (int k = lane; k < e; k += 32) dst[k] = src[scan[k]];
   }
 }
 
@@ -132,6 +191,10 @@ extern "C" int b200_frame_pipe_create(b200_ctx *ctx, const b200_frame_pipe_cfg *
     if (quant) p->d_q = p->d_cout; else p->d_coef = p->d_cout;
     p->d_eob = ob ? (uint16_t *)((uint8_t *)p->d_cout + (quant ? p->q_bytes : p->coef_bytes)) : nullptr;
     p->d_dist = ob ? (uint64_t *)((uint8_t *)p->d_eob + b200_align_up(nb * 2, 8)) : nullptr;
+    if (quant) {
+      p->d_pack_offs = (uint32_t *)c.take((nb + 1) * 4);
+      p->d_packed = c.take(p->q_bytes);
+    }
     if (pass == 0) {
       const cudaError_t e = cudaMalloc(&p->dbase, c.used + 256);
       if (e != cudaSuccess) {
@@ -154,6 +217,8 @@ extern "C" int b200_frame_pipe_create(b200_ctx *ctx, const b200_frame_pipe_cfg *
         cudaDeviceSynchronize() != cudaSuccess)
       st = b200_fail(ctx, B200_ERR_CUDA, "b200_frame_pipe_create: descriptor upload failed");
   }
+  if (!st && p->q_bytes && cudaHostAlloc((void **)&p->h_total, 8, cudaHostAllocDefault) != cudaSuccess)
+    st = b200_fail(ctx, B200_ERR_CUDA, "b200_frame_pipe_create: pinned scalar");
   if (st) {
     b200_frame_pipe_destroy(p);
     return st;
@@ -169,6 +234,7 @@ extern "C" void b200_frame_pipe_destroy(b200_frame_pipe *p) {
   for (auto &pl : p->planes)
     if (pl.alloc) cudaFree(pl.alloc);
   if (p->dbase) cudaFree(p->dbase);
+  if (p->h_total) cudaFreeHost(p->h_total);
   delete p;
 }
 
@@ -189,7 +255,9 @@ extern "C" int b200_frame_pipe_push(b200_frame_pipe *p, const void *frame, ptrdi
   const int nxt = p->cur < 0 ? 0 : p->cur ^ 1;
   const bool first = p->cur < 0;
   const size_t row_bytes = (size_t)cfg.width * cfg.bpp;
-  B200_REQUIRE(ctx, first || ((ns == 0 || sad_offsets) && (nt == 0 || satd_offsets)), "NULL candidate offsets");
+  const bool resident = p->lists_resident && !sad_offsets && !satd_offsets && !centers;
+  B200_REQUIRE(ctx, first || resident || ((ns == 0 || sad_offsets) && (nt == 0 || satd_offsets)),
+               "NULL candidate offsets (and no resident lists: b200_frame_pipe_set_lists)");
   const uint8_t *fend = (const uint8_t *)frame + p->frame_bytes;
   const bool dense = (size_t)frame_stride_bytes == row_bytes;
   size_t one = 0;  // bytes covered by the first (possibly only) copy
@@ -214,12 +282,15 @@ extern "C" int b200_frame_pipe_push(b200_frame_pipe *p, const void *frame, ptrdi
     if (!ctx->async_batch) B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return B200_OK;
   }
-  if (ns && one < p->frame_bytes + ns * 2)
-    B200_CUDA(ctx, cudaMemcpyAsync(p->d_o8_sad, sad_offsets, ns * 2, cudaMemcpyHostToDevice, ctx->stream));
-  if (nt && one < p->frame_bytes + ns * 2 + nt * 2)
-    B200_CUDA(ctx, cudaMemcpyAsync(p->d_o8_satd, satd_offsets, nt * 2, cudaMemcpyHostToDevice, ctx->stream));
-  if (centers && one < p->frame_bytes + ns * 2 + nt * 2 + nb * 4)
-    B200_CUDA(ctx, cudaMemcpyAsync(p->d_centers, centers, nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (!resident) {
+    if (ns && one < p->frame_bytes + ns * 2)
+      B200_CUDA(ctx, cudaMemcpyAsync(p->d_o8_sad, sad_offsets, ns * 2, cudaMemcpyHostToDevice, ctx->stream));
+    if (nt && one < p->frame_bytes + ns * 2 + nt * 2)
+      B200_CUDA(ctx, cudaMemcpyAsync(p->d_o8_satd, satd_offsets, nt * 2, cudaMemcpyHostToDevice, ctx->stream));
+    if (centers && one < p->frame_bytes + ns * 2 + nt * 2 + nb * 4)
+      B200_CUDA(ctx, cudaMemcpyAsync(p->d_centers, centers, nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    p->lists_resident = false;  // per-push lists replace whatever was resident
+  }
   const b200_plane *cur = &p->planes[nxt], *ref = &p->planes[nxt ^ 1];
   b200_me_params mp{};
   mp.w = cfg.block_w, mp.h = cfg.block_h;
@@ -228,7 +299,7 @@ extern "C" int b200_frame_pipe_push(b200_frame_pipe *p, const void *frame, ptrdi
   mp.lambda = cfg.lambda;
   mp.bit_depth = cfg.bit_depth;
   mp.window_hint_px = cfg.window_hint_px;
-  if (ns + nt) {
+  if ((ns + nt) && !resident) {  // (resident lists were expanded once, by b200_frame_pipe_set_lists)
     expand_offsets_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(
         (const char2 *)p->d_o8_sad, cfg.sad_per_block, p->d_cand_sad, (const char2 *)p->d_o8_satd, cfg.satd_per_block,
         p->d_cand_satd, centers ? (const short2 *)p->d_centers : nullptr, nb);
@@ -283,5 +354,86 @@ extern "C" int b200_frame_pipe_push(b200_frame_pipe *p, const void *frame, ptrdi
   if (quant && eob) B200_CUDA(ctx, cudaMemcpyAsync(eob, p->d_eob, nb * 2, cudaMemcpyDeviceToHost, ctx->stream));
   if (quant && tx_dist) B200_CUDA(ctx, cudaMemcpyAsync(tx_dist, p->d_dist, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (!ctx->async_batch) B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+extern "C" int b200_frame_pipe_set_lists(b200_frame_pipe *p, const int8_t *sad_offsets, const int8_t *satd_offsets,
+                                         const int16_t *centers) {
+  if (!p) return b200_fail(nullptr, B200_ERR_ARG, "b200_frame_pipe_set_lists: pipe is NULL");
+  b200_ctx *ctx = p->ctx;
+  const b200_frame_pipe_cfg &cfg = p->cfg;
+  const size_t nb = p->nblocks, ns = nb * (size_t)cfg.sad_per_block, nt = nb * (size_t)cfg.satd_per_block;
+  B200_REQUIRE(ctx, (ns == 0 || sad_offsets) && (nt == 0 || satd_offsets), "NULL candidate offsets");
+  B200_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ns) B200_CUDA(ctx, cudaMemcpyAsync(p->d_o8_sad, sad_offsets, ns * 2, cudaMemcpyHostToDevice, ctx->stream));
+  if (nt) B200_CUDA(ctx, cudaMemcpyAsync(p->d_o8_satd, satd_offsets, nt * 2, cudaMemcpyHostToDevice, ctx->stream));
+  if (centers) B200_CUDA(ctx, cudaMemcpyAsync(p->d_centers, centers, nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (ns + nt) {
+    expand_offsets_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(
+        (const char2 *)p->d_o8_sad, cfg.sad_per_block, p->d_cand_sad, (const char2 *)p->d_o8_satd, cfg.satd_per_block,
+        p->d_cand_satd, centers ? (const short2 *)p->d_centers : nullptr, nb);
+    B200_LAUNCH_CHECK(ctx);
+  }
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host lists may be reused at once
+  p->lists_resident = true;
+  p->centers_resident = centers != nullptr;
+  return B200_OK;
+}
+
+extern "C" int b200_frame_pipe_push_packed(b200_frame_pipe *p, const void *frame, ptrdiff_t frame_stride_bytes,
+                                           b200_me_result *best_sad, b200_me_result *best_satd, uint16_t *eob,
+                                           uint64_t *tx_dist, void *packed, size_t packed_capacity,
+                                           size_t *packed_count) {
+  if (!p) return b200_fail(nullptr, B200_ERR_ARG, "b200_frame_pipe_push_packed: pipe is NULL");
+  b200_ctx *ctx = p->ctx;
+  const b200_frame_pipe_cfg &cfg = p->cfg;
+  B200_REQUIRE(ctx, p->q_bytes != 0, "packed output needs a quantizing pipe (tx_size >= 0 and ac_quant != 0)");
+  B200_REQUIRE(ctx, p->lists_resident, "packed pushes use resident lists: call b200_frame_pipe_set_lists first");
+  B200_REQUIRE(ctx, packed_count != nullptr && (packed != nullptr || packed_capacity == 0), "NULL packed buffer");
+  const bool first = p->cur < 0;
+  const int was_async = ctx->async_batch;
+  // the frame, the kernels up to the quantize chain; nothing comes back yet
+  ctx->async_batch = 1;
+  const int st = b200_frame_pipe_push(p, frame, frame_stride_bytes, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                      nullptr, nullptr, nullptr);
+  ctx->async_batch = was_async;
+  if (st) return st;
+  *packed_count = 0;
+  if (first) {
+    if (!was_async) B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+  }
+  const size_t nb = p->nblocks;
+  const int coded = b200_coded_tx_area(cfg.tx_size);
+  const uint16_t *d_scan = nullptr;
+  if (int s2 = b200_scan_table_internal(ctx, cfg.tx_size, cfg.tx_type, &d_scan)) return s2;
+  eob_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p->d_eob, p->d_pack_offs, nb);
+  B200_LAUNCH_CHECK(ctx);
+  const int grid = (int)std::min<size_t>((nb + 7) / 8, (size_t)ctx->num_sms * 8);
+  if (cfg.bpp == 1)
+    pack_gather_kernel<int16_t><<<grid, 256, 0, ctx->stream>>>((const int16_t *)p->d_q, p->d_eob, p->d_pack_offs, d_scan,
+                                                               coded, nb, (int16_t *)p->d_packed);
+  else
+    pack_gather_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>((const int32_t *)p->d_q, p->d_eob, p->d_pack_offs, d_scan,
+                                                               coded, nb, (int32_t *)p->d_packed);
+  B200_LAUNCH_CHECK(ctx);
+  // the small fixed-size results and the total
+  const size_t rb = nb * sizeof(b200_me_result);
+  if (best_sad && best_satd == best_sad + nb) {
+    B200_CUDA(ctx, cudaMemcpyAsync(best_sad, p->d_best_sad, 2 * rb, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    if (best_sad) B200_CUDA(ctx, cudaMemcpyAsync(best_sad, p->d_best_sad, rb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (best_satd) B200_CUDA(ctx, cudaMemcpyAsync(best_satd, p->d_best_satd, rb, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (eob) B200_CUDA(ctx, cudaMemcpyAsync(eob, p->d_eob, nb * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  if (tx_dist) B200_CUDA(ctx, cudaMemcpyAsync(tx_dist, p->d_dist, nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  B200_CUDA(ctx, cudaMemcpyAsync(p->h_total, p->d_pack_offs + nb, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the size of the packed copy is a result
+  const size_t total = *p->h_total;
+  *packed_count = total;
+  const size_t ncopy = std::min(total, packed_capacity);
+  if (ncopy)
+    B200_CUDA(ctx, cudaMemcpyAsync(packed, p->d_packed, ncopy * (cfg.bpp == 1 ? 2 : 4), cudaMemcpyDeviceToHost, ctx->stream));
+  if (!was_async) B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return B200_OK;
 }

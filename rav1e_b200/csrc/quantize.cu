@@ -19,6 +19,12 @@ extern "C" int b200_coded_tx_area(int tx_size) {
   return tx_size >= 0 && tx_size < 19 ? std::min(kQtxW[tx_size], 32) * std::min(kQtxH[tx_size], 32) : 0;
 }
 
+int b200_scan_table_internal(b200_ctx *ctx, int tx_size, int tx_type, const uint16_t **d_scan) {
+  const uint16_t *iscan = nullptr;
+  const int kind = tx_type < 10 ? 0 : ((tx_type & 1) ? 2 : 1);  // as quant_setup
+  return scan_tables(ctx, tx_size, kind, d_scan, &iscan);
+}
+
 extern "C" int b200_quantize_dev(b200_ctx *ctx, const void *d_coeffs, size_t nblocks, int tx_size,
                                  int tx_type, uint32_t dc_quant, uint32_t ac_quant, int is_intra,
                                  int coeff_is_i32, void *d_qcoeffs, void *d_rcoeffs, uint16_t *d_eob,
