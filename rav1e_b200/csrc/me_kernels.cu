@@ -568,14 +568,9 @@ __global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 
     uint32_t g0 = 0, pb0 = a.pr.block_begin;
     if (a.pr.n > 1) {
       // first pair whose group_end exceeds grp: one lane per pair, a ballot instead of a search
-#ifdef B200_V_OLD_LOOKUP
-      pi = pair_lookup(a.pr.group_end, a.pr.n, (uint32_t)grp);
-      if (pi) g0 = a.pr.group_end[pi - 1], pb0 = a.pr.block_end[pi - 1];
-#else
       const uint32_t e = lane < a.pr.n ? s_gend[lane] : 0xffffffffu;
       pi = __ffs(__ballot_sync(0xffffffffu, (uint32_t)grp < e)) - 1;
       if (pi) g0 = s_gend[pi - 1], pb0 = a.pr.block_end[pi - 1];
-#endif
     }
     const PlaneView cur = a.pr.cur[pi], ref = a.pr.ref[pi];
     const size_t gb0 = pb0 + (grp - g0) * G, gb1 = min(gb0 + (size_t)G, (size_t)a.pr.block_end[pi]);
@@ -620,18 +615,6 @@ __global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 
       pre.mv_col = 0;
       if (hinted && lo + threadIdx.x < hi) pre = a.cands[lo + threadIdx.x];
       if (hinted) {
-#ifdef B200_V_OLD_EXTENT
-        if (threadIdx.x == 0) {
-          int x0 = INT_MAX, x1 = INT_MIN, y0 = INT_MAX, y1 = INT_MIN;
-          for (int k = 0; k < nb; k++) {
-            const MvRange r = s_rng[k];
-            x0 = min(x0, s_blk[k].x + max(-a.hint_px, r.x_min / 8));
-            x1 = max(x1, s_blk[k].x + min(a.hint_px, r.x_max / 8));
-            y0 = min(y0, s_blk[k].y + max(-a.hint_px, r.y_min / 8));
-            y1 = max(y1, s_blk[k].y + min(a.hint_px, r.y_max / 8));
-          }
-        {
-#else
         if (threadIdx.x < 32) {  // warp 0: a lane per block, never beyond what get_mv_range allows (plane padding)
           int x0 = INT_MAX, x1 = INT_MIN, y0 = INT_MAX, y1 = INT_MIN;
           if (lane < nb) {
@@ -645,28 +628,27 @@ __global__ void __launch_bounds__(SATD ? 128 : B200_SAD_THREADS, (!SATD && W >= 
           x1 = __reduce_max_sync(0xffffffffu, x1);
           y0 = __reduce_min_sync(0xffffffffu, y0);
           y1 = __reduce_max_sync(0xffffffffu, y1);
-        if (lane == 0) {
-#endif
-          s_box[0] = x0;
-          s_box[1] = x1;
-          s_box[2] = y0;
-          s_box[3] = y1;
-          // TMA: the fixed box must cover the extent, and the set must be dense enough to stage
-          int by_tma = 0;
-          if (tma_on) {
-            const bool dense0 = (long long)(hi - lo) * (W * H) * 2 >= (long long)tm.box_h * tm.box_w;
-            // the box starts on a 16-byte column of the tensor (measured: any other x faults)
-            const int cx = (x0 + tm.ox[pi]) & ~15;
-            const int wx = cx - tm.ox[pi];
-            by_tma = dense0 && x1 - wx + W + 4 <= tm.box_w && y1 - y0 + H <= tm.box_h;
-            if (by_tma) {
-              tma_load_window(smem_u32(win), &tm.map[pi], cx >> 2, y0 + tm.oy[pi], mbar,
-                              (uint32_t)(tm.box_w * tm.box_h));
-              s_box[0] = wx;
+          if (lane == 0) {
+            s_box[0] = x0;
+            s_box[1] = x1;
+            s_box[2] = y0;
+            s_box[3] = y1;
+            // TMA: the fixed box must cover the extent, and the set must be dense enough to stage
+            int by_tma = 0;
+            if (tma_on) {
+              const bool dense0 = (long long)(hi - lo) * (W * H) * 2 >= (long long)tm.box_h * tm.box_w;
+              // the box starts on a 16-byte column of the tensor (measured: any other x faults)
+              const int cx = (x0 + tm.ox[pi]) & ~15;
+              const int wx = cx - tm.ox[pi];
+              by_tma = dense0 && x1 - wx + W + 4 <= tm.box_w && y1 - y0 + H <= tm.box_h;
+              if (by_tma) {
+                tma_load_window(smem_u32(win), &tm.map[pi], cx >> 2, y0 + tm.oy[pi], mbar,
+                                (uint32_t)(tm.box_w * tm.box_h));
+                s_box[0] = wx;
+              }
             }
+            s_box[4] = by_tma;
           }
-          s_box[4] = by_tma;
-        }
         }
       } else {
         int bx0 = INT_MAX, bx1 = INT_MIN, by0 = INT_MAX, by1 = INT_MIN;
