@@ -104,3 +104,63 @@ def test_get_mv_params_chroma_and_negative_vectors():
     assert [o.value for o in out] == [-2, 3, (-13 * 2) & 15, (27 * 2) & 15]
     L.orc_get_mv_params(-13, 27, 1, 1, *[C.byref(o) for o in out])
     assert [o.value for o in out] == [-1, 1, -13 & 15, 27 & 15]
+
+
+def test_filter_tables_have_the_normative_structure():
+    """Structure every AV1 interpolation kernel has (spec section 7.11.3.4, Subpel_Filters): position 0 is the
+    identity, position 16 - f is position f mirrored (the kernel sits between taps 3 and 4), every row sums to 128,
+    the 4-tap variants (block dimension <= 4) have zero outer taps, BILINEAR is (128 - 8 f, 8 f)."""
+    L = O.lib()
+    f, g = (C.c_int32 * 8)(), (C.c_int32 * 8)()
+    for mode in range(4):
+        for length in (4, 8):
+            L.orc_get_filter(mode, 0, length, f)
+            assert list(f) == [0, 0, 0, 128, 0, 0, 0, 0]
+            for frac in range(1, 16):
+                L.orc_get_filter(mode, frac, length, f)
+                L.orc_get_filter(mode, 16 - frac, length, g)
+                assert list(f) == list(g)[::-1], (mode, length, frac)
+                if length == 4 and mode != 3:
+                    assert f[0] == f[1] == f[6] == f[7] == 0
+    for frac in range(16):
+        L.orc_get_filter(3, frac, 8, f)
+        assert list(f) == [0, 0, 0, 128 - 8 * frac, 8 * frac, 0, 0, 0]
+
+
+@pytest.mark.parametrize("dtype,bd", [(np.uint8, 8), (np.uint16, 10), (np.uint16, 12)])
+def test_put_equals_the_specification_two_pass_form(dtype, bd):
+    """The AV1 specification (7.11.3.4 block inter prediction, non-compound) states ONE form for every sub-pel
+    position: a horizontal pass rounded by InterRound0 (3; 5 at 12 bit) into an intermediate of h + 7 rows, a vertical
+    pass rounded by InterRound1 (11; 9 at 12 bit), Clip1 - with the identity kernel at position 0.  The reference's
+    four special-cased paths (mc.rs:264-352) must all equal it."""
+    p = make_plane(dtype, bd, seed=40 + bd)
+    L = O.lib()
+    r0, r1 = (5, 9) if bd == 12 else (3, 11)
+    maxv = (1 << bd) - 1
+    img = p.data.astype(np.int64)
+    rnd = lambda v, b: (v + (1 << (b - 1))) >> b
+    fx, fy = (C.c_int32 * 8)(), (C.c_int32 * 8)()
+    rng = np.random.default_rng(bd)
+    for w, h in ((8, 8), (4, 16), (16, 4)):
+        for _ in range(6):
+            cf, rf = (int(v) for v in rng.integers(0, 16, 2))
+            if rng.integers(0, 3) == 0:
+                cf = 0
+            if rng.integers(0, 3) == 0:
+                rf = 0
+            mx, my = (int(v) for v in rng.integers(0, 4, 2))
+            x0, y0 = (int(v) for v in rng.integers(4, 40, 2))
+            L.orc_get_filter(mx, cf, w, fx)
+            L.orc_get_filter(my, rf, h, fy)
+            kx, ky = np.array(list(fx), np.int64), np.array(list(fy), np.int64)
+            inter = np.zeros((h + 7, w), np.int64)
+            for r in range(h + 7):
+                for c in range(w):
+                    py, px = p.pad + y0 + r - 3, p.pad + x0 + c - 3
+                    inter[r, c] = rnd(int((kx * img[py, px:px + 8]).sum()), r0)
+            want = np.zeros((h, w), np.int64)
+            for r in range(h):
+                for c in range(w):
+                    want[r, c] = min(max(rnd(int((ky * inter[r:r + 8, c]).sum()), r1), 0), maxv)
+            got = O.put_8tap(p, x0, y0, w, h, cf, rf, mx, my, bd)
+            np.testing.assert_array_equal(got, want, err_msg=f"{w}x{h} frac ({cf},{rf}) modes ({mx},{my})")
