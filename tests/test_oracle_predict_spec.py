@@ -201,3 +201,109 @@ def test_edge_filter_length_is_clipped_at_the_plane_border():
             for delta in (-6, 3):
                 for ief in (0, 1):
                     run_case(rng, w, h, 8, mode, delta, ief, True, x=64, y=48, plane_w=64 + w // 2, plane_h=48 + h // 4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# non-directional predictors beyond the reference's 4x4 KATs (predict.rs:1514-1566): every block size, 8 / 10 / 12 bit,
+# against the specification's DC (7.11.2.5), Paeth (7.11.2.2) and smooth (7.11.2.6) processes.
+SM_WEIGHTS = {
+    4: [255, 149, 85, 64],
+    8: [255, 197, 146, 105, 73, 50, 37, 32],
+    16: [255, 225, 196, 170, 145, 123, 102, 84, 68, 54, 43, 33, 26, 20, 17, 16],
+    32: [255, 240, 225, 210, 196, 182, 169, 157, 145, 133, 122, 111, 101, 92, 83, 74, 66, 59, 52, 45, 39, 34, 29, 25,
+         21, 17, 14, 12, 10, 9, 8, 8],
+    64: [255, 248, 240, 233, 225, 218, 210, 203, 196, 189, 182, 176, 169, 163, 156, 150, 144, 138, 133, 127, 121, 116,
+         111, 106, 101, 96, 91, 86, 82, 77, 73, 69, 65, 61, 57, 54, 50, 47, 44, 41, 38, 35, 32, 29, 27, 25, 22, 20, 18,
+         16, 15, 13, 12, 10, 9, 8, 7, 6, 6, 5, 5, 4, 4, 4],
+}
+ALL_SIZES = [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (4, 8), (8, 4), (8, 16), (16, 8), (16, 32), (32, 16), (32, 64),
+             (64, 32), (4, 16), (16, 4), (8, 32), (32, 8), (16, 64), (64, 16)]
+
+
+def spec_nondirectional(mode, variant, above, left, tl, w, h, bd):
+    a, l = [int(v) for v in above], [int(v) for v in left]
+    out = np.zeros((h, w), np.int64)
+    if mode == "DC_PRED":
+        if variant == 3:
+            v = (sum(l[:h]) + sum(a[:w]) + ((w + h) >> 1)) // (w + h)
+        elif variant == 1:
+            v = (sum(l[:h]) + (h >> 1)) >> (h.bit_length() - 1)
+        elif variant == 2:
+            v = (sum(a[:w]) + (w >> 1)) >> (w.bit_length() - 1)
+        else:
+            v = 1 << (bd - 1)
+        out[:] = v
+        return out
+    wv, wh = SM_WEIGHTS[h], SM_WEIGHTS[w]
+    for i in range(h):
+        for j in range(w):
+            if mode == "PAETH_PRED":
+                base = a[j] + l[i] - tl
+                p_left, p_top, p_tl = abs(base - l[i]), abs(base - a[j]), abs(base - tl)
+                out[i, j] = l[i] if (p_left <= p_top and p_left <= p_tl) else a[j] if p_top <= p_tl else tl
+            elif mode == "SMOOTH_PRED":
+                s = wv[i] * a[j] + (256 - wv[i]) * l[h - 1] + wh[j] * l[i] + (256 - wh[j]) * a[w - 1]
+                out[i, j] = (s + 256) >> 9
+            elif mode == "SMOOTH_V_PRED":
+                out[i, j] = (wv[i] * a[j] + (256 - wv[i]) * l[h - 1] + 128) >> 8
+            elif mode == "SMOOTH_H_PRED":
+                out[i, j] = (wh[j] * l[i] + (256 - wh[j]) * a[w - 1] + 128) >> 8
+            elif mode == "V_PRED":
+                out[i, j] = a[j]
+            elif mode == "H_PRED":
+                out[i, j] = l[i]
+    return out
+
+
+@pytest.mark.parametrize("bd", [8, 10, 12])
+def test_nondirectional_predictors_equal_the_specification_at_every_size(bd):
+    rng = np.random.default_rng(300 + bd)
+    dtype = np.uint8 if bd == 8 else np.uint16
+    for w, h in ALL_SIZES:
+        for trial in range(3):
+            if trial == 0:
+                e = rng.integers(0, 1 << bd, O.EDGE_LEN)
+            elif trial == 1:   # extremes: saturation of the smooth sums, Paeth ties
+                e = rng.choice([0, (1 << bd) - 1], O.EDGE_LEN)
+            else:
+                e = np.clip((1 << (bd - 1)) + np.cumsum(rng.integers(-3, 4, O.EDGE_LEN)), 0, (1 << bd) - 1)
+            e = e.astype(dtype)
+            above, left, tl = e[129:129 + w], e[127::-1][:h], int(e[128])
+            for mode in ("DC_PRED", "PAETH_PRED", "SMOOTH_PRED", "SMOOTH_V_PRED", "SMOOTH_H_PRED", "V_PRED", "H_PRED"):
+                for variant in ((0, 1, 2, 3) if mode == "DC_PRED" else (3,)):
+                    angle = {"V_PRED": 90, "H_PRED": 180}.get(mode, 0)
+                    got = O.predict_intra(M[mode], variant, e, w, h, bd, angle=angle, left_len=h, above_len=w)
+                    want = spec_nondirectional(mode, variant, above, left, tl, w, h, bd)
+                    np.testing.assert_array_equal(got, want, err_msg=f"{mode} variant {variant} {w}x{h} bd {bd}")
+
+
+@pytest.mark.parametrize("xdec,ydec", [(1, 1), (1, 0), (0, 0)])
+@pytest.mark.parametrize("bd", [8, 10])
+def test_cfl_luma_subsampling_equals_the_specification(xdec, ydec, bd):
+    """7.11.5 (predict chroma from luma): L[i][j] = (sum of the co-located luma samples) << (3 - subX - subY) with the
+    luma position clamped to the last one inside the frame (MaxLumaW / MaxLumaH), lumaAvg = Round2(total,
+    log2W + log2H), ac = L - lumaAvg; every chroma block size the mode allows, with and without the clamp."""
+    rng = np.random.default_rng(17 * bd + 2 * xdec + ydec)
+    dtype = np.uint8 if bd == 8 else np.uint16
+    for bw, bh in ((4, 4), (8, 8), (16, 16), (32, 32), (4, 8), (8, 4), (8, 16), (16, 8), (16, 32), (32, 16), (4, 16),
+                   (16, 4), (8, 32), (32, 8)):
+        for w_pad, h_pad in ((0, 0), (1, 0), (0, 1), (bw // 8, bh // 8)):
+            if 4 * w_pad >= bw or 4 * h_pad >= bh:
+                continue
+            luma = rng.integers(0, 1 << bd, (bh << ydec, bw << xdec)).astype(dtype)
+            got = O.pred_cfl_ac(luma, bw, bh, w_pad, h_pad, xdec, ydec).reshape(bh, bw).astype(np.int64)
+            max_w = max((bw - 4 * w_pad) << xdec, 8)
+            max_h = max((bh - 4 * h_pad) << ydec, 8)
+            L = np.zeros((bh, bw), np.int64)
+            for i in range(bh):
+                ly = min(i << ydec, max_h - (1 << ydec))
+                for j in range(bw):
+                    lx = min(j << xdec, max_w - (1 << xdec))
+                    t = 0
+                    for dy in range(1 << ydec):
+                        for dx in range(1 << xdec):
+                            t += int(luma[ly + dy, lx + dx])
+                    L[i, j] = t << (3 - xdec - ydec)
+            shift = (bw.bit_length() - 1) + (bh.bit_length() - 1)
+            avg = (int(L.sum()) + (1 << (shift - 1))) >> shift
+            np.testing.assert_array_equal(got, L - avg, err_msg=f"{bw}x{bh} pad ({w_pad},{h_pad})")
