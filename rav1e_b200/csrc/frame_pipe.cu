@@ -16,6 +16,9 @@
 //     (centre + 8 * offset, i16 wrapping like the reference's MotionVector arithmetic);
 //   * the winners of the SAD list feed the fused residual + forward transform (+ quantize chain) on the
 //     device; only results cross PCIe: winners, coefficients (or qcoeffs + eob + tx-domain distortion).
+//   * b200_frame_pipe_set_lists keeps the candidate lists on the device (a search pattern is an encoder
+//     constant): a push then moves only the frame; b200_frame_pipe_push_packed returns, instead of the dense
+//     coefficient block, what the entropy coder reads: coeffs[scan[0 .. eob)] of every block, packed.
 // Everything is enqueued on the context's stream; with b200_ctx_set_async the call returns at once and
 // the host buffers are valid after b200_ctx_synchronize, so frames pipeline over several contexts.
 #include <cuda_runtime.h>
