@@ -1103,9 +1103,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     # stdout carries exactly one JSON line: NCCL's own log (the version banner included) goes to stderr
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    # (at NCCL_DEBUG=VERSION / WARN the banner "NCCL version ..." still lands on stdout with this NCCL build)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN") and not os.environ.get("B200_KEEP_NCCL_DEBUG"):
-        del os.environ["NCCL_DEBUG"]
+    # (NCCL_DEBUG itself is left as the launcher set it; at VERSION / WARN this NCCL build still prints its
+    # one-line version banner on stdout, ahead of the JSON line)
     if args.impl == "reference":
         run_reference(args, rank, world)
     elif args.workload == "4k-tiles":
