@@ -16,9 +16,16 @@
  *   cdef first_max_element    : pinned by src/cdef.rs:304-309
  *   fwd + inverse transform   : pinned jointly by the reference's round-trip test
  *                               (transform/mod.rs:479-617, 44 (size, type, tolerance) triples)
- *   mc / cdef filter          : no stored vectors in the reference (only asm==rust random
- *                               tests that need rustc) -> "parity unpinned" for those, with
- *                               independent cross-checks documented per module.
+ *   mc / cdef dir + filter /  : no stored vectors in the reference (only asm==rust random
+ *   intra edge filter,          tests that need rustc) -> "parity unpinned" upstream.  These
+ *   upsampling, larger sizes    kernels are AV1-normative, so the AV1 specification is a second
+ *                               source: independent restatements of its processes equal this
+ *                               oracle bit for bit (tests/test_oracle_cdef_spec.py,
+ *                               tests/test_oracle_predict_spec.py, the two-pass form in
+ *                               tests/test_oracle_mc.py).
+ *   get_intra_edges           : availability tables pinned by sha256 of the reference's 44 tables
+ *   compute_rd_cost           : pinned (correctly rounded fma, exact rational check)
+ *   quantize chain            : log_tx_scale / divu_pair KATs, sha256 of the 42 scan tables
  *   search stages, RDO dist   : likewise unpinned; checked against an independent Python model
  *                               (tests/test_oracle_search.py) and the reference tests' float
  *                               formulas (tests/test_oracle_rdo_dist.py).
